@@ -1,0 +1,144 @@
+"""oracle/taylor_numpy.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Second, independently written transcription of the reference CPU propagator in
+plain numpy (complex128).  It exists to cross-validate oracle/elhl_oracle.cpp
+("a second, independently written numpy transcription to
+~1e-13") and is only usable at small N.  It deliberately shares no code with
+the C++ restatement: matrix products go through numpy's BLAS, the inverse
+through LAPACK dsytrf/dsytri as the reference does (GPU_Interface.cpp:936-949).
+
+References (relative to /root/reference): Taylor.f:35-303, ElHl_Chebyshev.f:174-276,
+Matrix_math.f:125-198, data_output.f:242-263, hamiltonians.f:33-63.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+ORDER = 25            # Taylor.f:20
+ERROR = 1.0e-8        # Taylor.f:21
+NORM_ERROR = 1.0e-8   # Taylor.f:22
+H_BAR = 6.58264e-4    # constants_m.f:23
+
+
+def coefficient(tau: float, k_max: int = ORDER) -> np.ndarray:
+    """Taylor.f:224-239 (index 0 here is Fortran's c(1))."""
+    c = np.zeros(k_max, dtype=np.complex128)
+    c[0] = 1.0
+    for k in range(1, k_max):
+        c[k] = -1j * c[k - 1] * (tau / k)
+    return c
+
+
+def _is_converged(a, b, tol):
+    """Taylor.f:290-303."""
+    return not np.any(np.abs(a - b) > tol)
+
+
+def convergence(Hp, bra, ket, tau, norm_ref, log=None):
+    """Taylor.f:132-219.  Returns (ok, bra, ket, C, k_ref, k_exit); k are 1-based."""
+    C = coefficient(tau)
+    small = np.nonzero(np.abs(C[1:]) < 1.0e-16)[0]
+    k_max = int(small[0]) + 2 if small.size else ORDER          # Taylor.f:165-171
+    term_b = bra.copy(); term_k = ket.copy()
+    old_b = bra.copy(); old_k = ket.copy()
+    HT = Hp.T
+    for k in range(2, k_max + 1):                                # Taylor.f:182
+        r = C[k - 1] / C[k - 2]
+        term_b = r * (HT @ term_b)                               # bra_x_op: dzgemv('T')
+        term_k = r * (Hp @ term_k)                               # op_x_ket: dzgemv('N')
+        if log is not None:
+            log["matvec_pairs"] = log.get("matvec_pairs", 0) + 1
+        new_b = old_b + term_b
+        new_k = old_k + term_k
+        if _is_converged(new_b, old_b, ERROR) and _is_converged(new_k, old_k, ERROR):
+            norm_tmp = abs(np.vdot(new_b, new_k))                # dotc: conj(first) . second
+            if abs(norm_tmp - norm_ref) < NORM_ERROR:
+                return True, new_b, new_k, C, k_max, k
+        old_b, old_k = new_b, new_k
+    return False, bra, ket, C, k_max, 0
+
+
+def propagation(Hp, bra, ket, t_init, t_max, tau, log=None):
+    """Taylor.f:35-127.  Returns (bra, ket, tau, save_tau)."""
+    if log is None:
+        log = {}
+    log.setdefault("events", [])
+    norm_ref = abs(np.vdot(bra, ket))                            # Taylor.f:62
+    while True:                                                  # Taylor.f:65-70
+        ok, bra, ket, C, k_ref, k_exit = convergence(Hp, bra, ket, tau, norm_ref, log)
+        log["events"].append((1, k_exit, int(ok), tau))
+        if ok:
+            break
+        tau *= 0.9
+    save_tau = tau
+    t = t_init + tau * H_BAR
+    if t_max - t < tau * H_BAR:                                  # Taylor.f:75-78
+        tau = (t_max - t) / H_BAR
+        C = coefficient(tau)
+    HT = Hp.T
+    while t < t_max:                                             # Taylor.f:81
+        term_b = bra.copy(); term_k = ket.copy()
+        sum_b = bra.copy(); sum_k = ket.copy()
+        for k in range(2, k_ref + 1):
+            r = C[k - 1] / C[k - 2]
+            term_b = r * (HT @ term_b)
+            term_k = r * (Hp @ term_k)
+            log["matvec_pairs"] = log.get("matvec_pairs", 0) + 1
+            sum_b = sum_b + term_b
+            sum_k = sum_k + term_k
+        norm_test = abs(np.vdot(sum_b, sum_k))
+        if abs(norm_test - norm_ref) < NORM_ERROR:               # Taylor.f:104
+            bra, ket = sum_b, sum_k
+            log["events"].append((2, k_ref, 1, tau))
+        else:
+            log["events"].append((2, k_ref, 0, tau))
+            ok = False
+            while not ok:                                        # Taylor.f:108-113
+                tau *= 0.975
+                ok, bra, ket, C, k_ref, k_exit = convergence(Hp, bra, ket, tau, norm_ref, log)
+                log["events"].append((1, k_exit, int(ok), tau))
+        t += tau * H_BAR
+        if t_max - t < tau * H_BAR:                              # Taylor.f:118-121
+            tau = (t_max - t) / H_BAR
+            C = coefficient(tau)
+    return bra, ket, tau, save_tau
+
+
+def sy_invert_full(S):
+    """Matrix_math.f:183-198 + GPU_Interface.cpp:936-949: dsytrf/dsytri('U') then mirror U->L."""
+    from scipy.linalg import lapack
+    A = np.array(S, dtype=np.float64, order="F", copy=True)
+    ldu, ipiv, info = lapack.dsytrf(A, lower=0)
+    assert info == 0
+    inv, info = lapack.dsytri(ldu, ipiv, lower=0)
+    assert info == 0
+    U = np.triu(inv)
+    return U + np.triu(inv, 1).T
+
+
+def h_prime(S, h):
+    """ElHl_Chebyshev.f:206-210: H' = S_inv * h  (dsymm 'L','U')."""
+    Sinv = sy_invert_full(S)
+    return Sinv @ h, Sinv
+
+
+def x_ij_matrix(IP, k_WH, V_shift):
+    """hamiltonians.f:33-63, vectorised over (i,j)."""
+    IP = np.asarray(IP, float); k_WH = np.asarray(k_WH, float); V = np.asarray(V_shift, float)
+    c1 = IP[:, None] - IP[None, :]
+    c2 = IP[:, None] + IP[None, :]
+    c3 = (c1 / c2) * (c1 / c2)
+    c4 = (V[:, None] + V[None, :]) * 0.5
+    kwh = (k_WH[:, None] + k_WH[None, :]) * 0.5
+    k_eff = kwh + c3 + c3 * c3 * (1.0 - kwh)
+    X = k_eff * c2 * 0.5 + c4
+    X[np.diag_indices_from(X)] = IP + V
+    return X
+
+
+def pop_slater(fragment, bra, ket, n_frag):
+    """data_output.f:242-263 over fragments; returns [frag pops..., total]."""
+    prod = bra * ket
+    out = [np.sum(prod[fragment == f]).real for f in range(n_frag)]
+    out.append(np.sum(prod).real)
+    return np.array(out)
