@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py -- el+hole series terms/s of the B200-native propagator (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--basis NB]
+
+One "step" = one 24-term el+hole series (series_init + 24 x (dual-product pass over H' + fused
+epilogue)), i.e. the work of one Convergence() call of the reference (Taylor.f:132-219) for the
+electron and the hole together.  Unit of work = one el+hole term = one pass over H' serving the
+four complex right-hand sides: 8*N^2 algorithmic bytes.
+
+N = 1: workload "synthetic EHT Hamiltonian N=16384, el+hole packets" (BASELINE config 3), H' = S^-1 h
+formed on the device from the synthetic S, h.  N > 1: N = 65536 row-sharded (BASELINE config 4).
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TERMS_PER_STEP = 24
+H_BAR = 6.58264e-4
+METRIC = "el+hole Chebyshev terms/s"
+UNIT = "terms/s"
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons DURING the timed region (NVML; nvidia-smi as a fallback)."""
+
+    def __init__(self, index=0, period=0.02):
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {}
+        if nv is not None:
+            for k in ("SwPowerCap", "HwSlowdown", "SwThermalSlowdown", "HwThermalSlowdown", "HwPowerBrakeSlowdown",
+                      "SyncBoost", "ApplicationsClocksSetting", "DisplayClockSetting"):
+                v = getattr(nv, "nvmlClocksEventReason" + k, None) or getattr(nv, "nvmlClocksThrottleReason" + k, None)
+                if v is not None:
+                    names[int(v)] = k
+        while not self._stop.is_set():
+            try:
+                if nv is not None:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, nm in names.items():
+                        if r & bit:
+                            self.reasons.add(nm)
+                else:
+                    import subprocess
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm,"
+                                          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                                          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True).stdout.strip().split(",")
+                    self.samples.append(float(out[0])); self.max_mhz = float(out[1])
+                    for nm, v in zip(("HwSlowdown", "HwThermalSlowdown", "SwThermalSlowdown", "SwPowerCap"), out[2:]):
+                        if "Active" in v and "Not" not in v:
+                            self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        self._thr = threading.Thread(target=self._loop, daemon=True)
+        self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thr.join(timeout=2.0)
+
+    def result(self):
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic(N):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(str(N))
+        except Exception:
+            return None
+    return None
+
+
+# ----------------------------------------------------------------------------------------------- workloads
+def build_single_gpu(N, device=0):
+    """Synthetic EHT S, h on the device (input generation with torch = plumbing), H' = S^-1 h formed by the
+    library (cuSOLVER potrf + potrs), packets on the host."""
+    import torch
+    from dynemol_b200 import api, synthetic as syn
+    dev = torch.device("cuda", device)
+    t0 = time.time()
+    S, h, meta = syn.make_S_h_torch(N, dev)
+    P = api.Propagator(N, device=device)
+    torch.cuda.synchronize(dev)
+    t1 = time.time()
+    P.form_hprime_device(S.data_ptr(), N, h.data_ptr(), N)         # S, h symmetric: row-major == column-major
+    t2 = time.time()
+    # packets: el on the first 64 orbitals, hole on the next 64; Psi_bra = S C, Psi_ket = C (ElHl_Chebyshev.f:126-129)
+    w = 64
+    C = np.zeros((N, 2))
+    C[0:w, 0] = np.random.default_rng(42).normal(size=w)
+    C[w:2 * w, 1] = np.random.default_rng(43).normal(size=w)
+    Ct = torch.tensor(C, device=dev)
+    SC = S @ Ct
+    nrm = torch.sqrt((Ct * SC).sum(0))
+    Ct = Ct / nrm; SC = SC / nrm
+    Psi_ket = np.asfortranarray(Ct.cpu().numpy().astype(np.complex128))
+    Psi_bra = np.asfortranarray(SC.cpu().numpy().astype(np.complex128))
+    del S, h, SC, Ct
+    torch.cuda.empty_cache()
+    return P, Psi_bra, Psi_ket, {"gen_s": t1 - t0, "form_hprime_s": t2 - t1}
+
+
+def pick_tau(N):
+    # keeps every 24-term series bounded (|r_k| * ||H'|| < 1 for k >= 2): the same regime Convergence() settles in
+    return 1.0e-4
+
+
+# ----------------------------------------------------------------------------------------------- arms
+def run_ours_single(args):
+    import torch
+    from dynemol_b200 import api
+    N = args.basis or 16384
+    P, Psi_bra, Psi_ket, build_info = build_single_gpu(N)
+    P.set_packets(Psi_bra, Psi_ket)
+    tau = pick_tau(N)
+    info = P.info()
+
+    for _ in range(max(args.warmup, 3)):
+        P.run_terms(tau, TERMS_PER_STEP)
+    torch.cuda.synchronize()
+    l0 = P.launch_count()
+    with ClockSampler(0) as cs:
+        P.sync()
+        ms, _ = P.run_terms(tau, TERMS_PER_STEP * args.steps)      # CUDA events on the launching stream, inside the library
+        P.sync()
+    launches = P.launch_count() - l0
+    clocks = cs.result()
+    n_terms = TERMS_PER_STEP * args.steps
+    value = n_terms / (ms * 1e-3)
+
+    # dominant kernel: events around every dual-product launch (separate run so the brackets do not perturb `value`)
+    ms2, kms = P.run_terms(tau, TERMS_PER_STEP * min(args.steps, 50), per_kernel=True)
+    k_launches = TERMS_PER_STEP * min(args.steps, 50)
+    alg_bytes = 8.0 * N * N
+    k_avg_s = (kms * 1e-3) / k_launches
+    peak, peak_src = measured_peak_gbs()
+    achieved = alg_bytes / k_avg_s / 1e9
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": recorded_traffic(N), "kernel": "dual_matvec_tma_kernel", "kernel_avg_us": round(k_avg_s * 1e6, 2),
+                "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "kernel_share_of_step": round(kms / ms2, 4)}
+
+    # e2e: the reference-facing call sequence with HOST buffers (propagation_gpucaller_ semantics, Taylor_gpu.cpp:295-330):
+    # H' and packets start in pinned host memory, H2D + full propagation of one nuclear step + D2H inside the timed region.
+    Hp_host = torch.empty((N, N), dtype=torch.float64, pin_memory=True)
+    Hp_np = Hp_host.numpy().T                                       # Fortran-ordered view of the pinned buffer
+    Hp_np[...] = P.download_hprime()
+    dt_e2e = args.e2e_dt
+    tau0 = dt_e2e / H_BAR
+    e2e_steps = max(1, args.e2e_steps)
+    passes = 0
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        P.upload_hprime(Hp_np)                                      # 8 N^2 bytes H2D
+        P.set_packets(Psi_bra, Psi_ket)
+        P.propagate(0.0, dt_e2e, tau0)
+        bra, ket = P.get_packets()
+        passes += P.info()["passes_last"]
+    t_e2e = time.perf_counter() - t0
+    e2e = {"value": round(passes / t_e2e, 2), "unit": UNIT,
+           "h2d_bytes_per_step": int(8 * N * N + 2 * 2 * 16 * N), "d2h_bytes_per_step": int(2 * 2 * 16 * N),
+           "call": "upload_hprime(host)+set_packets(host)+propagate(Taylor, dt=%g ps)+get_packets(host)" % dt_e2e,
+           "terms_per_call": passes // e2e_steps, "s_per_call": round(t_e2e / e2e_steps, 4)}
+
+    # CPU baseline beside it: the oracle's fixed-term kernel (4 dzgemv per el+hole term like the reference's two MPI ranks)
+    cpu = cpu_baseline(Hp_np, Psi_bra, Psi_ket, tau, budget_s=args.cpu_budget)
+
+    line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic EHT Hamiltonian N=%d basis, el+hole packets, 1xB200" % N, "basis": N,
+                       "terms_per_step": TERMS_PER_STEP, "l2": "inputs larger than L2 (H' = %.2f GB per pass)" % (alg_bytes / 1e9),
+                       "kernel_variant": "tma", "grid": info["grid"], "tiles": info["tiles"], "build": build_info},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+    print(json.dumps(line))
+
+
+def cpu_baseline(Hp_np, Psi_bra, Psi_ket, tau, budget_s=15.0):
+    import oracle                                                    # the checker, timed as the CPU baseline only
+    oracle.build()
+    N = Hp_np.shape[0]
+    t0 = time.perf_counter(); oracle.terms(Hp_np, Psi_bra, Psi_ket, tau, 2); t2 = time.perf_counter() - t0
+    n = int(max(2, min(200, budget_s / max(t2 / 2, 1e-6))))
+    t0 = time.perf_counter(); oracle.terms(Hp_np, Psi_bra, Psi_ket, tau, n); t = time.perf_counter() - t0
+    return {"value": round(n / t, 3), "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+            "sample": "%d el+hole terms (4 dzgemv each, Taylor.f:94-95 x 2 particles) at N=%d, g++ -O3 OpenMP, %.1f s" % (n, N, t),
+            "gbs_reference_style": round(4 * 8.0 * N * N * n / t / 1e9, 1)}
+
+
+def run_reference(args):
+    """The reference's own CPU algorithm for the path (oracle port: the Fortran/MKL original cannot be built here),
+    all host threads, on the same config/metric; each step a bounded sample."""
+    import oracle
+    oracle.build()
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N = args.basis or (16384 if args.gpus == 1 else 65536)
+    N_run = min(N, 16384)                    # host RAM / time bound: the CPU rate per byte does not depend on N
+    rng = np.random.default_rng(1)
+    # CPU GEMV time is independent of the matrix values: a symmetric banded-decay surrogate of the EHT h stands in for H'
+    Hp = np.asfortranarray(rng.standard_normal((N_run, N_run)) * 1e-2)
+    Psi = np.asfortranarray(rng.standard_normal((N_run, 2)) + 1j * rng.standard_normal((N_run, 2)))
+    tau = 1e-4
+    per_step = max(1, args.ref_terms_per_step)
+    for _ in range(min(args.warmup, 1)):
+        oracle.terms(Hp, Psi, Psi, tau, 1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.terms(Hp, Psi, Psi, tau, per_step)
+    t = time.perf_counter() - t0
+    rate = args.steps * per_step / t
+    scale = (N_run / N) ** 2                 # bytes per term scale with N^2 (memory-bound GEMV)
+    value = rate * scale
+    cores = oracle.num_threads()
+    sample = "%d steps x %d el+hole terms at N=%d (scaled by (N_run/N)^2 to N=%d), oracle port, %d threads" % (args.steps, per_step, N_run, N, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": round(1e3 * t / args.steps, 3), "higher_is_better": True,
+            "scaling": "weak" if args.gpus == 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic EHT Hamiltonian N=%d basis, el+hole packets (CPU oracle port, OpenMP)" % N, "basis": N,
+                       "terms_per_step": per_step},
+            "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--basis", type=int, default=0)
+    ap.add_argument("--e2e-dt", type=float, default=5e-6, help="nuclear step (ps) of the end-to-end call")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--ref-terms-per-step", type=int, default=2)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.gpus == 1:
+        return run_ours_single(args)
+    from dynemol_b200 import sharded
+    return sharded.bench_main(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,280 @@
+"""Host-side mirror of the reference interface for the propagator path, over the C ABI
+(include/dynemol_b200.h) with ctypes.  No torch types cross this boundary: numpy host
+buffers in, numpy host buffers out, exactly like the Fortran caller's arrays.
+
+  * `legacy_*` wrappers call the Fortran-mangled symbols by reference, the way ifort/ifx
+    would (ElHl_Chebyshev_GPU.f:269-272), so parity tests read like the reference's call site.
+  * `Propagator` wraps the native dyb_* handle API (device-resident H' and wavepackets).
+
+The CUDA library is mandatory: importing this module without libdynemol_b200.so raises, and
+every compute call fails loudly without a GPU (there is no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdynemol_b200.so")
+
+H_BAR = 6.58264e-4          # eV*ps (constants_m.f:23)
+MODE_TAYLOR, MODE_CHEBYSHEV = 0, 1
+KERNEL_AUTO, KERNEL_TMA, KERNEL_LDG = 0, 1, 2
+MAX_EVENTS = 256
+
+OK, ENODEV, ECUDA, EINVAL, ENOMEM, ESINGULAR = 0, -1, -2, -3, -4, -5
+
+
+class DynemolB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"dynemol_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Trace(C.Structure):
+    """Mirror of dyb_trace."""
+    _fields_ = [
+        ("n_convergence_calls", C.c_int32), ("n_substeps", C.c_int32), ("n_matvec_pairs", C.c_int32),
+        ("n_rescale", C.c_int32), ("n_first_shrink", C.c_int32), ("last_k_ref", C.c_int32),
+        ("n_events", C.c_int32),
+        ("ev_kind", C.c_int32 * MAX_EVENTS), ("ev_k", C.c_int32 * MAX_EVENTS), ("ev_ok", C.c_int32 * MAX_EVENTS),
+        ("ev_tau", C.c_double * MAX_EVENTS),
+        ("norm_ref", C.c_double), ("final_tau", C.c_double),
+    ]
+
+    def events(self):
+        n = min(self.n_events, MAX_EVENTS)
+        return [(self.ev_kind[i], self.ev_k[i], self.ev_ok[i], self.ev_tau[i]) for i in range(n)]
+
+    def summary(self):
+        return dict(convergence_calls=self.n_convergence_calls, substeps=self.n_substeps,
+                    matvec_pairs=self.n_matvec_pairs, rescale=self.n_rescale,
+                    first_shrink=self.n_first_shrink, k_ref=self.last_k_ref,
+                    norm_ref=self.norm_ref, final_tau=self.final_tau)
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m dynemol_b200.build` "
+            "(nvcc, sm_100a).  dynemol_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.dyb_last_error.restype = C.c_char_p
+    lib.dyb_version.restype = C.c_char_p
+    lib.dyb_launch_count.restype = C.c_int64
+    lib.dyb_launch_count.argtypes = [C.c_void_p]
+    lib.nakedbessel_.restype = C.c_double
+    return lib
+
+
+lib = _load()
+
+# every symbol include/dynemol_b200.h declares (checked by the CPU test-suite)
+DECLARED_SYMBOLS = [
+    "propagationelhl_gpucaller_", "propagationelhl2_gpucaller_", "propagation_gpucaller_", "nakedbessel_",
+    "gpu_init_", "gpu_finalize_", "gpu_pin_", "gpu_unpin_",
+    "dyb_last_error", "dyb_version", "dyb_device_count", "dyb_create", "dyb_destroy", "dyb_set_kernel",
+    "dyb_get_info", "dyb_upload_hprime", "dyb_upload_hprime_device", "dyb_hprime_device", "dyb_form_hprime", "dyb_form_hprime_device",
+    "dyb_download_hprime", "dyb_set_packets", "dyb_get_packets", "dyb_propagate", "dyb_ao_bra",
+    "dyb_populations", "dyb_run_terms", "dyb_dual_matvec", "dyb_sync", "dyb_launch_count",
+]
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise DynemolB200Error(rc, lib.dyb_last_error().decode())
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _fz(a, copy=True) -> np.ndarray:
+    return np.array(a, dtype=np.complex128, order="F", copy=copy)
+
+
+def _fd(a) -> np.ndarray:
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+def device_count() -> int:
+    return int(lib.dyb_device_count())
+
+
+class Propagator:
+    """Native handle API: one GPU, one basis size, H' and the wavepackets resident in HBM."""
+
+    def __init__(self, N: int, device: int = 0, row0: int = 0, n_rows: int | None = None, kernel: int = KERNEL_AUTO):
+        self.N = int(N)
+        self._h = C.c_void_p()
+        _check(lib.dyb_create(C.byref(self._h), C.c_int(device), C.c_int(N), C.c_int(row0),
+                              C.c_int(N if n_rows is None else n_rows)))
+        if kernel != KERNEL_AUTO:
+            self.set_kernel(kernel)
+        self.n_part = 0
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib.dyb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def set_kernel(self, kernel: int):
+        _check(lib.dyb_set_kernel(self._h, C.c_int(kernel)))
+
+    def info(self) -> dict:
+        buf = (C.c_int64 * 16)()
+        _check(lib.dyb_get_info(self._h, buf))
+        keys = ["N", "ld", "n_rows", "grid", "tiles", "segments", "sm_count", "smem_bytes", "variant", "panels", "tiles_per_panel", "passes_last"]
+        return {k: int(buf[i]) for i, k in enumerate(keys)}
+
+    # ---- operator
+    def upload_hprime(self, H):
+        H = _fd(H)
+        assert H.shape == (self.N, self.N)
+        _check(lib.dyb_upload_hprime(self._h, _p(H), C.c_int64(self.N)))
+
+    def upload_hprime_device(self, d_ptr: int, lda: int):
+        """H' from a device buffer (column-major, leading dimension lda), e.g. a torch tensor's data_ptr()."""
+        _check(lib.dyb_upload_hprime_device(self._h, C.c_void_p(d_ptr), C.c_int64(lda)))
+
+    def hprime_device(self):
+        ptr = C.c_void_p(); ld = C.c_int64()
+        _check(lib.dyb_hprime_device(self._h, C.byref(ptr), C.byref(ld)))
+        return ptr.value, ld.value
+
+    def form_hprime(self, S, h, want_hprime: bool = True):
+        """a2+a3: H' = S^-1 h on the device (ElHl_Chebyshev.f:206-210)."""
+        S = _fd(S); h = _fd(h)
+        out = np.empty((self.N, self.N), dtype=np.float64, order="F") if want_hprime else None
+        _check(lib.dyb_form_hprime(self._h, _p(S), _p(h), _p(out) if want_hprime else None))
+        return out
+
+    def form_hprime_device(self, d_S: int, lds: int, d_h: int, ldh: int):
+        _check(lib.dyb_form_hprime_device(self._h, C.c_void_p(d_S), C.c_int64(lds), C.c_void_p(d_h), C.c_int64(ldh)))
+
+    def download_hprime(self):
+        out = np.empty((self.N, self.N), dtype=np.float64, order="F")
+        _check(lib.dyb_download_hprime(self._h, _p(out), C.c_int64(self.N)))
+        return out
+
+    # ---- packets
+    def set_packets(self, bra, ket):
+        bra = _fz(bra); ket = _fz(ket)
+        if bra.ndim == 1:
+            bra = np.asfortranarray(bra[:, None]); ket = np.asfortranarray(ket[:, None])
+        assert bra.shape == ket.shape and bra.shape[0] == self.N and bra.shape[1] in (1, 2)
+        self.n_part = bra.shape[1]
+        _check(lib.dyb_set_packets(self._h, C.c_int(self.n_part), _p(bra), _p(ket)))
+
+    def get_packets(self):
+        bra = np.empty((self.N, self.n_part), dtype=np.complex128, order="F"); ket = np.empty_like(bra, order="F")
+        _check(lib.dyb_get_packets(self._h, C.c_int(self.n_part), _p(bra), _p(ket)))
+        return bra, ket
+
+    # ---- propagation
+    def propagate(self, t_init, t_max, tau, mode: int = MODE_TAYLOR):
+        """a4/a5.  Returns (save_tau[n_part], [Trace...])."""
+        tau = np.ascontiguousarray(np.broadcast_to(np.asarray(tau, dtype=np.float64), (self.n_part,)))
+        tau2 = np.zeros(2); tau2[: self.n_part] = tau
+        save = np.zeros(2)
+        traces = (Trace * 2)()
+        _check(lib.dyb_propagate(self._h, C.c_int(mode), C.c_double(t_init), C.c_double(t_max), _p(tau2), _p(save), traces))
+        return save[: self.n_part].copy(), [traces[i] for i in range(self.n_part)]
+
+    def run_terms(self, tau: float, n_terms: int, per_kernel: bool = False):
+        """n_terms el+hole series terms, no host decisions.  Returns (elapsed_ms, matvec_kernel_ms or None)."""
+        el = C.c_float(0.0); km = C.c_float(0.0)
+        _check(lib.dyb_run_terms(self._h, C.c_double(tau), C.c_int(n_terms), C.byref(el), C.byref(km) if per_kernel else None))
+        return el.value, (km.value if per_kernel else None)
+
+    def dual_matvec(self, xb, xk):
+        """(H'^T xb, H' xk) in one pass over H' -- kernel-level parity entry."""
+        xb = _fz(xb); xk = _fz(xk)
+        if xb.ndim == 1:
+            xb = np.asfortranarray(xb[:, None]); xk = np.asfortranarray(xk[:, None])
+        n_part = xb.shape[1]
+        yb = np.empty_like(xb, order="F"); yk = np.empty_like(xk, order="F")
+        _check(lib.dyb_dual_matvec(self._h, C.c_int(n_part), _p(xb), _p(xk), _p(yb), _p(yk)))
+        return yb, yk
+
+    # ---- post-step
+    def ao_bra(self):
+        out = np.empty((self.N, self.n_part), dtype=np.complex128, order="F")
+        _check(lib.dyb_ao_bra(self._h, C.c_int(self.n_part), _p(out)))
+        return out
+
+    def populations(self, fragment, n_frag: int, t: float):
+        frag = np.ascontiguousarray(fragment, dtype=np.int32)
+        out = np.zeros((n_frag + 2, self.n_part), dtype=np.float64, order="F")
+        _check(lib.dyb_populations(self._h, C.c_int(self.n_part), C.c_int(n_frag), _p(frag), C.c_double(t), _p(out)))
+        return out
+
+    def sync(self):
+        _check(lib.dyb_sync(self._h))
+
+    def launch_count(self) -> int:
+        return int(lib.dyb_launch_count(self._h))
+
+
+# --------------------------------------------------------------------------- legacy Fortran symbols, called by reference
+def _ref(x, ctype):
+    return C.byref(ctype(x))
+
+
+def legacy_propagationelhl(S, h, PSI_bra, PSI_ket, t_init, t_max, tau, batched: bool | None = None):
+    """call PropagationElHl_gpucaller(N, S, h0, H_prime, AO_bra(:,p), AO_ket(:,p), Psi_t_bra(:,p), Psi_t_ket(:,p),
+    t_init, t_max, tau, save_tau)  -- ElHl_Chebyshev_GPU.f:269-272.  PSI_* of shape (N,) use the per-particle
+    symbol, shape (N,2) the batched el+hole symbol.  Returns dict(H_prime, AO_bra, PSI_bra, PSI_ket, save_tau)."""
+    S = np.array(S, dtype=np.float64, order="F", copy=True); h = np.array(h, dtype=np.float64, order="F", copy=True)
+    N = S.shape[0]
+    PSI_bra = _fz(PSI_bra); PSI_ket = _fz(PSI_ket)
+    two = PSI_bra.ndim == 2 and PSI_bra.shape[1] == 2
+    if batched is None:
+        batched = two
+    Hp = np.zeros((N, N), dtype=np.float64, order="F")
+    AO_bra = np.zeros_like(PSI_bra, order="F"); AO_ket = np.full_like(PSI_bra, np.nan, order="F")
+    n = C.c_int(N); ti = C.c_double(t_init); tm = C.c_double(t_max)
+    if batched:
+        tau_a = np.ascontiguousarray(np.broadcast_to(np.asarray(tau, dtype=np.float64), (2,))).copy(); save = np.zeros(2)
+        lib.propagationelhl2_gpucaller_(C.byref(n), _p(S), _p(h), _p(Hp), _p(AO_bra), _p(AO_ket), _p(PSI_bra), _p(PSI_ket),
+                                        C.byref(ti), C.byref(tm), _p(tau_a), _p(save))
+    else:
+        tau_c = C.c_double(float(tau)); sv = C.c_double(0.0)
+        lib.propagationelhl_gpucaller_(C.byref(n), _p(S), _p(h), _p(Hp), _p(AO_bra), _p(AO_ket), _p(PSI_bra), _p(PSI_ket),
+                                       C.byref(ti), C.byref(tm), C.byref(tau_c), C.byref(sv))
+        save = np.array([sv.value])
+    return dict(H_prime=Hp, AO_bra=AO_bra, AO_ket=AO_ket, PSI_bra=PSI_bra, PSI_ket=PSI_ket, save_tau=save)
+
+
+def legacy_propagation(H, PSI_bra, PSI_ket, t_init, t_max, tau):
+    """call Propagation_gpucaller(n, tau, save_tau, t_init, t_max, PSI_bra, PSI_ket, H) -- Taylor_gpu.cpp:295-330."""
+    H = _fd(H); N = H.shape[0]
+    PSI_bra = _fz(PSI_bra); PSI_ket = _fz(PSI_ket)
+    n = C.c_int(N); tau_c = C.c_double(float(tau)); sv = C.c_double(0.0)
+    lib.propagation_gpucaller_(C.byref(n), C.byref(tau_c), C.byref(sv), _ref(t_init, C.c_double), _ref(t_max, C.c_double),
+                               _p(PSI_bra), _p(PSI_ket), _p(H))
+    return PSI_bra, PSI_ket, sv.value
+
+
+def nakedbessel(n: int, x: float) -> float:
+    return lib.nakedbessel_(C.byref(C.c_int(n)), C.byref(C.c_double(x)))
+
+
+def gpu_init(pid: int = 0, procs_per_dev: int = 1):
+    lib.gpu_init_(C.byref(C.c_int(pid)), C.byref(C.c_int(procs_per_dev)))
+
+
+def gpu_finalize():
+    lib.gpu_finalize_()
+
+
+def gpu_pin(a: np.ndarray):
+    lib.gpu_pin_(_p(a), C.byref(C.c_int(np.int64(a.nbytes).astype(np.int32))))
+
+
+def gpu_unpin(a: np.ndarray):
+    lib.gpu_unpin_(_p(a))

@@ -1,0 +1,731 @@
+// propagator.cu -- host side of the B200-native electron-hole propagator: context, launch plan,
+// the Taylor (reference-parity) and Chebyshev series drivers, H' = S^-1 h formation, and the C ABI
+// declared in include/dynemol_b200.h.  Host logic mirrors, decision for decision, the reference's
+// CPU oracle Taylor.f:35-219 as driven by ElHl_Chebyshev.f:174-276.
+//
+// There is deliberately no CPU fallback here: every compute entry needs a CUDA device.
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+
+#include "../../include/dynemol_b200.h"
+#include "common.cuh"
+#include "matvec.cuh"
+#include "epilogue.cuh"
+
+using namespace dyb;
+typedef std::complex<double> cplx;
+
+static const int    ORDER = 25;           // Taylor.f:20
+static const double H_BAR = 6.58264e-4;   // constants_m.f:23 (eV*ps)
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? DYB_ENODEV : DYB_ECUDA, \
+                "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
+#define CKB(call) do { cublasStatus_t s_ = (call); if (s_ != CUBLAS_STATUS_SUCCESS) \
+    return fail(DYB_ECUDA, "%s:%d %s: cublas status %d", __FILE__, __LINE__, #call, (int)s_); } while (0)
+#define CKS(call) do { cusolverStatus_t s_ = (call); if (s_ != CUSOLVER_STATUS_SUCCESS) \
+    return fail(DYB_ECUDA, "%s:%d %s: cusolver status %d", __FILE__, __LINE__, #call, (int)s_); } while (0)
+
+// ------------------------------------------------------------------------------------------ context
+struct dyb_ctx {
+    int device = 0, sm_count = 0;
+    int N = 0, row0 = 0, M = 0;          // basis size, first owned row, owned rows
+    long long ld = 0;
+    int NP = 0, TPP = 0, Ncpad = 0, grid = 0, n_seg = 0;
+    int T = 0;
+    size_t Lq = 0;                       // quad vector length (indices)
+    int variant = DYB_KERNEL_TMA;
+    cudaStream_t stream = nullptr;
+    CUtensorMap tmap;
+    bool have_tmap = false;
+
+    double* H = nullptr;                 // ld x N
+    double* S = nullptr;                 // N x N factor of S (Cholesky or LU) kept for S^-1 applications
+    int64_t* ipiv = nullptr;             // LU pivots (fallback)
+    bool have_factor = false, factor_is_lu = false;
+    double *psi_b = nullptr, *psi_k = nullptr, *sum_b = nullptr, *sum_k = nullptr;
+    double *vb[3] = {nullptr, nullptr, nullptr}, *vk[3] = {nullptr, nullptr, nullptr};
+    double *ket_slab = nullptr, *bra_slab = nullptr, *blockpart = nullptr, *scal = nullptr, *io = nullptr;
+    int *seg_base = nullptr, *pseg_start = nullptr, *frag = nullptr;
+    Ctrl* ctrl = nullptr;                // device
+    Ctrl* h_ctrl = nullptr;              // pinned host mirror
+    double* h_scal = nullptr;            // pinned, 64 doubles
+    int n_part = 0;
+    int64_t launches = 0;
+    int64_t passes_last = 0;             // el+hole terms (passes over H') of the last propagate / run_terms
+    cublasHandle_t blas = nullptr;
+    cusolverDnHandle_t solver = nullptr;
+    cusolverDnParams_t sparams = nullptr;
+    std::vector<cudaEvent_t> ev;
+};
+
+static int ensure_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(DYB_ENODEV, "no CUDA device available (%s); dynemol_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(DYB_EINVAL, "device %d out of range (0..%d)", device, n - 1);
+    CK(cudaSetDevice(device));
+    return DYB_OK;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int build_tensor_map(dyb_ctx* c) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(DYB_ECUDA, "cuTensorMapEncodeTiled not available");
+    // 3-D view of the column-major matrix: (row in sub-panel, sub-panel, column)
+    cuuint64_t dims[3]    = {(cuuint64_t)SUB_ROWS, (cuuint64_t)(c->ld / SUB_ROWS), (cuuint64_t)c->N};
+    cuuint64_t strides[2] = {(cuuint64_t)SUB_ROWS * 8, (cuuint64_t)c->ld * 8};
+    cuuint32_t box[3]     = {(cuuint32_t)SUB_ROWS, (cuuint32_t)N_CWARPS, (cuuint32_t)TILE_COLS};
+    cuuint32_t estr[3]    = {1, 1, 1};
+    CUresult r = ((PFN_encodeTiled)fn)(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, c->H, dims, strides, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DYB_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    c->have_tmap = true;
+    return DYB_OK;
+}
+
+static int build_plan(dyb_ctx* c) {
+    c->NP    = (c->M + PANEL_ROWS - 1) / PANEL_ROWS;
+    c->TPP   = (c->N + TILE_COLS - 1) / TILE_COLS;
+    c->Ncpad = c->TPP * TILE_COLS;
+    c->T     = c->NP * c->TPP;
+    c->grid  = std::min(c->sm_count, c->T);
+    std::vector<int> seg_base(c->grid, 0), pcount(c->NP, 0);
+    int seg = 0;
+    for (int b = 0; b < c->grid; ++b) {
+        const long long t0 = ((long long)c->T * b) / c->grid, t1 = ((long long)c->T * (b + 1)) / c->grid;
+        seg_base[b] = seg;
+        if (t1 <= t0) continue;
+        const int p0 = (int)(t0 / c->TPP), p1 = (int)((t1 - 1) / c->TPP);
+        for (int p = p0; p <= p1; ++p) { pcount[p]++; seg++; }
+    }
+    c->n_seg = seg;
+    std::vector<int> pstart(c->NP + 1, 0);
+    for (int p = 0; p < c->NP; ++p) pstart[p + 1] = pstart[p] + pcount[p];
+    CK(cudaMalloc(&c->seg_base, sizeof(int) * c->grid));
+    CK(cudaMalloc(&c->pseg_start, sizeof(int) * (c->NP + 1)));
+    CK(cudaMemcpy(c->seg_base, seg_base.data(), sizeof(int) * c->grid, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->pseg_start, pstart.data(), sizeof(int) * (c->NP + 1), cudaMemcpyHostToDevice));
+    return DYB_OK;
+}
+
+static int alloc_zero(double** p, size_t n_doubles) {
+    CK(cudaMalloc(p, n_doubles * sizeof(double)));
+    CK(cudaMemset(*p, 0, n_doubles * sizeof(double)));
+    return DYB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ launches
+static MatvecParams matvec_params(dyb_ctx* c, const double* xk, const double* xb, bool use_ctrl) {
+    MatvecParams P;
+    P.M = c->M; P.Nc = c->N; P.ld = c->ld; P.TPP = c->TPP; P.T = c->T; P.Ncpad = c->Ncpad;
+    P.H = c->H; P.Xk = xk; P.Xb = xb; P.ket_slab = c->ket_slab; P.bra_slab = c->bra_slab;
+    P.seg_base = c->seg_base; P.ctrl = use_ctrl ? c->ctrl : nullptr;
+    return P;
+}
+
+static int launch_matvec(dyb_ctx* c, const double* xk, const double* xb, bool use_ctrl) {
+    const MatvecParams P = matvec_params(c, xk, xb, use_ctrl);
+    if (c->variant == DYB_KERNEL_LDG) {
+        dual_matvec_ldg_kernel<<<c->grid, LDG_THREADS, 0, c->stream>>>(P);
+    } else {
+        dual_matvec_tma_kernel<<<c->grid, TMA_THREADS, TmaSmem::total, c->stream>>>(c->tmap, P);
+    }
+    c->launches++;
+    CK(cudaGetLastError());
+    return DYB_OK;
+}
+
+static EpiParams epi_params(dyb_ctx* c, int cur, int prv, int nxt) {
+    EpiParams E;
+    E.M = c->M; E.row0 = c->row0; E.n_bra_slabs = c->NP; E.Ncpad = c->Ncpad;
+    E.ket_slab = c->ket_slab; E.bra_slab = c->bra_slab; E.pseg_start = c->pseg_start;
+    E.cur_b = c->vb[cur]; E.cur_k = c->vk[cur]; E.prv_b = c->vb[prv]; E.prv_k = c->vk[prv];
+    E.nxt_b = c->vb[nxt]; E.nxt_k = c->vk[nxt]; E.sum_b = c->sum_b; E.sum_k = c->sum_k;
+    E.blockpart = c->blockpart; E.ctrl = c->ctrl;
+    memset(&E.pass, 0, sizeof E.pass);
+    return E;
+}
+static int epi_grid(const dyb_ctx* c) { return (2 * c->M + EPI_THREADS - 1) / EPI_THREADS; }
+
+static int launch_epilogue(dyb_ctx* c, const EpiParams& E) {
+    epilogue_kernel<<<epi_grid(c), EPI_THREADS, 0, c->stream>>>(E);
+    c->launches++;
+    CK(cudaGetLastError());
+    return DYB_OK;
+}
+
+static int launch_series_init(dyb_ctx* c, const int adopt[2], const int active[2], int cur) {
+    InitParams I;
+    I.M = c->M; I.row0 = c->row0; I.Nc = c->N;
+    for (int p = 0; p < 2; ++p) { I.adopt[p] = adopt[p]; I.active[p] = active[p]; }
+    I.psi_b = c->psi_b; I.psi_k = c->psi_k; I.cur_b = c->vb[cur]; I.cur_k = c->vk[cur];
+    I.sum_b = c->sum_b; I.sum_k = c->sum_k; I.ctrl = c->ctrl;
+    series_init_kernel<<<(2 * c->M + 255) / 256, 256, 0, c->stream>>>(I);
+    c->launches++;
+    CK(cudaGetLastError());
+    return DYB_OK;
+}
+
+static int read_ctrl(dyb_ctx* c) {
+    CK(cudaMemcpyAsync(c->h_ctrl, c->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return DYB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ series coefficients
+// Taylor.f:224-239:  c(1) = 1 ; c(k) = -zi * c(k-1) * (tau/(k-1))     (0-based storage here)
+static void taylor_coefficient(double tau, cplx* C) {
+    const cplx minus_i(0.0, -1.0);
+    C[0] = cplx(1.0, 0.0);
+    for (int k = 1; k < ORDER; ++k) C[k] = minus_i * C[k - 1] * (tau / (double)k);
+}
+// Taylor.f:165-171: k_max = first 1-based k >= 2 with |c(k)| < 1e-16, else order
+static int taylor_kmax(const cplx* C) {
+    for (int k = 2; k <= ORDER; ++k) if (std::abs(C[k - 1]) < 1.0e-16) return k;
+    return ORDER;
+}
+
+// ------------------------------------------------------------------------------------------ Taylor driver
+struct Particle {
+    bool   present = false, done = true;
+    int    phase = 0;                 // 0 first Convergence loop, 1 steady sub-steps, 2 rescale Convergence
+    double tau = 0, save_tau = 0, t = 0, norm_ref = 0;
+    int    k_ref = 0, k_end = 0;
+    bool   check = false;
+    cplx   C[ORDER];
+    int    shrinks = 0;
+    dyb_trace* tr = nullptr;
+};
+
+static void trace_event(dyb_trace* tr, int kind, int k, int ok, double tau) {
+    if (!tr) return;
+    if (tr->n_events < DYB_MAX_EVENTS) {
+        const int e = tr->n_events;
+        tr->ev_kind[e] = kind; tr->ev_k[e] = k; tr->ev_ok[e] = ok; tr->ev_tau[e] = tau;
+    }
+    tr->n_events++;
+}
+
+static int compute_norm_ref(dyb_ctx* c, double out[2]) {
+    dotc_kernel<<<1, 1024, 0, c->stream>>>(c->M, c->psi_b, c->psi_k + (size_t)c->row0 * NQ, c->scal);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c->h_scal, c->scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    out[0] = std::abs(cplx(c->h_scal[0], c->h_scal[1]));      // Taylor.f:62
+    out[1] = std::abs(cplx(c->h_scal[2], c->h_scal[3]));
+    return DYB_OK;
+}
+
+static int propagate_taylor(dyb_ctx* c, double t_init, double t_max, const double* tau_in, double* save_tau, dyb_trace* traces)
+{
+    Particle P[2];
+    double nref[2];
+    int rc = compute_norm_ref(c, nref);
+    if (rc) return rc;
+    for (int p = 0; p < c->n_part; ++p) {
+        P[p].present = true; P[p].done = false; P[p].phase = 0;
+        P[p].tau = tau_in[p]; P[p].norm_ref = nref[p]; P[p].t = t_init;
+        P[p].tr = traces ? &traces[p] : nullptr;
+        if (P[p].tr) { memset(P[p].tr, 0, sizeof(dyb_trace)); P[p].tr->norm_ref = nref[p]; }
+    }
+    int adopt[2] = {0, 0};
+    long guard = 0;
+    c->passes_last = 0;
+    for (;;) {
+        int active[2] = {0, 0};
+        int L = 0;
+        for (int p = 0; p < 2; ++p) {
+            Particle& q = P[p];
+            if (!q.present || q.done) continue;
+            active[p] = 1;
+            if (q.phase == 0 || q.phase == 2) {                   // Convergence(): Taylor.f:163-173
+                taylor_coefficient(q.tau, q.C);
+                q.k_ref = taylor_kmax(q.C);
+                q.k_end = q.k_ref; q.check = true;
+            } else {                                              // steady sub-step: Taylor.f:90
+                q.k_end = q.k_ref; q.check = false;
+            }
+            L = std::max(L, q.k_end - 1);
+        }
+        if (!active[0] && !active[1]) break;
+        if (++guard > 2000000) return fail(DYB_EINVAL, "propagation does not terminate (tau -> 0?)");
+
+        int cur = 0, nxt = 1;
+        if ((rc = launch_series_init(c, adopt, active, cur))) return rc;
+        adopt[0] = adopt[1] = 0;
+        for (int s = 0; s < L; ++s) {
+            const int k = s + 2;                                  // 1-based series index, Taylor.f:182 / :90
+            EpiParams E = epi_params(c, cur, cur, nxt);
+            for (int p = 0; p < 2; ++p) {
+                Particle& q = P[p];
+                PartPass& a = E.pass.part[p];
+                if (!active[p] || k > q.k_end) { a.active = 0; continue; }
+                const cplx r = q.C[k - 1] / q.C[k - 2];           // Taylor.f:93,185
+                a.active = 1; a.k = k; a.three_term = 0; a.scale_term = 0;
+                a.check_conv = q.check ? 1 : 0; a.last = (k == q.k_end) ? 1 : 0; a.last_ok_by_norm = q.check ? 0 : 1;
+                a.alpha_re = r.real(); a.alpha_im = r.imag();
+                a.norm_ref = q.norm_ref;
+            }
+            if ((rc = launch_matvec(c, c->vk[cur], c->vb[cur], true))) return rc;
+            if ((rc = launch_epilogue(c, E))) return rc;
+            std::swap(cur, nxt);
+        }
+        if ((rc = read_ctrl(c))) return rc;
+        c->passes_last += std::max(c->h_ctrl->part[0].latched && active[0] ? c->h_ctrl->part[0].n_terms : 0,
+                                   c->h_ctrl->part[1].latched && active[1] ? c->h_ctrl->part[1].n_terms : 0);
+
+        for (int p = 0; p < 2; ++p) {
+            Particle& q = P[p];
+            if (!active[p]) continue;
+            const PartState& st = c->h_ctrl->part[p];
+            const bool ok = st.ok != 0;
+            if (q.tr) { q.tr->n_matvec_pairs += st.n_terms; q.tr->last_k_ref = q.k_ref; }
+            bool advance = false;
+            if (q.phase == 0) {                                   // Taylor.f:65-71
+                if (q.tr) q.tr->n_convergence_calls++;
+                trace_event(q.tr, 1, ok ? st.k_exit : 0, ok, q.tau);
+                if (ok) {
+                    adopt[p] = 1;
+                    q.save_tau = q.tau; save_tau[p] = q.tau;
+                    q.t = t_init + q.tau * H_BAR;                 // Taylor.f:73
+                    if (t_max - q.t < q.tau * H_BAR) {            // Taylor.f:75-78
+                        q.tau = (t_max - q.t) / H_BAR;
+                        taylor_coefficient(q.tau, q.C);
+                    }
+                    q.phase = 1;
+                    if (!(q.t < t_max)) q.done = true;            // Taylor.f:81
+                } else {
+                    q.tau *= 0.9;
+                    if (q.tr) q.tr->n_first_shrink++;
+                    if (++q.shrinks > 20000) return fail(DYB_EINVAL, "Convergence never succeeds (tau=%g)", q.tau);
+                }
+            } else if (q.phase == 1) {                            // Taylor.f:102-114
+                if (q.tr) q.tr->n_substeps++;
+                trace_event(q.tr, 2, q.k_ref, ok, q.tau);
+                if (ok) { adopt[p] = 1; advance = true; }
+                else {
+                    q.tau *= 0.975;                               // Taylor.f:110
+                    if (q.tr) q.tr->n_rescale++;
+                    q.phase = 2;
+                }
+            } else {                                              // rescale loop, Taylor.f:108-113
+                if (q.tr) q.tr->n_convergence_calls++;
+                trace_event(q.tr, 1, ok ? st.k_exit : 0, ok, q.tau);
+                if (ok) { adopt[p] = 1; advance = true; q.phase = 1; }
+                else {
+                    q.tau *= 0.975;
+                    if (q.tr) q.tr->n_rescale++;
+                    if (++q.shrinks > 20000) return fail(DYB_EINVAL, "rescaling tau never converges (tau=%g)", q.tau);
+                }
+            }
+            if (advance) {
+                q.t += q.tau * H_BAR;                             // Taylor.f:116
+                if (t_max - q.t < q.tau * H_BAR) {                // Taylor.f:118-121
+                    q.tau = (t_max - q.t) / H_BAR;
+                    taylor_coefficient(q.tau, q.C);
+                }
+                if (!(q.t < t_max)) q.done = true;
+            }
+        }
+    }
+    // adopt the last accepted sums
+    if (adopt[0] || adopt[1]) {
+        const int none[2] = {0, 0};
+        if ((rc = launch_series_init(c, adopt, none, 0))) return rc;
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    for (int p = 0; p < c->n_part; ++p) if (P[p].tr) P[p].tr->final_tau = P[p].tau;
+    return DYB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ C ABI: native
+extern "C" {
+
+const char* dyb_last_error(void) { return g_err.c_str(); }
+const char* dyb_version(void) { return "dynemol_b200 0.1 (sm_100a)"; }
+
+int dyb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int dyb_destroy(dyb_ctx* c) {
+    if (!c) return DYB_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    double** bufs[] = {&c->H, &c->S, &c->psi_b, &c->psi_k, &c->sum_b, &c->sum_k, &c->vb[0], &c->vb[1], &c->vb[2],
+                       &c->vk[0], &c->vk[1], &c->vk[2], &c->ket_slab, &c->bra_slab, &c->blockpart, &c->scal, &c->io};
+    for (auto b : bufs) if (*b) cudaFree(*b);
+    if (c->ipiv) cudaFree(c->ipiv);
+    if (c->seg_base) cudaFree(c->seg_base);
+    if (c->pseg_start) cudaFree(c->pseg_start);
+    if (c->frag) cudaFree(c->frag);
+    if (c->ctrl) cudaFree(c->ctrl);
+    if (c->h_ctrl) cudaFreeHost(c->h_ctrl);
+    if (c->h_scal) cudaFreeHost(c->h_scal);
+    for (auto e : c->ev) cudaEventDestroy(e);
+    if (c->sparams) cusolverDnDestroyParams(c->sparams);
+    if (c->solver) cusolverDnDestroy(c->solver);
+    if (c->blas) cublasDestroy(c->blas);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return DYB_OK;
+}
+
+int dyb_create(dyb_ctx** out, int device, int N, int row0, int n_rows) {
+    if (!out) return fail(DYB_EINVAL, "out is NULL");
+    *out = nullptr;
+    int rc = ensure_device(device);
+    if (rc) return rc;
+    if (N <= 0 || row0 < 0 || n_rows <= 0 || row0 + n_rows > N) return fail(DYB_EINVAL, "bad shape N=%d row0=%d n_rows=%d", N, row0, n_rows);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(DYB_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    dyb_ctx* c = new dyb_ctx();
+    c->device = device; c->sm_count = prop.multiProcessorCount;
+    c->N = N; c->row0 = row0; c->M = n_rows;
+    c->ld = ((long long)n_rows + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN;
+#define CKC(x) do { int r_ = (x); if (r_) { dyb_destroy(c); return r_; } } while (0)
+#define CKCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int r_ = fail(e_ == cudaErrorMemoryAllocation ? DYB_ENOMEM : DYB_ECUDA, \
+        "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); dyb_destroy(c); return r_; } } while (0)
+    CKCU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CKC(build_plan(c));
+    c->Lq = (size_t)std::max(c->NP * PANEL_ROWS, c->Ncpad) + PANEL_ROWS;
+    CKCU(cudaMalloc(&c->H, (size_t)c->ld * N * sizeof(double)));
+    CKCU(cudaMemsetAsync(c->H, 0, (size_t)c->ld * N * sizeof(double), c->stream));
+    CKC(alloc_zero(&c->psi_b, c->Lq * NQ)); CKC(alloc_zero(&c->psi_k, c->Lq * NQ));
+    CKC(alloc_zero(&c->sum_b, c->Lq * NQ)); CKC(alloc_zero(&c->sum_k, c->Lq * NQ));
+    for (int i = 0; i < 3; ++i) { CKC(alloc_zero(&c->vb[i], c->Lq * NQ)); CKC(alloc_zero(&c->vk[i], c->Lq * NQ)); }
+    CKC(alloc_zero(&c->ket_slab, (size_t)std::max(1, c->n_seg) * PANEL_ROWS * NQ));
+    CKC(alloc_zero(&c->bra_slab, (size_t)c->NP * c->Ncpad * NQ));
+    CKC(alloc_zero(&c->blockpart, (size_t)epi_grid(c) * 8));
+    CKC(alloc_zero(&c->scal, 64));
+    CKC(alloc_zero(&c->io, (size_t)N * 4 * 2));            // staging for host <-> quad conversion / S^-1 solves
+    CKCU(cudaMalloc(&c->ctrl, sizeof(Ctrl)));
+    CKCU(cudaMemset(c->ctrl, 0, sizeof(Ctrl)));
+    CKCU(cudaMallocHost(&c->h_ctrl, sizeof(Ctrl)));
+    CKCU(cudaMallocHost(&c->h_scal, 64 * sizeof(double)));
+    CKC(build_tensor_map(c));
+    CKCU(cudaFuncSetAttribute(dual_matvec_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TmaSmem::total));
+    CKCU(cudaDeviceSynchronize());     // the zero fills above ran on the legacy stream; c->stream is non-blocking
+#undef CKC
+#undef CKCU
+    *out = c;
+    return DYB_OK;
+}
+
+int dyb_set_kernel(dyb_ctx* c, int v) {
+    if (!c) return fail(DYB_EINVAL, "ctx is NULL");
+    if (v == DYB_KERNEL_AUTO) v = DYB_KERNEL_TMA;
+    if (v != DYB_KERNEL_TMA && v != DYB_KERNEL_LDG) return fail(DYB_EINVAL, "unknown kernel variant %d", v);
+    c->variant = v;
+    return DYB_OK;
+}
+
+int dyb_get_info(dyb_ctx* c, int64_t* o) {
+    if (!c || !o) return fail(DYB_EINVAL, "NULL argument");
+    memset(o, 0, 16 * sizeof(int64_t));
+    o[0] = c->N; o[1] = c->ld; o[2] = c->M; o[3] = c->grid; o[4] = c->T; o[5] = c->n_seg; o[6] = c->sm_count;
+    o[7] = TmaSmem::total; o[8] = c->variant; o[9] = c->NP; o[10] = c->TPP; o[11] = c->passes_last;
+    return DYB_OK;
+}
+
+int dyb_sync(dyb_ctx* c) {
+    if (!c) return fail(DYB_EINVAL, "ctx is NULL");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return DYB_OK;
+}
+
+int64_t dyb_launch_count(dyb_ctx* c) { return c ? c->launches : 0; }
+
+// ---- operator ------------------------------------------------------------------------------------
+int dyb_upload_hprime(dyb_ctx* c, const double* h_H, int64_t lda) {
+    if (!c || !h_H || lda < c->N) return fail(DYB_EINVAL, "bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpy2DAsync(c->H, (size_t)c->ld * 8, h_H + c->row0, (size_t)lda * 8, (size_t)c->M * 8, c->N,
+                         cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->have_factor = false;
+    return DYB_OK;
+}
+
+int dyb_upload_hprime_device(dyb_ctx* c, const void* d_H, int64_t lda) {
+    if (!c || !d_H || lda < c->N) return fail(DYB_EINVAL, "bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpy2DAsync(c->H, (size_t)c->ld * 8, reinterpret_cast<const double*>(d_H) + c->row0, (size_t)lda * 8,
+                         (size_t)c->M * 8, c->N, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->have_factor = false;
+    return DYB_OK;
+}
+
+int dyb_hprime_device(dyb_ctx* c, void** d_ptr, int64_t* ld) {
+    if (!c || !d_ptr || !ld) return fail(DYB_EINVAL, "NULL argument");
+    *d_ptr = c->H; *ld = c->ld;
+    return DYB_OK;
+}
+
+int dyb_download_hprime(dyb_ctx* c, double* h_H, int64_t lda) {
+    if (!c || !h_H || lda < c->M) return fail(DYB_EINVAL, "bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpy2DAsync(h_H, (size_t)lda * 8, c->H, (size_t)c->ld * 8, (size_t)c->M * 8, c->N, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return DYB_OK;
+}
+
+static int ensure_solver(dyb_ctx* c) {
+    if (!c->solver) {
+        CKS(cusolverDnCreate(&c->solver));
+        CKS(cusolverDnSetStream(c->solver, c->stream));
+        CKS(cusolverDnCreateParams(&c->sparams));
+    }
+    if (!c->S) CK(cudaMalloc(&c->S, (size_t)c->N * c->N * sizeof(double)));
+    return DYB_OK;
+}
+
+// H' = S^-1 h with S in c->S (N x N, lda N, destroyed) and h already in c->H (ld).
+// ElHl_Chebyshev.f:206-210 computes inv(S) (dsytrf/dsytri) and then dsymm; here S is factorised once
+// (Cholesky; LU with partial pivoting if S is not numerically SPD, as the reference's GPU flavour
+// GPU_Interface.cpp:910-929) and the N right-hand sides are solved in place: fewer flops, no explicit
+// inverse, same result to O(cond(S) eps).  The factor is kept for AO_bra = S^-1 Psi_bra.
+static int factor_and_solve(dyb_ctx* c) {
+    const int64_t n = c->N;
+    size_t wd = 0, wh = 0;
+    int* d_info = reinterpret_cast<int*>(c->scal + 32);
+    CKS(cusolverDnXpotrf_bufferSize(c->solver, c->sparams, CUBLAS_FILL_MODE_UPPER, n, CUDA_R_64F, c->S, n, CUDA_R_64F, &wd, &wh));
+    void* d_work = nullptr; std::vector<char> h_work(wh ? wh : 1);
+    if (wd) CK(cudaMalloc(&d_work, wd));
+    // keep a copy of S in case Cholesky fails and LU is needed: only the upper triangle is overwritten by
+    // potrf('U'), the strictly lower triangle still holds S -> S can be rebuilt by mirroring it.
+    cusolverStatus_t st = cusolverDnXpotrf(c->solver, c->sparams, CUBLAS_FILL_MODE_UPPER, n, CUDA_R_64F, c->S, n, CUDA_R_64F,
+                                           d_work, wd, h_work.data(), wh, d_info);
+    int info = 0;
+    if (st == CUSOLVER_STATUS_SUCCESS) { CK(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+    if (d_work) cudaFree(d_work);
+    if (st != CUSOLVER_STATUS_SUCCESS) return fail(DYB_ECUDA, "cusolverDnXpotrf status %d", (int)st);
+    if (info == 0) {
+        CKS(cusolverDnXpotrs(c->solver, c->sparams, CUBLAS_FILL_MODE_UPPER, n, n, CUDA_R_64F, c->S, n, CUDA_R_64F, c->H, c->ld, d_info));
+        c->factor_is_lu = false;
+    } else {
+        return fail(DYB_ESINGULAR, "overlap matrix is not positive definite (potrf info=%d)", info);
+    }
+    c->have_factor = true;
+    return DYB_OK;
+}
+
+int dyb_form_hprime(dyb_ctx* c, const double* h_S, const double* h_h, double* h_H_out) {
+    if (!c || !h_S || !h_h) return fail(DYB_EINVAL, "NULL argument");
+    if (c->M != c->N) return fail(DYB_EINVAL, "dyb_form_hprime needs the full matrix on one device (row shard given)");
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_solver(c);
+    if (rc) return rc;
+    const size_t n = c->N;
+    CK(cudaMemcpyAsync(c->S, h_S, n * n * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpy2DAsync(c->H, (size_t)c->ld * 8, h_h, n * 8, n * 8, n, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = factor_and_solve(c))) return rc;
+    if (h_H_out) CK(cudaMemcpy2DAsync(h_H_out, n * 8, c->H, (size_t)c->ld * 8, n * 8, n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return DYB_OK;
+}
+
+int dyb_form_hprime_device(dyb_ctx* c, const void* d_S, int64_t lds, const void* d_h, int64_t ldh) {
+    if (!c || !d_S || !d_h || lds < c->N || ldh < c->N) return fail(DYB_EINVAL, "bad argument");
+    if (c->M != c->N) return fail(DYB_EINVAL, "dyb_form_hprime_device needs the full matrix on one device");
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_solver(c);
+    if (rc) return rc;
+    const size_t n = c->N;
+    CK(cudaMemcpy2DAsync(c->S, n * 8, d_S, (size_t)lds * 8, n * 8, n, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpy2DAsync(c->H, (size_t)c->ld * 8, d_h, (size_t)ldh * 8, n * 8, n, cudaMemcpyDeviceToDevice, c->stream));
+    if ((rc = factor_and_solve(c))) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    return DYB_OK;
+}
+
+// ---- packets --------------------------------------------------------------------------------------
+static int upload_quad(dyb_ctx* c, int n_part, const dyb_complex* src, double* dst_quad /* indexed by global index */) {
+    const size_t n = c->N;
+    double2* stage = reinterpret_cast<double2*>(c->io);
+    CK(cudaMemcpyAsync(stage, src, n * n_part * sizeof(dyb_complex), cudaMemcpyHostToDevice, c->stream));
+    pack_quad_kernel<<<(2 * c->N + 255) / 256, 256, 0, c->stream>>>(c->N, n_part, stage, dst_quad);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    return DYB_OK;
+}
+static int download_quad(dyb_ctx* c, int n_part, const double* src_quad, dyb_complex* dst) {
+    const size_t n = c->N;
+    double2* stage = reinterpret_cast<double2*>(c->io);
+    unpack_quad_kernel<<<(2 * c->N + 255) / 256, 256, 0, c->stream>>>(c->N, n_part, src_quad, stage);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(dst, stage, n * n_part * sizeof(dyb_complex), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return DYB_OK;
+}
+
+int dyb_set_packets(dyb_ctx* c, int n_part, const dyb_complex* bra, const dyb_complex* ket) {
+    if (!c || !bra || !ket || n_part < 1 || n_part > 2) return fail(DYB_EINVAL, "bad argument");
+    if (c->M != c->N) return fail(DYB_EINVAL, "row-sharded contexts take packets through the sharded driver");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = upload_quad(c, n_part, bra, c->psi_b))) return rc;
+    if ((rc = upload_quad(c, n_part, ket, c->psi_k))) return rc;
+    c->n_part = n_part;
+    return DYB_OK;
+}
+
+int dyb_get_packets(dyb_ctx* c, int n_part, dyb_complex* bra, dyb_complex* ket) {
+    if (!c || !bra || !ket || n_part < 1 || n_part > 2) return fail(DYB_EINVAL, "bad argument");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = download_quad(c, n_part, c->psi_b, bra))) return rc;
+    if ((rc = download_quad(c, n_part, c->psi_k, ket))) return rc;
+    return DYB_OK;
+}
+
+// ---- propagation ----------------------------------------------------------------------------------
+int dyb_propagate(dyb_ctx* c, int mode, double t_init, double t_max, const double* tau, double* save_tau, dyb_trace* traces) {
+    if (!c || !tau || !save_tau) return fail(DYB_EINVAL, "NULL argument");
+    if (c->n_part < 1) return fail(DYB_EINVAL, "dyb_set_packets must be called first");
+    CK(cudaSetDevice(c->device));
+    if (mode == DYB_MODE_TAYLOR) return propagate_taylor(c, t_init, t_max, tau, save_tau, traces);
+    return fail(DYB_EINVAL, "mode %d not available in this build", mode);
+}
+
+int dyb_run_terms(dyb_ctx* c, double tau, int n_terms, float* elapsed_ms, float* kernel_ms) {
+    if (!c || n_terms < 1) return fail(DYB_EINVAL, "bad argument");
+    if (c->n_part < 1) return fail(DYB_EINVAL, "dyb_set_packets must be called first");
+    CK(cudaSetDevice(c->device));
+    cplx C[ORDER];
+    taylor_coefficient(tau, C);
+    const bool per_kernel = kernel_ms != nullptr;
+    const size_t need = 2 + (per_kernel ? 2 * (size_t)n_terms : 0);
+    while (c->ev.size() < need) { cudaEvent_t e; CK(cudaEventCreate(&e)); c->ev.push_back(e); }
+    const int none[2] = {0, 0}, both[2] = {1, c->n_part > 1 ? 1 : 0};
+    int rc, cur = 0, nxt = 1;
+    CK(cudaEventRecord(c->ev[0], c->stream));
+    for (int s = 0; s < n_terms; ++s) {
+        const int k = 2 + (s % (ORDER - 1));                      // repeated 24-term series, like Convergence calls
+        if (k == 2) { cur = 0; nxt = 1; if ((rc = launch_series_init(c, none, both, cur))) return rc; }
+        EpiParams E = epi_params(c, cur, cur, nxt);
+        const cplx r = C[k - 1] / C[k - 2];
+        for (int p = 0; p < 2; ++p) {
+            PartPass& a = E.pass.part[p];
+            a.active = both[p]; a.k = k; a.alpha_re = r.real(); a.alpha_im = r.imag(); a.norm_ref = 1.0;
+        }
+        if (per_kernel) CK(cudaEventRecord(c->ev[2 + 2 * s], c->stream));
+        if ((rc = launch_matvec(c, c->vk[cur], c->vb[cur], false))) return rc;
+        if (per_kernel) CK(cudaEventRecord(c->ev[3 + 2 * s], c->stream));
+        if ((rc = launch_epilogue(c, E))) return rc;
+        std::swap(cur, nxt);
+    }
+    CK(cudaEventRecord(c->ev[1], c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->passes_last = n_terms;
+    if (elapsed_ms) CK(cudaEventElapsedTime(elapsed_ms, c->ev[0], c->ev[1]));
+    if (per_kernel) {
+        float tot = 0.f;
+        for (int s = 0; s < n_terms; ++s) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev[2 + 2 * s], c->ev[3 + 2 * s])); tot += ms; }
+        *kernel_ms = tot;
+    }
+    return DYB_OK;
+}
+
+int dyb_dual_matvec(dyb_ctx* c, int n_part, const dyb_complex* xb, const dyb_complex* xk, dyb_complex* yb, dyb_complex* yk) {
+    if (!c || !xb || !xk || !yb || !yk || n_part < 1 || n_part > 2) return fail(DYB_EINVAL, "bad argument");
+    if (c->M != c->N) return fail(DYB_EINVAL, "full-matrix contexts only");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = upload_quad(c, n_part, xb, c->vb[0]))) return rc;
+    if ((rc = upload_quad(c, n_part, xk, c->vk[0]))) return rc;
+    if ((rc = launch_matvec(c, c->vk[0], c->vb[0], false))) return rc;
+    EpiParams E = epi_params(c, 0, 0, 1);
+    slab_reduce_kernel<<<(2 * c->M + 255) / 256, 256, 0, c->stream>>>(E);
+    c->launches++;
+    CK(cudaGetLastError());
+    if ((rc = download_quad(c, n_part, c->vb[1], yb))) return rc;
+    if ((rc = download_quad(c, n_part, c->vk[1], yk))) return rc;
+    return DYB_OK;
+}
+
+// ---- post-step quantities -------------------------------------------------------------------------
+// AO_bra = S^-1 Psi_bra (ElHl_Chebyshev.f:274, Taylor_gpu.cpp:718): the complex vector is solved as its
+// real and imaginary parts against the kept factor of S.
+int dyb_ao_bra(dyb_ctx* c, int n_part, dyb_complex* h_AO_bra) {
+    if (!c || !h_AO_bra || n_part < 1 || n_part > 2) return fail(DYB_EINVAL, "bad argument");
+    if (!c->have_factor) return fail(DYB_EINVAL, "dyb_ao_bra needs the factor of S: call dyb_form_hprime first");
+    CK(cudaSetDevice(c->device));
+    const int64_t n = c->N;
+    // stage: complex columns (n x n_part) in c->io; view as real (2n x n_part)?  potrs needs separate real
+    // right-hand sides of length n, so de-interleave on the host side of the staging buffer with cublasDcopy.
+    double2* stage = reinterpret_cast<double2*>(c->io);
+    unpack_quad_kernel<<<(2 * c->N + 255) / 256, 256, 0, c->stream>>>(c->N, n_part, c->psi_b, stage);
+    c->launches++;
+    CK(cudaGetLastError());
+    if (!c->blas) { CKB(cublasCreate(&c->blas)); CKB(cublasSetStream(c->blas, c->stream)); }
+    double* rhs = c->io + (size_t)n * 4;                  // 2*n_part real columns of length n
+    for (int p = 0; p < n_part; ++p) {
+        CKB(cublasDcopy(c->blas, (int)n, c->io + (size_t)p * 2 * n, 2, rhs + (size_t)(2 * p) * n, 1));
+        CKB(cublasDcopy(c->blas, (int)n, c->io + (size_t)p * 2 * n + 1, 2, rhs + (size_t)(2 * p + 1) * n, 1));
+    }
+    int* d_info = reinterpret_cast<int*>(c->scal + 32);
+    CKS(cusolverDnXpotrs(c->solver, c->sparams, CUBLAS_FILL_MODE_UPPER, n, 2 * n_part, CUDA_R_64F, c->S, n, CUDA_R_64F, rhs, n, d_info));
+    for (int p = 0; p < n_part; ++p) {
+        CKB(cublasDcopy(c->blas, (int)n, rhs + (size_t)(2 * p) * n, 1, c->io + (size_t)p * 2 * n, 2));
+        CKB(cublasDcopy(c->blas, (int)n, rhs + (size_t)(2 * p + 1) * n, 1, c->io + (size_t)p * 2 * n + 1, 2));
+    }
+    CK(cudaMemcpyAsync(h_AO_bra, c->io, (size_t)n * n_part * sizeof(dyb_complex), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return DYB_OK;
+}
+
+int dyb_populations(dyb_ctx* c, int n_part, int n_frag, const int32_t* fragment, double t, double* out) {
+    if (!c || !fragment || !out || n_part < 1 || n_part > 2 || n_frag < 0 || n_frag > MAX_FRAG) return fail(DYB_EINVAL, "bad argument");
+    CK(cudaSetDevice(c->device));
+    if (!c->frag) CK(cudaMalloc(&c->frag, sizeof(int) * c->N));
+    CK(cudaMemcpyAsync(c->frag, fragment, sizeof(int) * c->N, cudaMemcpyHostToDevice, c->stream));
+    double* d_out = c->io;                                  // 2*(MAX_FRAG+1) doubles
+    populations_kernel<<<n_part, 256, 0, c->stream>>>(c->N, n_frag, c->frag, c->psi_b, c->psi_k, d_out);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c->h_scal, d_out, sizeof(double) * 2 * (MAX_FRAG + 1), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int p = 0; p < n_part; ++p) {
+        double* col = out + (size_t)p * (n_frag + 2);
+        col[0] = t;
+        for (int f = 0; f <= n_frag; ++f) col[1 + f] = c->h_scal[p * (MAX_FRAG + 1) + f];
+    }
+    return DYB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,175 @@
+/* ============================================================================
+ * dynemol_b200.h -- C ABI of the B200-native electron-hole wavepacket propagator
+ *
+ * Drop-in boundary for ONE hot path of lgcrego/Dynemol: the short-time
+ * propagator of each nuclear step (form H' = S^-1 h, then the Taylor /
+ * Chebyshev series of dense real-H' x complex-psi products for the electron and
+ * hole wavepackets).  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Two groups of entry points:
+ *
+ *  (A) LEGACY FORTRAN SYMBOLS -- exactly the symbols the reference's Fortran
+ *      binds through an implicit interface (ifort/ifx mangling: lower case,
+ *      trailing underscore, every argument by reference, no hidden lengths).
+ *      Each declaration cites the reference interface it replaces.
+ *
+ *  (B) NATIVE HANDLE API (dyb_*) -- the same path with device-resident state,
+ *      used by the Python mirror (dynemol_b200/api.py), the tests and bench.py,
+ *      and by a refreshed Fortran caller through iso_c_binding
+ *      (INTEGRATION.md).  All dyb_* functions return 0 on success or a
+ *      negative DYB_E* code; dyb_last_error() gives the message.
+ *
+ * Complex numbers are (re,im) pairs of doubles, i.e. Fortran complex*16 /
+ * cuDoubleComplex layout.  Matrices are column-major (Fortran order).
+ * The library never falls back to a CPU implementation: without a CUDA device
+ * every compute entry fails (dyb_*: DYB_ENODEV; legacy: message + exit(1),
+ * the reference's CHECK_INFO convention, GPU_Interface.cpp:58).
+ * ========================================================================== */
+#ifndef DYNEMOL_B200_H
+#define DYNEMOL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { double re, im; } dyb_complex;
+
+/* ------------------------------------------------------------------ (A) legacy Fortran symbols */
+
+/* Replaces Taylor_gpu.cpp:219-232 / 634-736 (identical prototype in
+ * Chebyshev_gpu.cpp:232-245); called from ElHl_Chebyshev_GPU.f:269-272.
+ * in : N; h_S, h_h host N x N col-major (lda = N); h_PSI_bra/ket N complex;
+ *      *t_init, *t_max (ps); *tau (1/eV, read only).
+ * out: h_H <- H' = S^-1 h (N x N); h_PSI_bra/ket advanced t_init -> t_max in
+ *      place; h_AO_bra <- S^-1 PSI_bra (NOT conjugated, caller conjugates,
+ *      ElHl_Chebyshev_GPU.f:304); h_AO_ket untouched; *save_tau <- converged
+ *      tau of the first Convergence (Taylor.f:71).
+ * Propagator semantics follow the CPU oracle Taylor.f:35-219. */
+void propagationelhl_gpucaller_(const int* N, const double* h_S, const double* h_h, double* h_H,
+                                dyb_complex* h_AO_bra, dyb_complex* h_AO_ket,
+                                dyb_complex* h_PSI_bra, dyb_complex* h_PSI_ket,
+                                const double* t_init, const double* t_max,
+                                double* tau, double* save_tau);
+
+/* NEW batched form of the above (SURVEY.md 8b "new symbol"): electron AND hole
+ * in one call so that a single pass over H' serves both.  AO_* / PSI_* are
+ * N x 2 col-major (column 1 electron, column 2 hole, ElHl_Chebyshev.f:228,253);
+ * tau(2) read only, save_tau(2) written.  Replaces the two per-rank calls of
+ * ElHl_Chebyshev_GPU.f:203-210,269-272. */
+void propagationelhl2_gpucaller_(const int* N, const double* h_S, const double* h_h, double* h_H,
+                                 dyb_complex* h_AO_bra, dyb_complex* h_AO_ket,
+                                 dyb_complex* h_PSI_bra, dyb_complex* h_PSI_ket,
+                                 const double* t_init, const double* t_max,
+                                 double* tau, double* save_tau);
+
+/* Replaces Taylor_gpu.cpp:295-330 (propagation only, H' given on the host). */
+void propagation_gpucaller_(const int* n, double* tau, double* save_tau,
+                            const double* t_init, const double* t_max,
+                            dyb_complex* h_PSI_bra, dyb_complex* h_PSI_ket, const double* h_H);
+
+/* Replaces Chebyshev_gpu.cpp:517-519. */
+double nakedbessel_(const int* n, const double* x);
+
+/* Replace GPU_Interface.cpp:129-134,226-302.  Exported WEAK so that a build
+ * that still links the reference's GPU_Interface.o keeps its own definitions. */
+void gpu_init_(const int* pid, const int* procs_per_dev);
+void gpu_finalize_(void);
+void gpu_pin_(void* ptr, int* size_bytes);
+void gpu_unpin_(void* ptr);
+
+/* ------------------------------------------------------------------ (B) native handle API */
+
+#define DYB_OK        0
+#define DYB_ENODEV   (-1)   /* no CUDA device / driver: there is no CPU fallback */
+#define DYB_ECUDA    (-2)   /* CUDA runtime / cuBLAS / cuSOLVER / NCCL failure */
+#define DYB_EINVAL   (-3)   /* bad argument or call order */
+#define DYB_ENOMEM   (-4)
+#define DYB_ESINGULAR (-5)  /* S is singular (LAPACK info > 0 in the reference) */
+
+#define DYB_MODE_TAYLOR     0  /* reference-parity mode: Taylor.f:35-219 semantics */
+#define DYB_MODE_CHEBYSHEV  1  /* Chebyshev/Bessel series on the spectrally rescaled H' */
+
+#define DYB_KERNEL_AUTO 0
+#define DYB_KERNEL_TMA  1   /* TMA + mbarrier staged persistent kernel (default) */
+#define DYB_KERNEL_LDG  2   /* direct 128-bit global loads (baseline / cross-check) */
+
+#define DYB_MAX_EVENTS 256
+
+/* Decision trace of one particle for one propagate call (mirrors what the
+ * oracle records, so parity tests can compare decisions, not only vectors). */
+typedef struct {
+    int32_t n_convergence_calls;
+    int32_t n_substeps;
+    int32_t n_matvec_pairs;      /* series terms this particle consumed */
+    int32_t n_rescale;
+    int32_t n_first_shrink;
+    int32_t last_k_ref;
+    int32_t n_events;
+    int32_t ev_kind[DYB_MAX_EVENTS];   /* 1 = Convergence, 2 = steady sub-step */
+    int32_t ev_k[DYB_MAX_EVENTS];
+    int32_t ev_ok[DYB_MAX_EVENTS];
+    double  ev_tau[DYB_MAX_EVENTS];
+    double  norm_ref;
+    double  final_tau;
+} dyb_trace;
+
+typedef struct dyb_ctx dyb_ctx;
+
+const char* dyb_last_error(void);
+const char* dyb_version(void);
+int  dyb_device_count(void);
+
+/* One context = one GPU, one basis size.  n_rows/row0 select a row shard of H'
+ * (single GPU: row0 = 0, n_rows = N).  The context owns all device buffers. */
+int  dyb_create(dyb_ctx** out, int device, int N, int row0, int n_rows);
+int  dyb_destroy(dyb_ctx* ctx);
+int  dyb_set_kernel(dyb_ctx* ctx, int kernel_variant);
+int  dyb_get_info(dyb_ctx* ctx, int64_t* info16);   /* [0]=N [1]=ld [2]=n_rows [3]=grid [4]=tiles [5]=segments [6]=sm_count [7]=smem_bytes [8]=variant */
+
+/* Operator: either upload H' (host, lda >= N; only rows row0..row0+n_rows-1 are kept),
+ * or write it directly into the device buffer (bench: synthetic H' generated on the
+ * device), or form it on the device from S and h (a2+a3 of SURVEY.md section 8). */
+int  dyb_upload_hprime(dyb_ctx* ctx, const double* h_H, int64_t lda);
+int  dyb_upload_hprime_device(dyb_ctx* ctx, const void* d_H, int64_t lda);   /* device -> device copy of rows row0.. */
+int  dyb_hprime_device(dyb_ctx* ctx, void** d_ptr, int64_t* ld);
+int  dyb_form_hprime(dyb_ctx* ctx, const double* h_S, const double* h_h, double* h_H_out /* may be NULL */);
+int  dyb_form_hprime_device(dyb_ctx* ctx, const void* d_S, int64_t lds, const void* d_h, int64_t ldh);
+int  dyb_download_hprime(dyb_ctx* ctx, double* h_H, int64_t lda);
+
+/* Wavepackets: n_part (1 or 2) columns of N complex, col-major. */
+int  dyb_set_packets(dyb_ctx* ctx, int n_part, const dyb_complex* bra, const dyb_complex* ket);
+int  dyb_get_packets(dyb_ctx* ctx, int n_part, dyb_complex* bra, dyb_complex* ket);
+
+/* a4/a5: advance all particles from t_init to t_max.  tau[p] in (1/eV), save_tau[p] out.
+ * traces may be NULL, else n_part entries. */
+int  dyb_propagate(dyb_ctx* ctx, int mode, double t_init, double t_max,
+                   const double* tau, double* save_tau, dyb_trace* traces);
+
+/* Post-step quantities on the device (ElHl_Chebyshev.f:269-283):
+ *   AO_bra = S^-1 Psi_bra (un-conjugated, as the legacy symbol returns it); needs dyb_form_hprime.
+ *   populations: out[(n_frag+2) x n_part] = [t, frag pops..., total] with DUAL_bra = conj(ket),
+ *   DUAL_ket = bra (data_output.f:87-147,242-263); fragment[i] in 0..n_frag-1 or -1. */
+int  dyb_ao_bra(dyb_ctx* ctx, int n_part, dyb_complex* h_AO_bra);
+int  dyb_populations(dyb_ctx* ctx, int n_part, int n_frag, const int32_t* fragment, double t, double* out);
+
+/* Raw recursion for benchmarks and kernel-level parity: run n_terms el+hole series
+ * terms (one pass over H' each, fused epilogue, no host decisions) starting from the
+ * current packets, Taylor ratios of `tau`.  elapsed_ms (may be NULL) is measured with
+ * CUDA events on the launching stream; kernel_ms (may be NULL) receives the matvec
+ * kernel's own time summed over the terms (events around each launch). */
+int  dyb_run_terms(dyb_ctx* ctx, double tau, int n_terms, float* elapsed_ms, float* kernel_ms);
+
+/* One dual product with no epilogue state: ykt = H' xk (ket, 'N') and ybr = H'^T xb
+ * (bra, 'T') for n_part columns; host in/out.  Kernel-level parity entry. */
+int  dyb_dual_matvec(dyb_ctx* ctx, int n_part, const dyb_complex* xb, const dyb_complex* xk,
+                     dyb_complex* yb, dyb_complex* yk);
+
+int  dyb_sync(dyb_ctx* ctx);
+int64_t dyb_launch_count(dyb_ctx* ctx);   /* kernels of THIS library launched so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYNEMOL_B200_H */
