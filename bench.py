@@ -161,6 +161,8 @@ def run_ours_single(args):
     N = args.basis or 16384
     P, Psi_bra, Psi_ket, build_info = build_single_gpu(N)
     P.set_packets(Psi_bra, Psi_ket)
+    if args.kernel == "ldg":
+        P.set_kernel(api.KERNEL_LDG)
     tau = pick_tau(N)
     info = P.info()
 
@@ -185,12 +187,30 @@ def run_ours_single(args):
     peak, peak_src = measured_peak_gbs()
     achieved = alg_bytes / k_avg_s / 1e9
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": recorded_traffic(N), "kernel": "dual_matvec_tma_kernel", "kernel_avg_us": round(k_avg_s * 1e6, 2),
+                "traffic": recorded_traffic(N), "kernel": "dual_matvec_%s_kernel" % args.kernel, "kernel_avg_us": round(k_avg_s * 1e6, 2),
                 "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "kernel_share_of_step": round(kms / ms2, 4)}
 
     # e2e: the reference-facing call sequence with HOST buffers (propagation_gpucaller_ semantics, Taylor_gpu.cpp:295-330):
     # H' and packets start in pinned host memory, H2D + full propagation of one nuclear step + D2H inside the timed region.
+    if args.skip_e2e:
+        e2e = None
+    else:
+        e2e = run_e2e(args, P, N, Psi_bra, Psi_ket)
+    cpu = None if args.skip_cpu else cpu_baseline(np.asfortranarray(P.download_hprime()), Psi_bra, Psi_ket, tau, budget_s=args.cpu_budget)
+
+    line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic EHT Hamiltonian N=%d basis, el+hole packets, 1xB200" % N, "basis": N,
+                       "terms_per_step": TERMS_PER_STEP, "l2": "inputs larger than L2 (H' = %.2f GB per pass)" % (alg_bytes / 1e9),
+                       "kernel_variant": args.kernel, "grid": info["grid"], "tiles": info["tiles"], "build": build_info},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+    print(json.dumps(line))
+
+
+def run_e2e(args, P, N, Psi_bra, Psi_ket):
+    import torch
     Hp_host = torch.empty((N, N), dtype=torch.float64, pin_memory=True)
     Hp_np = Hp_host.numpy().T                                       # Fortran-ordered view of the pinned buffer
     Hp_np[...] = P.download_hprime()
@@ -211,17 +231,7 @@ def run_ours_single(args):
            "call": "upload_hprime(host)+set_packets(host)+propagate(Taylor, dt=%g ps)+get_packets(host)" % dt_e2e,
            "terms_per_call": passes // e2e_steps, "s_per_call": round(t_e2e / e2e_steps, 4)}
 
-    # CPU baseline beside it: the oracle's fixed-term kernel (4 dzgemv per el+hole term like the reference's two MPI ranks)
-    cpu = cpu_baseline(Hp_np, Psi_bra, Psi_ket, tau, budget_s=args.cpu_budget)
-
-    line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic EHT Hamiltonian N=%d basis, el+hole packets, 1xB200" % N, "basis": N,
-                       "terms_per_step": TERMS_PER_STEP, "l2": "inputs larger than L2 (H' = %.2f GB per pass)" % (alg_bytes / 1e9),
-                       "kernel_variant": "tma", "grid": info["grid"], "tiles": info["tiles"], "build": build_info},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
-    print(json.dumps(line))
+    return e2e
 
 
 def cpu_baseline(Hp_np, Psi_bra, Psi_ket, tau, budget_s=15.0):
@@ -284,6 +294,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--ref-terms-per-step", type=int, default=2)
+    ap.add_argument("--kernel", default="tma", choices=["tma", "ldg"])
+    ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: no CPU baseline leg")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: no end-to-end leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -31,26 +31,38 @@ struct EpiParams {
 struct Cx { double re, im; };
 __device__ __forceinline__ Cx cmul(Cx a, Cx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
 
-// fixed-order slab sums for owned row i, particle pp
-__device__ __forceinline__ void reduce_slabs(const EpiParams& E, int i, int pp, Cx& hk, Cx& hb) {
+// Fixed-order sum of `n` slab entries spaced `stride` doubles apart.  Loads are issued in batches of 8
+// (independent, latency overlapped) and added strictly in slab order, so the result does not depend on
+// the batching.
+__device__ __forceinline__ Cx slab_sum(const double* __restrict__ base, size_t stride, int n) {
+    double re = 0.0, im = 0.0;
+    for (int s = 0; s < n; s += 8) {
+        double2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (s + u < n) v[u] = __ldcg(reinterpret_cast<const double2*>(base + (size_t)(s + u) * stride));
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (s + u < n) { re += v[u].x; im += v[u].y; }
+    }
+    return {re, im};
+}
+
+// H' x_ket at owned row i (sum over the panel's segments) / H'^T x_bra at global column row0+i (sum over panels)
+__device__ __forceinline__ Cx reduce_ket(const EpiParams& E, int i, int pp) {
     const int panel = i / PANEL_ROWS, il = i % PANEL_ROWS;
     const int s0 = E.pseg_start[panel], s1 = E.pseg_start[panel + 1];
-    double kr = 0.0, ki = 0.0;
-    for (int s = s0; s < s1; ++s) {
-        const double2 v = *reinterpret_cast<const double2*>(E.ket_slab + (((size_t)s * PANEL_ROWS + il) * NQ + 2 * pp));
-        kr += v.x; ki += v.y;
-    }
-    double br = 0.0, bi = 0.0;
-    const size_t col = (size_t)E.row0 + i;
-    for (int p = 0; p < E.n_bra_slabs; ++p) {
-        const double2 v = *reinterpret_cast<const double2*>(E.bra_slab + (((size_t)p * E.Ncpad + col) * NQ + 2 * pp));
-        br += v.x; bi += v.y;
-    }
-    hk = {kr, ki}; hb = {br, bi};
+    return slab_sum(E.ket_slab + (((size_t)s0 * PANEL_ROWS + il) * NQ + 2 * pp), (size_t)PANEL_ROWS * NQ, s1 - s0);
+}
+__device__ __forceinline__ Cx reduce_bra(const EpiParams& E, int i, int pp) {
+    return slab_sum(E.bra_slab + (((size_t)E.row0 + i) * NQ + 2 * pp), (size_t)E.Ncpad * NQ, E.n_bra_slabs);
 }
 
 constexpr int EPI_THREADS = 256;
+constexpr int EPI_ROWS_PER_BLOCK = EPI_THREADS / 4;    // 4 threads per row: (particle, side)
 
+// thread layout: idx = 4*i + 2*pp + side ; side 0 = ket, 1 = bra.  The two sides of one (row, particle) sit in
+// neighbouring lanes and exchange their new sums with one shuffle for the <bra|ket> product.
 __global__ void __launch_bounds__(EPI_THREADS)
 epilogue_kernel(const EpiParams E)
 {
@@ -58,54 +70,60 @@ epilogue_kernel(const EpiParams E)
     __shared__ int    is_last;
 
     const int idx = blockIdx.x * EPI_THREADS + threadIdx.x;
-    const int i = idx >> 1, pp = idx & 1;
+    const int i = idx >> 2, pp = (idx >> 1) & 1, side = idx & 1;
     const PartPass pa = E.pass.part[pp];
     const bool live = (i < E.M) && pa.active && !E.ctrl->part[pp].latched;
 
-    double mb = 0.0, mk = 0.0, dr = 0.0, di = 0.0;
+    double mx = 0.0;            // |new - old| of this thread's side
+    Cx nw = {0.0, 0.0};         // new running sum of this thread's side
     if (live) {
-        Cx hk, hb;
-        reduce_slabs(E, i, pp, hk, hb);
+        const Cx hx = side ? reduce_bra(E, i, pp) : reduce_ket(E, i, pp);
         const Cx alpha = {pa.alpha_re, pa.alpha_im};
-        Cx yk = cmul(alpha, hk), yb = cmul(alpha, hb);
-        const size_t ob = (size_t)i * NQ + 2 * pp;                       // owned-row slot (bra side, sums)
-        const size_t ok = ((size_t)E.row0 + i) * NQ + 2 * pp;            // global-column slot (ket vectors)
+        Cx y = cmul(alpha, hx);
+        const size_t ob = (size_t)i * NQ + 2 * pp;                       // owned-row slot (bra vectors, both sums)
+        const size_t og = ((size_t)E.row0 + i) * NQ + 2 * pp;            // global-column slot (ket vectors)
+        const size_t ov = side ? ob : og;
+        const double* cur = side ? E.cur_b : E.cur_k;
+        const double* prv = side ? E.prv_b : E.prv_k;
+        double* nxt = side ? E.nxt_b : E.nxt_k;
+        double* sum = side ? E.sum_b : E.sum_k;
         if (pa.three_term) {
             const Cx beta = {pa.beta_re, pa.beta_im};
-            const double2 ck = *reinterpret_cast<const double2*>(E.cur_k + ok);
-            const double2 cb = *reinterpret_cast<const double2*>(E.cur_b + ob);
-            const double2 pk = *reinterpret_cast<const double2*>(E.prv_k + ok);
-            const double2 pb = *reinterpret_cast<const double2*>(E.prv_b + ob);
-            const Cx bk = cmul(beta, {ck.x, ck.y}), bb = cmul(beta, {cb.x, cb.y});
-            yk.re += bk.re + pa.gamma * pk.x; yk.im += bk.im + pa.gamma * pk.y;
-            yb.re += bb.re + pa.gamma * pb.x; yb.im += bb.im + pa.gamma * pb.y;
+            const double2 c = *reinterpret_cast<const double2*>(cur + ov);
+            const double2 pv = *reinterpret_cast<const double2*>(prv + ov);
+            const Cx bc = cmul(beta, {c.x, c.y});
+            y.re += bc.re + pa.gamma * pv.x; y.im += bc.im + pa.gamma * pv.y;
         }
-        *reinterpret_cast<double2*>(E.nxt_k + ok) = make_double2(yk.re, yk.im);
-        *reinterpret_cast<double2*>(E.nxt_b + ob) = make_double2(yb.re, yb.im);
-
-        Cx tk = yk, tb = yb;
-        if (pa.scale_term) { const Cx c = {pa.c_re, pa.c_im}; tk = cmul(c, yk); tb = cmul(c, yb); }
-        const double2 sk = *reinterpret_cast<const double2*>(E.sum_k + ob);
-        const double2 sb = *reinterpret_cast<const double2*>(E.sum_b + ob);
-        const Cx nk = {sk.x + tk.re, sk.y + tk.im}, nb = {sb.x + tb.re, sb.y + tb.im};   // new = old + term
-        *reinterpret_cast<double2*>(E.sum_k + ob) = make_double2(nk.re, nk.im);
-        *reinterpret_cast<double2*>(E.sum_b + ob) = make_double2(nb.re, nb.im);
-        mk = hypot(nk.re - sk.x, nk.im - sk.y);                          // abs(new - old), Taylor.f:300
-        mb = hypot(nb.re - sb.x, nb.im - sb.y);
-        dr = nb.re * nk.re + nb.im * nk.im;                              // conj(bra)*ket, dotc
-        di = nb.re * nk.im - nb.im * nk.re;
+        *reinterpret_cast<double2*>(nxt + ov) = make_double2(y.re, y.im);
+        Cx t = y;
+        if (pa.scale_term) t = cmul({pa.c_re, pa.c_im}, y);
+        const double2 so = *reinterpret_cast<const double2*>(sum + ob);
+        nw = {so.x + t.re, so.y + t.im};                                 // new = old + term   (Taylor.f:190-191)
+        *reinterpret_cast<double2*>(sum + ob) = make_double2(nw.re, nw.im);
+        mx = hypot(nw.re - so.x, nw.im - so.y);                          // abs(new - old)      (Taylor.f:300)
     }
-
-    // warp reduction that keeps the lane parity (= particle) separate; fmax ignores NaN like `abs(..)>tol`
+    // partner lane (other side of the same row/particle); idle threads carry zeros
+    const double ore = __shfl_xor_sync(0xffffffffu, nw.re, 1), oim = __shfl_xor_sync(0xffffffffu, nw.im, 1);
+    const double omx = __shfl_xor_sync(0xffffffffu, mx, 1);
+    double mb = 0.0, mk = 0.0, dr = 0.0, di = 0.0;
+    if (side == 0) {                                                     // ket lane owns the pair's contribution
+        mk = mx; mb = omx;
+        dr = ore * nw.re + oim * nw.im;                                  // conj(bra)*ket, dotc (Taylor.f:62,103,197)
+        di = ore * nw.im - oim * nw.re;
+    }
+    // reduce over lanes of equal particle (lane bit 1), sides already merged (lane bit 0)
 #pragma unroll
-    for (int off = 2; off < 32; off <<= 1) {
+    for (int off = 4; off < 32; off <<= 1) {
         mb = fmax(mb, __shfl_xor_sync(0xffffffffu, mb, off));
         mk = fmax(mk, __shfl_xor_sync(0xffffffffu, mk, off));
         dr += __shfl_xor_sync(0xffffffffu, dr, off);
         di += __shfl_xor_sync(0xffffffffu, di, off);
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane < 2) { wpart[warp][lane * 4 + 0] = mb; wpart[warp][lane * 4 + 1] = mk; wpart[warp][lane * 4 + 2] = dr; wpart[warp][lane * 4 + 3] = di; }
+    if (lane == 0 || lane == 2) {
+        const int p = lane >> 1;
+        wpart[warp][p * 4 + 0] = mb; wpart[warp][p * 4 + 1] = mk; wpart[warp][p * 4 + 2] = dr; wpart[warp][p * 4 + 3] = di;
+    }
     __syncthreads();
     if (threadIdx.x < 8) {
         const int t = threadIdx.x;
@@ -122,14 +140,32 @@ epilogue_kernel(const EpiParams E)
     __syncthreads();
     if (!is_last) return;
 
-    // ---- last block: final scalars in block order, then the decision the host used to take per term
+    // ---- last block: final scalars (fixed strided order + fixed tree => deterministic), then the decision
+    //      the host used to take per term
     __threadfence();
-    if (threadIdx.x < 8) {
-        const int t = threadIdx.x;
-        const volatile double* bp = E.blockpart;
-        double v = bp[t];
-        for (unsigned bb = 1; bb < gridDim.x; ++bb) v = ((t & 3) < 2) ? fmax(v, bp[(size_t)bb * 8 + t]) : v + bp[(size_t)bb * 8 + t];
-        wpart[0][t] = v;
+    {
+        __shared__ double fin[EPI_THREADS][8];
+        double v[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        for (unsigned bb = threadIdx.x; bb < gridDim.x; bb += EPI_THREADS) {
+            const double2* bp = reinterpret_cast<const double2*>(E.blockpart + (size_t)bb * 8);
+            const double2 a0 = __ldcg(bp), a1 = __ldcg(bp + 1), a2 = __ldcg(bp + 2), a3 = __ldcg(bp + 3);
+            v[0] = fmax(v[0], a0.x); v[1] = fmax(v[1], a0.y); v[2] += a1.x; v[3] += a1.y;
+            v[4] = fmax(v[4], a2.x); v[5] = fmax(v[5], a2.y); v[6] += a3.x; v[7] += a3.y;
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) fin[threadIdx.x][t] = v[t];
+        __syncthreads();
+        for (int st = EPI_THREADS / 2; st > 0; st >>= 1) {
+            if (threadIdx.x < st) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const double a = fin[threadIdx.x][t], b = fin[threadIdx.x + st][t];
+                    fin[threadIdx.x][t] = ((t & 3) < 2) ? fmax(a, b) : a + b;
+                }
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x < 8) wpart[0][threadIdx.x] = fin[0][threadIdx.x];
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -203,8 +239,7 @@ __global__ void slab_reduce_kernel(const EpiParams E)
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = idx >> 1, pp = idx & 1;
     if (i >= E.M) return;
-    Cx hk, hb;
-    reduce_slabs(E, i, pp, hk, hb);
+    const Cx hk = reduce_ket(E, i, pp), hb = reduce_bra(E, i, pp);
     *reinterpret_cast<double2*>(E.nxt_k + ((size_t)E.row0 + i) * NQ + 2 * pp) = make_double2(hk.re, hk.im);
     *reinterpret_cast<double2*>(E.nxt_b + (size_t)i * NQ + 2 * pp) = make_double2(hb.re, hb.im);
 }

@@ -99,18 +99,29 @@ __device__ __forceinline__ void store_acc(const ConsumerRegs& r, double* __restr
     }
 }
 
-// One column of the thread's 8 rows: 32 FMAs for the ket, 32 for the bra.
+// One column of the thread's 8 rows: 32 FMAs for the ket, 32 for the bra (two independent chains per
+// right-hand side -- even and odd rows -- summed at the end; fixed order, so still deterministic).
 __device__ __forceinline__ void fma_column(ConsumerRegs& r, const double2 (&h)[4], const double (&xk)[NQ], double (&p)[NQ]) {
+    double p1[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        p[q]  = h[0].x * r.xb[0][0][q];
+        p1[q] = h[0].y * r.xb[0][1][q];
+    }
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
             r.acc[m][0][q] = fma(h[m].x, xk[q], r.acc[m][0][q]);
             r.acc[m][1][q] = fma(h[m].y, xk[q], r.acc[m][1][q]);
-            p[q] = fma(h[m].x, r.xb[m][0][q], p[q]);
-            p[q] = fma(h[m].y, r.xb[m][1][q], p[q]);
+            if (m > 0) {
+                p[q]  = fma(h[m].x, r.xb[m][0][q], p[q]);
+                p1[q] = fma(h[m].y, r.xb[m][1][q], p1[q]);
+            }
         }
     }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) p[q] += p1[q];
 }
 
 // =================================================================================================
@@ -124,12 +135,12 @@ constexpr int TMA_THREADS = N_CWARPS * 32;   // 256
 constexpr int RETIRE_LAG  = 2;               // tiles between computing a tile and retiring it
 
 struct TmaSmem {
-    // dynamic shared memory carve-up (base aligned to 1024 B by the kernel)
+    // dynamic shared memory carve-up
     static constexpr int off_bar_full  = TMA_STAGES * STAGE_BYTES;
     static constexpr int off_bar_empty = off_bar_full + TMA_STAGES * 8;
     static constexpr int off_red       = off_bar_empty + TMA_STAGES * 8 + 32;   // keep 16 B alignment
     static constexpr int red_bytes     = RED_SLOTS * N_CWARPS * TILE_COLS * NQ * 8;
-    static constexpr int total         = ((off_red + red_bytes + 127) / 128) * 128 + 1024;  // + alignment slack
+    static constexpr int total         = ((off_red + red_bytes + 127) / 128) * 128;
 };
 
 // tile index inside this CTA -> (panel, column tile)
@@ -151,8 +162,9 @@ dual_matvec_tma_kernel(const __grid_constant__ CUtensorMap tmap, const MatvecPar
 {
     if (P.ctrl != nullptr && P.ctrl->all_latched) return;          // series already decided: skip the pass
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 128 B alignment is all the un-swizzled TMA destinations need; plain pointer arithmetic on the
+    // __shared__ array keeps the address space visible to the compiler (LDS/STS, not generic LD/ST)
+    extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bar_full  = reinterpret_cast<uint64_t*>(smem + TmaSmem::off_bar_full);
     uint64_t* bar_empty = reinterpret_cast<uint64_t*>(smem + TmaSmem::off_bar_empty);
     double*   red       = reinterpret_cast<double*>(smem + TmaSmem::off_red);
@@ -203,7 +215,7 @@ dual_matvec_tma_kernel(const __grid_constant__ CUtensorMap tmap, const MatvecPar
                 double2 h[4];
 #pragma unroll
                 for (int m = 0; m < 4; ++m) h[m] = hp[m * 32];
-                double p[NQ] = {0.0, 0.0, 0.0, 0.0};
+                double p[NQ];
                 fma_column(r, h, xk, p);
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) pv[c * NQ + q] = p[q];
@@ -303,7 +315,7 @@ dual_matvec_ldg_kernel(const MatvecParams P)
             const double2* xp = reinterpret_cast<const double2*>(P.Xk + ((size_t)ct * TILE_COLS + c) * NQ);
             const double2 x01 = __ldg(xp), x23 = __ldg(xp + 1);
             const double xk[NQ] = {x01.x, x01.y, x23.x, x23.y};
-            double p[NQ] = {0.0, 0.0, 0.0, 0.0};
+            double p[NQ];
             fma_column(r, h[c], xk, p);
 #pragma unroll
             for (int q = 0; q < NQ; ++q) pv[c * NQ + q] = p[q];

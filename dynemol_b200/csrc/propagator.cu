@@ -171,7 +171,7 @@ static EpiParams epi_params(dyb_ctx* c, int cur, int prv, int nxt) {
     memset(&E.pass, 0, sizeof E.pass);
     return E;
 }
-static int epi_grid(const dyb_ctx* c) { return (2 * c->M + EPI_THREADS - 1) / EPI_THREADS; }
+static int epi_grid(const dyb_ctx* c) { return (4 * c->M + EPI_THREADS - 1) / EPI_THREADS; }
 
 static int launch_epilogue(dyb_ctx* c, const EpiParams& E) {
     epilogue_kernel<<<epi_grid(c), EPI_THREADS, 0, c->stream>>>(E);
