@@ -76,9 +76,10 @@ DECLARED_SYMBOLS = [
     "propagationelhl_gpucaller_", "propagationelhl2_gpucaller_", "propagation_gpucaller_", "nakedbessel_",
     "gpu_init_", "gpu_finalize_", "gpu_pin_", "gpu_unpin_",
     "dyb_last_error", "dyb_version", "dyb_device_count", "dyb_create", "dyb_destroy", "dyb_set_kernel",
-    "dyb_get_info", "dyb_upload_hprime", "dyb_upload_hprime_device", "dyb_hprime_device", "dyb_form_hprime", "dyb_form_hprime_device",
+    "dyb_get_info", "dyb_upload_hprime", "dyb_upload_hprime_device", "dyb_upload_hprime_rows_device", "dyb_hprime_device", "dyb_form_hprime", "dyb_form_hprime_device",
     "dyb_download_hprime", "dyb_set_packets", "dyb_get_packets", "dyb_propagate", "dyb_ao_bra",
     "dyb_populations", "dyb_run_terms", "dyb_dual_matvec", "dyb_sync", "dyb_launch_count",
+    "dyb_comm_unique_id", "dyb_comm_init",
 ]
 
 
@@ -97,6 +98,12 @@ def _fz(a, copy=True) -> np.ndarray:
 
 def _fd(a) -> np.ndarray:
     return np.asfortranarray(a, dtype=np.float64)
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _check(lib.dyb_comm_unique_id(buf))
+    return buf.raw
 
 
 def device_count() -> int:
@@ -140,6 +147,10 @@ class Propagator:
     def upload_hprime_device(self, d_ptr: int, lda: int):
         """H' from a device buffer (column-major, leading dimension lda), e.g. a torch tensor's data_ptr()."""
         _check(lib.dyb_upload_hprime_device(self._h, C.c_void_p(d_ptr), C.c_int64(lda)))
+
+    def upload_hprime_rows_device(self, d_ptr: int, lda: int, local_row0: int, n_rows: int):
+        """A block of owned rows of H' from a device buffer holding only those rows (n_rows x N, column-major)."""
+        _check(lib.dyb_upload_hprime_rows_device(self._h, C.c_void_p(d_ptr), C.c_int64(lda), C.c_int(local_row0), C.c_int(n_rows)))
 
     def hprime_device(self):
         ptr = C.c_void_p(); ld = C.c_int64()
@@ -212,6 +223,10 @@ class Propagator:
         out = np.zeros((n_frag + 2, self.n_part), dtype=np.float64, order="F")
         _check(lib.dyb_populations(self._h, C.c_int(self.n_part), C.c_int(n_frag), _p(frag), C.c_double(t), _p(out)))
         return out
+
+    def comm_init(self, rank: int, world: int, unique_id: bytes):
+        assert len(unique_id) == 128
+        _check(lib.dyb_comm_init(self._h, C.c_int(rank), C.c_int(world), C.c_char_p(unique_id)))
 
     def sync(self):
         _check(lib.dyb_sync(self._h))

@@ -25,6 +25,9 @@ struct EpiParams {
     double* sum_b; double* sum_k;               // running series sums (owned rows)
     double* blockpart;            // [grid][8] per-block partial scalars
     Ctrl*   ctrl;
+    int     bra_col0;             // index of owned row 0 inside the bra slab rows (single GPU: row0; sharded: 0)
+    int     defer_decision;       // sharded: write this rank's 8 scalars to scal_out, decide after the all-gather
+    double* scal_out;
     PassParams pass;
 };
 
@@ -55,7 +58,32 @@ __device__ __forceinline__ Cx reduce_ket(const EpiParams& E, int i, int pp) {
     return slab_sum(E.ket_slab + (((size_t)s0 * PANEL_ROWS + il) * NQ + 2 * pp), (size_t)PANEL_ROWS * NQ, s1 - s0);
 }
 __device__ __forceinline__ Cx reduce_bra(const EpiParams& E, int i, int pp) {
-    return slab_sum(E.bra_slab + (((size_t)E.row0 + i) * NQ + 2 * pp), (size_t)E.Ncpad * NQ, E.n_bra_slabs);
+    return slab_sum(E.bra_slab + (((size_t)E.bra_col0 + i) * NQ + 2 * pp), (size_t)E.Ncpad * NQ, E.n_bra_slabs);
+}
+
+// The per-term decision the reference takes on the host (Taylor.f:194-207 inside Convergence, :102-105 in
+// the steady loop), from the 8 reduced scalars v = {max_b, max_k, dot_re, dot_im} x {el, hl}.
+__device__ __forceinline__ void apply_decision(Ctrl* c, const PassParams& pass, const double* v) {
+    for (int p = 0; p < 2; ++p) {
+        const PartPass q = pass.part[p];
+        PartState& st = c->part[p];
+        if (!q.active || st.latched) continue;
+        st.n_terms += 1;
+        st.max_b = v[p * 4 + 0]; st.max_k = v[p * 4 + 1];
+        st.dot_re = v[p * 4 + 2]; st.dot_im = v[p * 4 + 3];
+        st.norm = hypot(st.dot_re, st.dot_im);
+        const bool norm_ok = fabs(st.norm - q.norm_ref) < TOL_NORM;                    // Taylor.f:104,199
+        if (q.check_conv) {
+            const bool conv = !(st.max_b > TOL_TERM) && !(st.max_k > TOL_TERM);        // Taylor.f:194-195
+            if (conv && norm_ok) { st.latched = 1; st.ok = 1; st.k_exit = q.k; }
+            else if (q.last)     { st.latched = 1; st.ok = 0; st.k_exit = 0; }
+        } else if (q.last) {
+            st.latched = 1; st.ok = (q.last_ok_by_norm ? (norm_ok ? 1 : 0) : 1); st.k_exit = q.k;
+        }
+    }
+    c->all_latched = (c->part[0].latched && c->part[1].latched) ? 1 : 0;
+    c->block_counter = 0u;
+    __threadfence();
 }
 
 constexpr int EPI_THREADS = 256;
@@ -169,27 +197,14 @@ epilogue_kernel(const EpiParams E)
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        Ctrl* c = E.ctrl;
-        for (int p = 0; p < 2; ++p) {
-            const PartPass q = E.pass.part[p];
-            PartState& st = c->part[p];
-            if (!q.active || st.latched) continue;
-            st.n_terms += 1;
-            st.max_b = wpart[0][p * 4 + 0]; st.max_k = wpart[0][p * 4 + 1];
-            st.dot_re = wpart[0][p * 4 + 2]; st.dot_im = wpart[0][p * 4 + 3];
-            st.norm = hypot(st.dot_re, st.dot_im);
-            const bool norm_ok = fabs(st.norm - q.norm_ref) < TOL_NORM;                    // Taylor.f:104,199
-            if (q.check_conv) {
-                const bool conv = !(st.max_b > TOL_TERM) && !(st.max_k > TOL_TERM);        // Taylor.f:194-195
-                if (conv && norm_ok) { st.latched = 1; st.ok = 1; st.k_exit = q.k; }
-                else if (q.last)     { st.latched = 1; st.ok = 0; st.k_exit = 0; }
-            } else if (q.last) {
-                st.latched = 1; st.ok = (q.last_ok_by_norm ? (norm_ok ? 1 : 0) : 1); st.k_exit = q.k;
-            }
+        if (E.defer_decision) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) E.scal_out[t] = wpart[0][t];
+            E.ctrl->block_counter = 0u;
+            __threadfence();
+        } else {
+            apply_decision(E.ctrl, E.pass, wpart[0]);
         }
-        c->all_latched = (c->part[0].latched && c->part[1].latched) ? 1 : 0;
-        c->block_counter = 0u;
-        __threadfence();
     }
 }
 
@@ -231,6 +246,28 @@ __global__ void series_init_kernel(const InitParams I)
         I.ctrl->all_latched = (I.active[0] || I.active[1]) ? 0 : 1;
         I.ctrl->block_counter = 0u;
     }
+}
+
+// ---- row-sharded H': sum this rank's bra panels into one full-length partial vector (reduce-scatter input)
+__global__ void bra_panel_reduce_kernel(int n_cols, int n_panels, int Ncpad, const double* __restrict__ bra_slab, double* __restrict__ out)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // one double2 (particle) of one column
+    if (idx >= 2 * n_cols) return;
+    const Cx v = slab_sum(bra_slab + (size_t)idx * 2, (size_t)Ncpad * NQ, n_panels);
+    *reinterpret_cast<double2*>(out + (size_t)idx * 2) = make_double2(v.re, v.im);
+}
+
+// ---- row-sharded H': combine the per-rank scalars (rank order => identical on every rank) and decide
+__global__ void decide_kernel(int world, const double* __restrict__ scal_all, Ctrl* ctrl, const PassParams pass)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double v[8];
+    for (int t = 0; t < 8; ++t) {
+        double a = scal_all[t];
+        for (int r = 1; r < world; ++r) a = ((t & 3) < 2) ? fmax(a, scal_all[r * 8 + t]) : a + scal_all[r * 8 + t];
+        v[t] = a;
+    }
+    apply_decision(ctrl, pass, v);
 }
 
 // ---- plain slab reduction into quad vectors (kernel-level parity entry dyb_dual_matvec)

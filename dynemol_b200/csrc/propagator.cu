@@ -13,8 +13,12 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+
 #include <cublas_v2.h>
 #include <cusolverDn.h>
+#include <nccl.h>       // types only: the library is bound with dlopen so that a process that already loaded
+                        // torch's bundled libnccl.so.2 keeps using that one copy
 
 #include "../../include/dynemol_b200.h"
 #include "common.cuh"
@@ -42,6 +46,36 @@ static int fail(int code, const char* fmt, ...) {
     return fail(DYB_ECUDA, "%s:%d %s: cublas status %d", __FILE__, __LINE__, #call, (int)s_); } while (0)
 #define CKS(call) do { cusolverStatus_t s_ = (call); if (s_ != CUSOLVER_STATUS_SUCCESS) \
     return fail(DYB_ECUDA, "%s:%d %s: cusolver status %d", __FILE__, __LINE__, #call, (int)s_); } while (0)
+
+// ------------------------------------------------------------------------------------------ NCCL (lazy)
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char*  (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+    if (g_nccl.h) return DYB_OK;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(DYB_ECUDA, "cannot load libnccl.so.2: %s", dlerror());
+#define NSYM(field, name) do { *(void**)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) return fail(DYB_ECUDA, "libnccl lacks %s", name); } while (0)
+    NSYM(GetUniqueId, "ncclGetUniqueId"); NSYM(CommInitRank, "ncclCommInitRank"); NSYM(CommDestroy, "ncclCommDestroy");
+    NSYM(GetErrorString, "ncclGetErrorString"); NSYM(AllReduce, "ncclAllReduce"); NSYM(ReduceScatter, "ncclReduceScatter");
+    NSYM(AllGather, "ncclAllGather"); NSYM(GroupStart, "ncclGroupStart"); NSYM(GroupEnd, "ncclGroupEnd");
+#undef NSYM
+    g_nccl.h = h;
+    return DYB_OK;
+}
+#define CKN(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) \
+    return fail(DYB_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_)); } while (0)
 
 // ------------------------------------------------------------------------------------------ context
 struct dyb_ctx {
@@ -74,6 +108,10 @@ struct dyb_ctx {
     cusolverDnHandle_t solver = nullptr;
     cusolverDnParams_t sparams = nullptr;
     std::vector<cudaEvent_t> ev;
+    // row-sharded operation (one process per GPU): NCCL communicator + exchange buffers
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+    double *rs_send = nullptr, *rs_recv = nullptr, *scal_all = nullptr, *full_tmp = nullptr;
 };
 
 static int ensure_device(int device) {
@@ -168,6 +206,11 @@ static EpiParams epi_params(dyb_ctx* c, int cur, int prv, int nxt) {
     E.cur_b = c->vb[cur]; E.cur_k = c->vk[cur]; E.prv_b = c->vb[prv]; E.prv_k = c->vk[prv];
     E.nxt_b = c->vb[nxt]; E.nxt_k = c->vk[nxt]; E.sum_b = c->sum_b; E.sum_k = c->sum_k;
     E.blockpart = c->blockpart; E.ctrl = c->ctrl;
+    E.bra_col0 = c->row0; E.defer_decision = 0; E.scal_out = nullptr;
+    if (c->world > 1) {            // bra partials arrive reduce-scattered: one "slab" holding the owned slice
+        E.bra_slab = c->rs_recv; E.n_bra_slabs = 1; E.bra_col0 = 0;
+        E.defer_decision = 1; E.scal_out = c->scal_all + (size_t)c->rank * 8;
+    }
     memset(&E.pass, 0, sizeof E.pass);
     return E;
 }
@@ -175,6 +218,29 @@ static int epi_grid(const dyb_ctx* c) { return (4 * c->M + EPI_THREADS - 1) / EP
 
 static int launch_epilogue(dyb_ctx* c, const EpiParams& E) {
     epilogue_kernel<<<epi_grid(c), EPI_THREADS, 0, c->stream>>>(E);
+    c->launches++;
+    CK(cudaGetLastError());
+    return DYB_OK;
+}
+
+// One el+hole series term.  Single GPU: dual product + fused epilogue.  Row-sharded: dual product on the local
+// rows, reduce-scatter of the bra partials, epilogue on the owned slice, all-gather of the new ket slice and of
+// the per-rank scalars, replicated decision.
+static int run_term(dyb_ctx* c, const EpiParams& E, int cur, int nxt, bool use_ctrl) {
+    int rc;
+    if ((rc = launch_matvec(c, c->vk[cur], c->vb[cur], use_ctrl))) return rc;
+    if (c->world == 1) return launch_epilogue(c, E);
+    const int n2 = 2 * c->N;
+    bra_panel_reduce_kernel<<<(n2 + 255) / 256, 256, 0, c->stream>>>(c->N, c->NP, c->Ncpad, c->bra_slab, c->rs_send);
+    c->launches++;
+    CK(cudaGetLastError());
+    CKN(g_nccl.ReduceScatter(c->rs_send, c->rs_recv, (size_t)c->M * NQ, ncclDouble, ncclSum, c->comm, c->stream));
+    if ((rc = launch_epilogue(c, E))) return rc;
+    CKN(g_nccl.GroupStart());
+    CKN(g_nccl.AllGather(c->vk[nxt] + (size_t)c->row0 * NQ, c->vk[nxt], (size_t)c->M * NQ, ncclDouble, c->comm, c->stream));
+    CKN(g_nccl.AllGather(c->scal_all + (size_t)c->rank * 8, c->scal_all, 8, ncclDouble, c->comm, c->stream));
+    CKN(g_nccl.GroupEnd());
+    decide_kernel<<<1, 32, 0, c->stream>>>(c->world, c->scal_all, c->ctrl, E.pass);
     c->launches++;
     CK(cudaGetLastError());
     return DYB_OK;
@@ -189,6 +255,8 @@ static int launch_series_init(dyb_ctx* c, const int adopt[2], const int active[2
     series_init_kernel<<<(2 * c->M + 255) / 256, 256, 0, c->stream>>>(I);
     c->launches++;
     CK(cudaGetLastError());
+    if (c->world > 1 && (active[0] || active[1]))     // every rank needs the full starting ket
+        CKN(g_nccl.AllGather(c->vk[cur] + (size_t)c->row0 * NQ, c->vk[cur], (size_t)c->M * NQ, ncclDouble, c->comm, c->stream));
     return DYB_OK;
 }
 
@@ -236,6 +304,7 @@ static int compute_norm_ref(dyb_ctx* c, double out[2]) {
     dotc_kernel<<<1, 1024, 0, c->stream>>>(c->M, c->psi_b, c->psi_k + (size_t)c->row0 * NQ, c->scal);
     c->launches++;
     CK(cudaGetLastError());
+    if (c->world > 1) CKN(g_nccl.AllReduce(c->scal, c->scal, 4, ncclDouble, ncclSum, c->comm, c->stream));
     CK(cudaMemcpyAsync(c->h_scal, c->scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     out[0] = std::abs(cplx(c->h_scal[0], c->h_scal[1]));      // Taylor.f:62
@@ -293,8 +362,7 @@ static int propagate_taylor(dyb_ctx* c, double t_init, double t_max, const doubl
                 a.alpha_re = r.real(); a.alpha_im = r.imag();
                 a.norm_ref = q.norm_ref;
             }
-            if ((rc = launch_matvec(c, c->vk[cur], c->vb[cur], true))) return rc;
-            if ((rc = launch_epilogue(c, E))) return rc;
+            if ((rc = run_term(c, E, cur, nxt, true))) return rc;
             std::swap(cur, nxt);
         }
         if ((rc = read_ctrl(c))) return rc;
@@ -384,6 +452,8 @@ int dyb_destroy(dyb_ctx* c) {
     double** bufs[] = {&c->H, &c->S, &c->psi_b, &c->psi_k, &c->sum_b, &c->sum_k, &c->vb[0], &c->vb[1], &c->vb[2],
                        &c->vk[0], &c->vk[1], &c->vk[2], &c->ket_slab, &c->bra_slab, &c->blockpart, &c->scal, &c->io};
     for (auto b : bufs) if (*b) cudaFree(*b);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (double** b : {&c->rs_send, &c->rs_recv, &c->scal_all, &c->full_tmp}) if (*b) cudaFree(*b);
     if (c->ipiv) cudaFree(c->ipiv);
     if (c->seg_base) cudaFree(c->seg_base);
     if (c->pseg_start) cudaFree(c->pseg_start);
@@ -483,6 +553,15 @@ int dyb_upload_hprime_device(dyb_ctx* c, const void* d_H, int64_t lda) {
     CK(cudaSetDevice(c->device));
     CK(cudaMemcpy2DAsync(c->H, (size_t)c->ld * 8, reinterpret_cast<const double*>(d_H) + c->row0, (size_t)lda * 8,
                          (size_t)c->M * 8, c->N, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->have_factor = false;
+    return DYB_OK;
+}
+
+int dyb_upload_hprime_rows_device(dyb_ctx* c, const void* d_rows, int64_t lda, int local_row0, int n_rows) {
+    if (!c || !d_rows || n_rows < 1 || lda < n_rows || local_row0 < 0 || local_row0 + n_rows > c->M) return fail(DYB_EINVAL, "bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpy2DAsync(c->H + local_row0, (size_t)c->ld * 8, d_rows, (size_t)lda * 8, (size_t)n_rows * 8, c->N, cudaMemcpyDeviceToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->have_factor = false;
     return DYB_OK;
@@ -593,23 +672,70 @@ static int download_quad(dyb_ctx* c, int n_part, const double* src_quad, dyb_com
     return DYB_OK;
 }
 
+// Full host packets in, on every rank.  Ket-type vectors live at their global index on every rank; bra-type
+// vectors are stored by LOCAL row (the dual product consumes x_bra at the shard's rows only).
 int dyb_set_packets(dyb_ctx* c, int n_part, const dyb_complex* bra, const dyb_complex* ket) {
     if (!c || !bra || !ket || n_part < 1 || n_part > 2) return fail(DYB_EINVAL, "bad argument");
-    if (c->M != c->N) return fail(DYB_EINVAL, "row-sharded contexts take packets through the sharded driver");
     CK(cudaSetDevice(c->device));
     int rc;
-    if ((rc = upload_quad(c, n_part, bra, c->psi_b))) return rc;
+    if (c->M == c->N) {
+        if ((rc = upload_quad(c, n_part, bra, c->psi_b))) return rc;
+    } else {
+        if (!c->full_tmp) return fail(DYB_EINVAL, "row-sharded context: call dyb_comm_init first");
+        if ((rc = upload_quad(c, n_part, bra, c->full_tmp))) return rc;
+        CK(cudaMemcpyAsync(c->psi_b, c->full_tmp + (size_t)c->row0 * NQ, (size_t)c->M * NQ * 8, cudaMemcpyDeviceToDevice, c->stream));
+    }
     if ((rc = upload_quad(c, n_part, ket, c->psi_k))) return rc;
+    CK(cudaStreamSynchronize(c->stream));
     c->n_part = n_part;
     return DYB_OK;
 }
 
+// Full host packets out, on every rank (row-sharded: the owned slices are all-gathered first; collective call).
 int dyb_get_packets(dyb_ctx* c, int n_part, dyb_complex* bra, dyb_complex* ket) {
     if (!c || !bra || !ket || n_part < 1 || n_part > 2) return fail(DYB_EINVAL, "bad argument");
     CK(cudaSetDevice(c->device));
     int rc;
-    if ((rc = download_quad(c, n_part, c->psi_b, bra))) return rc;
-    if ((rc = download_quad(c, n_part, c->psi_k, ket))) return rc;
+    if (c->M == c->N) {
+        if ((rc = download_quad(c, n_part, c->psi_b, bra))) return rc;
+        if ((rc = download_quad(c, n_part, c->psi_k, ket))) return rc;
+        return DYB_OK;
+    }
+    if (!c->comm) return fail(DYB_EINVAL, "row-sharded context: call dyb_comm_init first");
+    CKN(g_nccl.AllGather(c->psi_b, c->full_tmp, (size_t)c->M * NQ, ncclDouble, c->comm, c->stream));
+    if ((rc = download_quad(c, n_part, c->full_tmp, bra))) return rc;
+    CKN(g_nccl.AllGather(c->psi_k + (size_t)c->row0 * NQ, c->full_tmp, (size_t)c->M * NQ, ncclDouble, c->comm, c->stream));
+    if ((rc = download_quad(c, n_part, c->full_tmp, ket))) return rc;
+    return DYB_OK;
+}
+
+// ---- row-sharded operation: NCCL communicator (one process per GPU; the unique id travels by the host layer)
+int dyb_comm_unique_id(char* out128) {
+    if (!out128) return fail(DYB_EINVAL, "NULL argument");
+    int rc = nccl_load();
+    if (rc) return rc;
+    ncclUniqueId id;
+    CKN(g_nccl.GetUniqueId(&id));
+    memcpy(out128, id.internal, NCCL_UNIQUE_ID_BYTES);
+    return DYB_OK;
+}
+
+int dyb_comm_init(dyb_ctx* c, int rank, int world, const char* id128) {
+    if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return fail(DYB_EINVAL, "bad argument");
+    if (c->N % world != 0 || c->M != c->N / world || c->row0 != rank * c->M)
+        return fail(DYB_EINVAL, "row sharding must be uniform: N=%d world=%d rank=%d row0=%d n_rows=%d", c->N, world, rank, c->row0, c->M);
+    int rc = nccl_load();
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    ncclUniqueId id;
+    memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
+    CKN(g_nccl.CommInitRank(&c->comm, world, id, rank));
+    c->rank = rank; c->world = world;
+    if ((rc = alloc_zero(&c->rs_send, (size_t)c->Lq * NQ))) return rc;
+    if ((rc = alloc_zero(&c->rs_recv, (size_t)c->Lq * NQ))) return rc;
+    if ((rc = alloc_zero(&c->scal_all, (size_t)world * 8))) return rc;
+    if ((rc = alloc_zero(&c->full_tmp, (size_t)c->Lq * NQ))) return rc;
+    CK(cudaDeviceSynchronize());
     return DYB_OK;
 }
 
@@ -643,10 +769,13 @@ int dyb_run_terms(dyb_ctx* c, double tau, int n_terms, float* elapsed_ms, float*
             PartPass& a = E.pass.part[p];
             a.active = both[p]; a.k = k; a.alpha_re = r.real(); a.alpha_im = r.imag(); a.norm_ref = 1.0;
         }
-        if (per_kernel) CK(cudaEventRecord(c->ev[2 + 2 * s], c->stream));
-        if ((rc = launch_matvec(c, c->vk[cur], c->vb[cur], false))) return rc;
-        if (per_kernel) CK(cudaEventRecord(c->ev[3 + 2 * s], c->stream));
-        if ((rc = launch_epilogue(c, E))) return rc;
+        if (per_kernel) {
+            CK(cudaEventRecord(c->ev[2 + 2 * s], c->stream));
+            if ((rc = launch_matvec(c, c->vk[cur], c->vb[cur], false))) return rc;
+            CK(cudaEventRecord(c->ev[3 + 2 * s], c->stream));
+            if (c->world > 1) return fail(DYB_EINVAL, "per-kernel timing is a single-GPU diagnostic");
+            if ((rc = launch_epilogue(c, E))) return rc;
+        } else if ((rc = run_term(c, E, cur, nxt, false))) return rc;
         std::swap(cur, nxt);
     }
     CK(cudaEventRecord(c->ev[1], c->stream));

@@ -1,0 +1,166 @@
+"""Row-sharded operation over the GPUs of one box: one process per GPU (torchrun), H' split by rows,
+per-term NCCL reduce-scatter (bra partials) + all-gather (new ket slices) inside the C++ driver.
+
+torch.distributed is plumbing here: it ships the NCCL unique id to the ranks, provides the barrier and the
+max-over-ranks of the device-timed region.  Import torch BEFORE dynemol_b200.api in a multi-rank process so
+that the library binds the NCCL copy torch already loaded.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import numpy as np
+
+
+def shard_rows(N: int, world: int, rank: int):
+    """Uniform contiguous row blocks (the reduce-scatter / all-gather need equal counts)."""
+    if N % world != 0:
+        raise ValueError(f"N={N} must be divisible by the number of GPUs ({world})")
+    m = N // world
+    if m % 4 != 0:
+        raise ValueError("rows per GPU must be a multiple of 4 (four orbitals per atom)")
+    return rank * m, m
+
+
+def broadcast_unique_id(dist, make_id, device=None):
+    """Rank 0 creates the 128-byte NCCL id, every rank receives it (works with the gloo and nccl backends)."""
+    import torch
+    buf = torch.zeros(128, dtype=torch.uint8, device=device if device is not None else "cpu")
+    if dist.get_rank() == 0:
+        raw = make_id()
+        buf.copy_(torch.tensor(list(raw), dtype=torch.uint8))
+    dist.broadcast(buf, src=0)
+    return bytes(buf.cpu().tolist())
+
+
+def init_sharded(N: int, dist, local_rank: int):
+    """Create this rank's context (rows rank*N/P ..) and join the NCCL communicator."""
+    import torch
+    from dynemol_b200 import api
+    world, rank = dist.get_world_size(), dist.get_rank()
+    row0, m = shard_rows(N, world, rank)
+    P = api.Propagator(N, device=local_rank, row0=row0, n_rows=m)
+    uid = broadcast_unique_id(dist, api.comm_unique_id, device=torch.device("cuda", local_rank))
+    P.comm_init(rank, world, uid)
+    return P, row0, m
+
+
+def synthetic_packets(N: int):
+    """el on orbitals 0..63, hole on 64..127; unnormalised S-free variant for the throughput configs."""
+    w = 64
+    C = np.zeros((N, 2))
+    C[0:w, 0] = np.random.default_rng(42).normal(size=w)
+    C[w:2 * w, 1] = np.random.default_rng(43).normal(size=w)
+    C /= np.linalg.norm(C, axis=0)
+    Psi = np.asfortranarray(C.astype(np.complex128))
+    return Psi, Psi.copy(order="F")
+
+
+def bench_main(args):
+    import torch
+    import torch.distributed as dist
+    from dynemol_b200 import synthetic as syn
+    import bench as B
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=dev)
+    N = args.basis or 65536
+    P, row0, m = init_sharded(N, dist, local_rank)
+    t0 = time.time()
+    fill_rows(P, N, row0, m, dev)
+    gen_s = time.time() - t0
+    bra, ket = synthetic_packets(N)
+    P.set_packets(bra, ket)
+    tau = B.pick_tau(N)
+    info = P.info()
+
+    for _ in range(max(args.warmup, 3)):
+        P.run_terms(tau, B.TERMS_PER_STEP)
+    dist.barrier(); torch.cuda.synchronize(dev)
+    l0 = P.launch_count()
+    with B.ClockSampler(local_rank) as cs:
+        ms, _ = P.run_terms(tau, B.TERMS_PER_STEP * args.steps)       # CUDA events on the launching stream
+        torch.cuda.synchronize(dev)
+    dist.barrier()
+    launches = P.launch_count() - l0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)                          # max over ranks of the device-timed region
+    ms_max = float(t.item())
+    n_terms = B.TERMS_PER_STEP * args.steps
+    value = n_terms / (ms_max * 1e-3)
+    clocks = cs.result()
+
+    # end-to-end through the host-buffer API: packets from host memory each call, result read back
+    e2e_terms = B.TERMS_PER_STEP * 4
+    dist.barrier(); torch.cuda.synchronize(dev)
+    t1 = time.perf_counter()
+    P.set_packets(bra, ket)
+    P.run_terms(tau, e2e_terms)
+    ob, ok = P.get_packets()
+    torch.cuda.synchronize(dev); dist.barrier()
+    t_e2e = time.perf_counter() - t1
+    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+
+    ref1 = None
+    if rank == 0 and not args.no_ref1:
+        ref1 = single_gpu_same_workload(args, N, dev, tau, bra, ket)
+    dist.barrier()
+
+    if rank == 0:
+        peak, peak_src = B.measured_peak_gbs()
+        per_gpu_bytes = 8.0 * m * N
+        achieved = per_gpu_bytes * n_terms / (ms_max * 1e-3) / 1e9
+        line = {"metric": B.METRIC, "value": round(value, 2), "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "synthetic EHT Hamiltonian N=%d basis, row-sharded H' over %d GPUs, NCCL reduce-scatter(bra)+all-gather(ket) per term" % (N, world),
+                           "basis": N, "rows_per_gpu": m, "terms_per_step": B.TERMS_PER_STEP,
+                           "l2": "inputs larger than L2 (%.2f GB of H' per GPU per pass)" % (per_gpu_bytes / 1e9),
+                           "operator": "Hueckel h as H' surrogate (SURVEY.md 8d)", "grid": info["grid"], "gen_s": round(gen_s, 1)},
+                "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                             "traffic": None, "kernel": "whole term incl. collectives, per GPU", "peak_source": peak_src,
+                             "alg_bytes_per_launch": per_gpu_bytes},
+                "e2e": {"value": round(e2e_terms / float(te.item()), 2), "unit": B.UNIT, "h2d_bytes_per_step": int(2 * 2 * 16 * N),
+                        "d2h_bytes_per_step": int(2 * 2 * 16 * N), "call": "set_packets(host)+%d terms+get_packets(host); H' shards resident" % e2e_terms},
+                "gpu_launches": int(launches), "clocks": clocks, "single_gpu_same_workload": ref1}
+        print(json.dumps(line))
+    dist.destroy_process_group()
+
+
+def fill_rows(P, N, row0, m, dev, blk=4096):
+    """Generate global rows row0..row0+m of the surrogate operator block by block and copy them into P's shard."""
+    import torch
+    from dynemol_b200 import synthetic as syn
+    for r in range(0, m, blk):
+        n = min(blk, m - r)
+        rows = syn.make_h_shard_colmajor_torch(N, row0 + r, n, dev)     # (N, n) = column-major n x N block
+        torch.cuda.synchronize(dev)
+        P.upload_hprime_rows_device(rows.data_ptr(), n, r, n)
+        del rows
+    torch.cuda.empty_cache()
+
+
+def single_gpu_same_workload(args, N, dev, tau, bra, ket):
+    """Strong-scaling denominator measured in the same run: the full N x N operator on rank 0's GPU alone."""
+    import torch
+    from dynemol_b200 import api
+    import bench as B
+    free, _ = torch.cuda.mem_get_info(dev)
+    need = 8.0 * N * N * 1.05 + 6e9
+    if free < need:
+        return {"skipped": "not enough free HBM for the full operator (%.0f GB needed, %.0f free)" % (need / 1e9, free / 1e9)}
+    P1 = api.Propagator(N, device=dev.index)
+    fill_rows(P1, N, 0, N, dev)
+    P1.set_packets(bra, ket)
+    for _ in range(2):
+        P1.run_terms(tau, B.TERMS_PER_STEP)
+    steps = max(2, min(args.steps, 10))
+    ms, _ = P1.run_terms(tau, B.TERMS_PER_STEP * steps)
+    P1.close()
+    return {"n_gpus": 1, "value": round(B.TERMS_PER_STEP * steps / (ms * 1e-3), 2), "unit": B.UNIT, "steps": steps}

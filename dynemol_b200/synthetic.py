@@ -150,44 +150,82 @@ def workload_at(pos: np.ndarray, species: np.ndarray, zeta: float = ZETA):
 
 
 # ----------------------------------------------------------------------------- device-side generation (bench only)
+def overlap_rows_torch(pos, a0: int, a1: int, zeta: float = ZETA):
+    """Rows 4*a0 .. 4*a1-1 of S (all N columns) on pos.device, float64, shape (4*(a1-a0), N)."""
+    import torch
+    n_atoms = pos.shape[0]
+    sz = float(np.sqrt(zeta))
+    eye3 = torch.eye(3, device=pos.device, dtype=torch.float64)
+    R = pos[a0:a1, None, :] - pos[None, :, :]
+    R2 = (R * R).sum(-1)
+    E = torch.exp(-0.5 * zeta * R2)
+    E = torch.where(R2 > CUTOFF_ANGS ** 2, torch.zeros_like(E), E)
+    blk = torch.empty((a1 - a0, 4, n_atoms, 4), device=pos.device, dtype=torch.float64)
+    blk[:, 0, :, 0] = E
+    blk[:, 0, :, 1:] = sz * R * E[..., None]
+    blk[:, 1:, :, 0] = (-sz * R * E[..., None]).permute(0, 2, 1)
+    pp = (eye3[None, None] - zeta * R[..., :, None] * R[..., None, :]) * E[..., None, None]   # [A,B,a,b]
+    blk[:, 1:, :, 1:] = pp.permute(0, 2, 1, 3)
+    out = blk.reshape(4 * (a1 - a0), 4 * n_atoms)
+    # exact unit diagonal / symmetric in exact arithmetic; enforce the diagonal like overlap_numpy does
+    idx = torch.arange(4 * a0, 4 * a1, device=pos.device)
+    out[idx - 4 * a0, idx] = 1.0
+    return out
+
+
+def huckel_rows_torch(S_rows, r0: int, IPt, Kt, Vt):
+    """h rows r0.. for the given S rows: h_ij = X_ij S_ij (hamiltonians.f:33-63)."""
+    r1 = r0 + S_rows.shape[0]
+    c1 = IPt[r0:r1, None] - IPt[None, :]
+    c2 = IPt[r0:r1, None] + IPt[None, :]
+    c3 = (c1 / c2) * (c1 / c2)
+    c4 = (Vt[r0:r1, None] + Vt[None, :]) * 0.5
+    kwh = (Kt[r0:r1, None] + Kt[None, :]) * 0.5
+    k_eff = kwh + c3 + c3 * c3 * (1.0 - kwh)
+    h = (k_eff * c2 * 0.5 + c4) * S_rows
+    import torch
+    idx = torch.arange(r0, r1, device=S_rows.device)
+    h[idx - r0, idx] = IPt[r0:r1] + Vt[r0:r1]        # X_ii * S_ii, S_ii = 1
+    return h
+
+
 def make_S_h_torch(N: int, device, zeta: float = ZETA, row_block: int = 512):
-    """Same recipe on the GPU with torch (input generation is plumbing, not the
-    product): returns column-major-compatible (symmetric) S and h as torch
-    float64 tensors of shape (N,N), plus pos/species/IP arrays (numpy)."""
+    """Same recipe on the GPU with torch (input generation is plumbing, not the product): returns (symmetric)
+    S and h as torch float64 tensors of shape (N,N), plus pos/species/IP arrays (numpy)."""
     import torch
     pos_np, species = lattice(N // 4, 1234 + N)
     IP, k_WH, V_shift = orbital_params(species)
     pos = torch.tensor(pos_np, device=device, dtype=torch.float64)
     n_atoms = pos.shape[0]
+    IPt = torch.tensor(IP, device=device); Kt = torch.tensor(k_WH, device=device); Vt = torch.tensor(V_shift, device=device)
     S = torch.empty((N, N), device=device, dtype=torch.float64)
-    sz = float(np.sqrt(zeta))
-    eye3 = torch.eye(3, device=device, dtype=torch.float64)
+    h = torch.empty_like(S)
     for a0 in range(0, n_atoms, row_block):
         a1 = min(n_atoms, a0 + row_block)
-        R = pos[a0:a1, None, :] - pos[None, :, :]
-        R2 = (R * R).sum(-1)
-        E = torch.exp(-0.5 * zeta * R2)
-        E = torch.where(R2 > CUTOFF_ANGS ** 2, torch.zeros_like(E), E)
-        blk = torch.empty((a1 - a0, 4, n_atoms, 4), device=device, dtype=torch.float64)
-        blk[:, 0, :, 0] = E
-        blk[:, 0, :, 1:] = sz * R * E[..., None]
-        blk[:, 1:, :, 0] = (-sz * R * E[..., None]).permute(0, 2, 1)
-        pp = (eye3[None, None] - zeta * R[..., :, None] * R[..., None, :]) * E[..., None, None]   # [A,B,a,b]
-        blk[:, 1:, :, 1:] = pp.permute(0, 2, 1, 3)
-        S[4 * a0:4 * a1, :] = blk.reshape(4 * (a1 - a0), N)
+        S[4 * a0:4 * a1, :] = overlap_rows_torch(pos, a0, a1, zeta)
     S = 0.5 * (S + S.T)
     S.fill_diagonal_(1.0)
-    IPt = torch.tensor(IP, device=device); Kt = torch.tensor(k_WH, device=device); Vt = torch.tensor(V_shift, device=device)
-    h = torch.empty_like(S)
-    rb = 2048
-    for r0 in range(0, N, rb):
-        r1 = min(N, r0 + rb)
-        c1 = IPt[r0:r1, None] - IPt[None, :]
-        c2 = IPt[r0:r1, None] + IPt[None, :]
-        c3 = (c1 / c2) * (c1 / c2)
-        c4 = (Vt[r0:r1, None] + Vt[None, :]) * 0.5
-        kwh = (Kt[r0:r1, None] + Kt[None, :]) * 0.5
-        k_eff = kwh + c3 + c3 * c3 * (1.0 - kwh)
-        h[r0:r1, :] = (k_eff * c2 * 0.5 + c4) * S[r0:r1, :]
-    h.diagonal().copy_(IPt + Vt)     # X_ii * S_ii, S_ii = 1
+    for a0 in range(0, n_atoms, row_block):
+        a1 = min(n_atoms, a0 + row_block)
+        h[4 * a0:4 * a1, :] = huckel_rows_torch(S[4 * a0:4 * a1, :], 4 * a0, IPt, Kt, Vt)
     return S, h, dict(pos=pos_np, species=species, IP=IP, k_WH=k_WH, V_shift=V_shift)
+
+
+def make_h_shard_colmajor_torch(N: int, row0: int, n_rows: int, device, zeta: float = ZETA, row_block: int = 256):
+    """Rows row0..row0+n_rows-1 of the Hueckel matrix h (all N columns), laid out COLUMN-major with leading
+    dimension n_rows, i.e. as a torch tensor of shape (N, n_rows).  Used as the H' surrogate of the N=65536
+    throughput configs (only throughput is measured there; forming S^-1 h at that size would need
+    a distributed factorisation)."""
+    import torch
+    assert row0 % 4 == 0 and n_rows % 4 == 0
+    pos_np, species = lattice(N // 4, 1234 + N)
+    IP, k_WH, V_shift = orbital_params(species)
+    pos = torch.tensor(pos_np, device=device, dtype=torch.float64)
+    IPt = torch.tensor(IP, device=device); Kt = torch.tensor(k_WH, device=device); Vt = torch.tensor(V_shift, device=device)
+    out = torch.empty((N, n_rows), device=device, dtype=torch.float64)
+    for a0 in range(row0 // 4, (row0 + n_rows) // 4, row_block):
+        a1 = min((row0 + n_rows) // 4, a0 + row_block)
+        S_rows = overlap_rows_torch(pos, a0, a1, zeta)
+        h_rows = huckel_rows_torch(S_rows, 4 * a0, IPt, Kt, Vt)
+        out[:, 4 * a0 - row0:4 * a1 - row0] = h_rows.t()
+    return out

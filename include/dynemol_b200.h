@@ -133,6 +133,9 @@ int  dyb_get_info(dyb_ctx* ctx, int64_t* info16);   /* [0]=N [1]=ld [2]=n_rows [
  * device), or form it on the device from S and h (a2+a3 of SURVEY.md section 8). */
 int  dyb_upload_hprime(dyb_ctx* ctx, const double* h_H, int64_t lda);
 int  dyb_upload_hprime_device(dyb_ctx* ctx, const void* d_H, int64_t lda);   /* device -> device copy of rows row0.. */
+/* device -> device copy of a block of owned rows: source holds ONLY rows local_row0..local_row0+n_rows-1
+ * of the shard (n_rows x N, column-major, lda >= n_rows) */
+int  dyb_upload_hprime_rows_device(dyb_ctx* ctx, const void* d_rows, int64_t lda, int local_row0, int n_rows);
 int  dyb_hprime_device(dyb_ctx* ctx, void** d_ptr, int64_t* ld);
 int  dyb_form_hprime(dyb_ctx* ctx, const double* h_S, const double* h_h, double* h_H_out /* may be NULL */);
 int  dyb_form_hprime_device(dyb_ctx* ctx, const void* d_S, int64_t lds, const void* d_h, int64_t ldh);
@@ -165,6 +168,14 @@ int  dyb_run_terms(dyb_ctx* ctx, double tau, int n_terms, float* elapsed_ms, flo
  * (bra, 'T') for n_part columns; host in/out.  Kernel-level parity entry. */
 int  dyb_dual_matvec(dyb_ctx* ctx, int n_part, const dyb_complex* xb, const dyb_complex* xk,
                      dyb_complex* yb, dyb_complex* yk);
+
+/* Row-sharded H' over the GPUs of one box: one process per GPU, each holding rows
+ * row0..row0+n_rows-1 (uniform: n_rows = N/world, row0 = rank*n_rows).  Rank 0 calls dyb_comm_unique_id, the host
+ * layer ships the 128 bytes to every rank (torch.distributed / MPI), every rank calls dyb_comm_init.  Afterwards
+ * dyb_set_packets / dyb_propagate / dyb_run_terms / dyb_get_packets are collective calls: per term the bra
+ * partials are reduce-scattered and the new ket slices all-gathered with NCCL over NVLink. */
+int  dyb_comm_unique_id(char* out128);
+int  dyb_comm_init(dyb_ctx* ctx, int rank, int world, const char* id128);
 
 int  dyb_sync(dyb_ctx* ctx);
 int64_t dyb_launch_count(dyb_ctx* ctx);   /* kernels of THIS library launched so far */
