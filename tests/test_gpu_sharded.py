@@ -20,7 +20,7 @@ def test_sharded_propagation_matches_oracle(world):
     oracle.build()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tests", "sharded_worker.py")]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=dict(os.environ, DYB_TEST_WATCHDOG="200"))
     lines = [l for l in res.stdout.splitlines() if l.startswith("SHARDED_RESULT ")]
     assert res.returncode == 0 and lines, res.stdout[-2000:] + res.stderr[-2000:]
     out = json.loads(lines[-1][len("SHARDED_RESULT "):])
