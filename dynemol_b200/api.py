@@ -79,7 +79,7 @@ DECLARED_SYMBOLS = [
     "dyb_get_info", "dyb_upload_hprime", "dyb_upload_hprime_device", "dyb_upload_hprime_rows_device", "dyb_hprime_device", "dyb_form_hprime", "dyb_form_hprime_device",
     "dyb_download_hprime", "dyb_set_packets", "dyb_get_packets", "dyb_propagate", "dyb_ao_bra",
     "dyb_populations", "dyb_run_terms", "dyb_dual_matvec", "dyb_sync", "dyb_launch_count",
-    "dyb_comm_unique_id", "dyb_comm_init",
+    "dyb_comm_unique_id", "dyb_comm_init", "dyb_set_spectral_bounds", "dyb_get_spectral_bounds", "dyb_estimate_spectral_bounds",
 ]
 
 
@@ -195,6 +195,15 @@ class Propagator:
         traces = (Trace * 2)()
         _check(lib.dyb_propagate(self._h, C.c_int(mode), C.c_double(t_init), C.c_double(t_max), _p(tau2), _p(save), traces))
         return save[: self.n_part].copy(), [traces[i] for i in range(self.n_part)]
+
+    def set_spectral_bounds(self, emin: float, emax: float):
+        _check(lib.dyb_set_spectral_bounds(self._h, C.c_double(emin), C.c_double(emax)))
+
+    def estimate_spectral_bounds(self, n_iter: int = 40, margin: float = 0.05):
+        """Lanczos (S inner product) from the current packets; returns and stores (emin, emax)."""
+        lo = C.c_double(); hi = C.c_double()
+        _check(lib.dyb_estimate_spectral_bounds(self._h, C.c_int(n_iter), C.c_double(margin), C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
 
     def run_terms(self, tau: float, n_terms: int, per_kernel: bool = False):
         """n_terms el+hole series terms, no host decisions.  Returns (elapsed_ms, matvec_kernel_ms or None)."""

@@ -118,9 +118,12 @@ epilogue_kernel(const EpiParams E)
         if (pa.three_term) {
             const Cx beta = {pa.beta_re, pa.beta_im};
             const double2 c = *reinterpret_cast<const double2*>(cur + ov);
-            const double2 pv = *reinterpret_cast<const double2*>(prv + ov);
             const Cx bc = cmul(beta, {c.x, c.y});
-            y.re += bc.re + pa.gamma * pv.x; y.im += bc.im + pa.gamma * pv.y;
+            y.re += bc.re; y.im += bc.im;
+            if (pa.gamma != 0.0) {                     // first Chebyshev term has no x_prev (buffer may hold anything)
+                const double2 pv = *reinterpret_cast<const double2*>(prv + ov);
+                y.re += pa.gamma * pv.x; y.im += pa.gamma * pv.y;
+            }
         }
         *reinterpret_cast<double2*>(nxt + ov) = make_double2(y.re, y.im);
         Cx t = y;
@@ -213,6 +216,8 @@ epilogue_kernel(const EpiParams E)
 struct InitParams {
     int M, row0, Nc;
     int adopt[2], active[2];
+    int scale_sum[2];                 // Chebyshev: the running sum starts as c_0 * psi instead of psi
+    double s_re[2], s_im[2];
     double* psi_b; double* psi_k;
     double* cur_b; double* cur_k;
     double* sum_b; double* sum_k;
@@ -233,8 +238,14 @@ __global__ void series_init_kernel(const InitParams I)
         if (I.active[pp]) {
             const double2 b = *reinterpret_cast<const double2*>(I.psi_b + ob);
             const double2 k = *reinterpret_cast<const double2*>(I.psi_k + ok);
-            *reinterpret_cast<double2*>(I.cur_b + ob) = b; *reinterpret_cast<double2*>(I.sum_b + ob) = b;
-            *reinterpret_cast<double2*>(I.cur_k + ok) = k; *reinterpret_cast<double2*>(I.sum_k + ob) = k;
+            *reinterpret_cast<double2*>(I.cur_b + ob) = b; *reinterpret_cast<double2*>(I.cur_k + ok) = k;
+            double2 sb = b, sk = k;
+            if (I.scale_sum[pp]) {
+                const Cx c0 = {I.s_re[pp], I.s_im[pp]};
+                const Cx tb = cmul(c0, {b.x, b.y}), tk = cmul(c0, {k.x, k.y});
+                sb = make_double2(tb.re, tb.im); sk = make_double2(tk.re, tk.im);
+            }
+            *reinterpret_cast<double2*>(I.sum_b + ob) = sb; *reinterpret_cast<double2*>(I.sum_k + ob) = sk;
         }
     }
     if (idx == 0) {

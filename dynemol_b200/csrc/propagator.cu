@@ -102,6 +102,8 @@ struct dyb_ctx {
     Ctrl* h_ctrl = nullptr;              // pinned host mirror
     double* h_scal = nullptr;            // pinned, 64 doubles
     int n_part = 0;
+    bool have_bounds = false;
+    double emin = 0.0, emax = 0.0;       // spectral bounds of H' for the Chebyshev mode
     int64_t launches = 0;
     int64_t passes_last = 0;             // el+hole terms (passes over H') of the last propagate / run_terms
     cublasHandle_t blas = nullptr;
@@ -246,10 +248,14 @@ static int run_term(dyb_ctx* c, const EpiParams& E, int cur, int nxt, bool use_c
     return DYB_OK;
 }
 
-static int launch_series_init(dyb_ctx* c, const int adopt[2], const int active[2], int cur) {
+static int launch_series_init(dyb_ctx* c, const int adopt[2], const int active[2], int cur, const cplx* sum_scale = nullptr) {
     InitParams I;
     I.M = c->M; I.row0 = c->row0; I.Nc = c->N;
-    for (int p = 0; p < 2; ++p) { I.adopt[p] = adopt[p]; I.active[p] = active[p]; }
+    for (int p = 0; p < 2; ++p) {
+        I.adopt[p] = adopt[p]; I.active[p] = active[p];
+        I.scale_sum[p] = sum_scale ? 1 : 0;
+        I.s_re[p] = sum_scale ? sum_scale[p].real() : 1.0; I.s_im[p] = sum_scale ? sum_scale[p].imag() : 0.0;
+    }
     I.psi_b = c->psi_b; I.psi_k = c->psi_k; I.cur_b = c->vb[cur]; I.cur_k = c->vk[cur];
     I.sum_b = c->sum_b; I.sum_k = c->sum_k; I.ctrl = c->ctrl;
     series_init_kernel<<<(2 * c->M + 255) / 256, 256, 0, c->stream>>>(I);
@@ -279,12 +285,28 @@ static int taylor_kmax(const cplx* C) {
     return ORDER;
 }
 
-// ------------------------------------------------------------------------------------------ Taylor driver
+// ------------------------------------------------------------------------------------------ series drivers
+// Chebyshev_gpu.cpp:636-643 with the spectral rescaling the reference lacks:
+//   R = de*tau ; c_0 = J_0(R) e^{-i ebar tau} ; c_k = 2 (-i)^k J_k(R) e^{-i ebar tau}
+static void cheb_coefficient(double tau, double ebar, double de, cplx* C) {
+    static const cplx pw[4] = {cplx(1, 0), cplx(0, -1), cplx(-1, 0), cplx(0, 1)};
+    const double R = de * tau;
+    const cplx ph = std::exp(cplx(0.0, -ebar * tau));
+    C[0] = jn(0, R) * ph;
+    for (int k = 1; k < ORDER; ++k) C[k] = (2.0 * jn(k, R)) * pw[k & 3] * ph;
+}
+static double naked_bessel(int n, double x) { return (double)(1 << (n - 2)) * (x * x + 4.0) / pow(x, (double)n); }
+// Chebyshev_gpu.cpp:565-574: first k in 6..24 with |c_k nakedBessel(k,R)| < 1e-20, else 25
+static int cheb_kmax(const cplx* C, double R) {
+    for (int k = 6; k < ORDER; ++k) if (std::abs(C[k] * naked_bessel(k, R)) < 1.0e-20) return k;
+    return ORDER;
+}
+
 struct Particle {
     bool   present = false, done = true;
     int    phase = 0;                 // 0 first Convergence loop, 1 steady sub-steps, 2 rescale Convergence
     double tau = 0, save_tau = 0, t = 0, norm_ref = 0;
-    int    k_ref = 0, k_end = 0;
+    int    k_ref = 0, n_terms = 0;    // n_terms: dual products of the series being run
     bool   check = false;
     cplx   C[ORDER];
     int    shrinks = 0;
@@ -312,58 +334,85 @@ static int compute_norm_ref(dyb_ctx* c, double out[2]) {
     return DYB_OK;
 }
 
-static int propagate_taylor(dyb_ctx* c, double t_init, double t_max, const double* tau_in, double* save_tau, dyb_trace* traces)
+// Fill the epilogue parameters of series step s (0-based) for particle q.
+//   Taylor    (Taylor.f:182-187 / :90-95):  step s produces term k = s+2:  y = (c_k/c_{k-1}) H' x ; sum += y
+//   Chebyshev (Chebyshev_gpu.cpp:552-589):  step s produces phi_j, j = s+1: phi_1 = Ht phi_0, phi_j = 2 Ht phi_{j-1} - phi_{j-2},
+//                                           Ht = (H' - ebar)/de ; sum += c_j phi_j ; tests start at j = 2
+static void fill_pass(PartPass& a, const Particle& q, int mode, int s, double ebar, double de) {
+    memset(&a, 0, sizeof a);
+    a.active = 1; a.norm_ref = q.norm_ref;
+    a.last = (s == q.n_terms - 1) ? 1 : 0;
+    a.last_ok_by_norm = q.check ? 0 : 1;
+    if (mode == DYB_MODE_TAYLOR) {
+        const int k = s + 2;
+        const cplx r = q.C[k - 1] / q.C[k - 2];               // Taylor.f:93,185
+        a.k = k; a.alpha_re = r.real(); a.alpha_im = r.imag();
+        a.check_conv = q.check ? 1 : 0;
+    } else {
+        const int j = s + 1;
+        a.k = j; a.three_term = 1; a.scale_term = 1;
+        a.c_re = q.C[j].real(); a.c_im = q.C[j].imag();
+        if (j == 1) { a.alpha_re = 1.0 / de; a.beta_re = -ebar / de; a.gamma = 0.0; }
+        else        { a.alpha_re = 2.0 / de; a.beta_re = -2.0 * ebar / de; a.gamma = -1.0; }
+        a.check_conv = (q.check && j >= 2) ? 1 : 0;
+    }
+}
+
+// Propagation(): Taylor.f:35-127 (identical control flow in Chebyshev_gpu.cpp:347-485), one state machine per
+// particle, all particles served by the same passes over H'.  Host decisions are taken once per series from
+// the device-side control block; per-term decisions (early exit of Convergence) are taken on the device.
+static int propagate_series(dyb_ctx* c, int mode, double t_init, double t_max, const double* tau_in, double* save_tau, dyb_trace* traces)
 {
     Particle P[2];
     double nref[2];
     int rc = compute_norm_ref(c, nref);
     if (rc) return rc;
+    const double ebar = 0.5 * (c->emax + c->emin), de = 0.5 * (c->emax - c->emin);
     for (int p = 0; p < c->n_part; ++p) {
         P[p].present = true; P[p].done = false; P[p].phase = 0;
         P[p].tau = tau_in[p]; P[p].norm_ref = nref[p]; P[p].t = t_init;
         P[p].tr = traces ? &traces[p] : nullptr;
         if (P[p].tr) { memset(P[p].tr, 0, sizeof(dyb_trace)); P[p].tr->norm_ref = nref[p]; }
     }
+    auto coefficient = [&](Particle& q) {
+        if (mode == DYB_MODE_TAYLOR) taylor_coefficient(q.tau, q.C); else cheb_coefficient(q.tau, ebar, de, q.C);
+    };
     int adopt[2] = {0, 0};
     long guard = 0;
     c->passes_last = 0;
     for (;;) {
         int active[2] = {0, 0};
         int L = 0;
+        cplx sum_scale[2] = {cplx(1, 0), cplx(1, 0)};
         for (int p = 0; p < 2; ++p) {
             Particle& q = P[p];
             if (!q.present || q.done) continue;
             active[p] = 1;
-            if (q.phase == 0 || q.phase == 2) {                   // Convergence(): Taylor.f:163-173
-                taylor_coefficient(q.tau, q.C);
-                q.k_ref = taylor_kmax(q.C);
-                q.k_end = q.k_ref; q.check = true;
-            } else {                                              // steady sub-step: Taylor.f:90
-                q.k_end = q.k_ref; q.check = false;
+            if (q.phase == 0 || q.phase == 2) {                   // Convergence(): Taylor.f:163-173 / Chebyshev_gpu.cpp:556-575
+                coefficient(q);
+                q.k_ref = (mode == DYB_MODE_TAYLOR) ? taylor_kmax(q.C) : cheb_kmax(q.C, de * q.tau);
+                q.check = true;
+            } else {                                              // steady sub-step: Taylor.f:90 / Chebyshev_gpu.cpp:418-425
+                q.check = false;
             }
-            L = std::max(L, q.k_end - 1);
+            q.n_terms = q.k_ref - 1;                              // Taylor: k = 2..k_ref ; Chebyshev: j = 1..k_ref-1
+            if (mode != DYB_MODE_TAYLOR) sum_scale[p] = q.C[0];
+            L = std::max(L, q.n_terms);
         }
         if (!active[0] && !active[1]) break;
         if (++guard > 2000000) return fail(DYB_EINVAL, "propagation does not terminate (tau -> 0?)");
 
-        int cur = 0, nxt = 1;
-        if ((rc = launch_series_init(c, adopt, active, cur))) return rc;
+        int prv = 2, cur = 0, nxt = 1;
+        if ((rc = launch_series_init(c, adopt, active, cur, mode == DYB_MODE_TAYLOR ? nullptr : sum_scale))) return rc;
         adopt[0] = adopt[1] = 0;
         for (int s = 0; s < L; ++s) {
-            const int k = s + 2;                                  // 1-based series index, Taylor.f:182 / :90
-            EpiParams E = epi_params(c, cur, cur, nxt);
+            EpiParams E = epi_params(c, cur, prv, nxt);
             for (int p = 0; p < 2; ++p) {
-                Particle& q = P[p];
-                PartPass& a = E.pass.part[p];
-                if (!active[p] || k > q.k_end) { a.active = 0; continue; }
-                const cplx r = q.C[k - 1] / q.C[k - 2];           // Taylor.f:93,185
-                a.active = 1; a.k = k; a.three_term = 0; a.scale_term = 0;
-                a.check_conv = q.check ? 1 : 0; a.last = (k == q.k_end) ? 1 : 0; a.last_ok_by_norm = q.check ? 0 : 1;
-                a.alpha_re = r.real(); a.alpha_im = r.imag();
-                a.norm_ref = q.norm_ref;
+                if (active[p] && s < P[p].n_terms) fill_pass(E.pass.part[p], P[p], mode, s, ebar, de);
+                else E.pass.part[p].active = 0;
             }
             if ((rc = run_term(c, E, cur, nxt, true))) return rc;
-            std::swap(cur, nxt);
+            const int old_prv = prv; prv = cur; cur = nxt; nxt = old_prv;
         }
         if ((rc = read_ctrl(c))) return rc;
         c->passes_last += std::max(c->h_ctrl->part[0].latched && active[0] ? c->h_ctrl->part[0].n_terms : 0,
@@ -385,7 +434,7 @@ static int propagate_taylor(dyb_ctx* c, double t_init, double t_max, const doubl
                     q.t = t_init + q.tau * H_BAR;                 // Taylor.f:73
                     if (t_max - q.t < q.tau * H_BAR) {            // Taylor.f:75-78
                         q.tau = (t_max - q.t) / H_BAR;
-                        taylor_coefficient(q.tau, q.C);
+                        coefficient(q);
                     }
                     q.phase = 1;
                     if (!(q.t < t_max)) q.done = true;            // Taylor.f:81
@@ -417,7 +466,7 @@ static int propagate_taylor(dyb_ctx* c, double t_init, double t_max, const doubl
                 q.t += q.tau * H_BAR;                             // Taylor.f:116
                 if (t_max - q.t < q.tau * H_BAR) {                // Taylor.f:118-121
                     q.tau = (t_max - q.t) / H_BAR;
-                    taylor_coefficient(q.tau, q.C);
+                    coefficient(q);
                 }
                 if (!(q.t < t_max)) q.done = true;
             }
@@ -744,8 +793,12 @@ int dyb_propagate(dyb_ctx* c, int mode, double t_init, double t_max, const doubl
     if (!c || !tau || !save_tau) return fail(DYB_EINVAL, "NULL argument");
     if (c->n_part < 1) return fail(DYB_EINVAL, "dyb_set_packets must be called first");
     CK(cudaSetDevice(c->device));
-    if (mode == DYB_MODE_TAYLOR) return propagate_taylor(c, t_init, t_max, tau, save_tau, traces);
-    return fail(DYB_EINVAL, "mode %d not available in this build", mode);
+    if (mode == DYB_MODE_TAYLOR) return propagate_series(c, mode, t_init, t_max, tau, save_tau, traces);
+    if (mode == DYB_MODE_CHEBYSHEV) {
+        if (!c->have_bounds) return fail(DYB_EINVAL, "Chebyshev mode needs spectral bounds: dyb_set_spectral_bounds / dyb_estimate_spectral_bounds");
+        return propagate_series(c, mode, t_init, t_max, tau, save_tau, traces);
+    }
+    return fail(DYB_EINVAL, "unknown mode %d", mode);
 }
 
 int dyb_run_terms(dyb_ctx* c, double tau, int n_terms, float* elapsed_ms, float* kernel_ms) {
@@ -804,6 +857,102 @@ int dyb_dual_matvec(dyb_ctx* c, int n_part, const dyb_complex* xb, const dyb_com
     CK(cudaGetLastError());
     if ((rc = download_quad(c, n_part, c->vb[1], yb))) return rc;
     if ((rc = download_quad(c, n_part, c->vk[1], yk))) return rc;
+    return DYB_OK;
+}
+
+// ---- spectral bounds for the Chebyshev mode ---------------------------------------------------------
+int dyb_set_spectral_bounds(dyb_ctx* c, double emin, double emax) {
+    if (!c || !(emax > emin)) return fail(DYB_EINVAL, "need emax > emin");
+    c->emin = emin; c->emax = emax; c->have_bounds = true;
+    return DYB_OK;
+}
+
+int dyb_get_spectral_bounds(dyb_ctx* c, double* emin, double* emax) {
+    if (!c || !emin || !emax) return fail(DYB_EINVAL, "NULL argument");
+    if (!c->have_bounds) return fail(DYB_EINVAL, "no spectral bounds set");
+    *emin = c->emin; *emax = c->emax;
+    return DYB_OK;
+}
+
+// number of eigenvalues of the symmetric tridiagonal (a, b) below x (Sturm sequence)
+static int sturm_count(const std::vector<double>& a, const std::vector<double>& b, double x) {
+    int cnt = 0; double d = 1.0;
+    for (size_t i = 0; i < a.size(); ++i) {
+        d = a[i] - x - (i ? b[i] * b[i] / d : 0.0);
+        if (d == 0.0) d = 1e-300;
+        if (d < 0.0) ++cnt;
+    }
+    return cnt;
+}
+static double tridiag_eig(const std::vector<double>& a, const std::vector<double>& b, int which /*0 = smallest, else largest*/) {
+    double lo = 1e300, hi = -1e300;
+    for (size_t i = 0; i < a.size(); ++i) {
+        const double r = (i ? fabs(b[i]) : 0.0) + (i + 1 < a.size() ? fabs(b[i + 1]) : 0.0);
+        lo = std::min(lo, a[i] - r); hi = std::max(hi, a[i] + r);
+    }
+    const int target = which ? (int)a.size() - 1 : 0;          // index of the wanted eigenvalue
+    for (int it = 0; it < 200; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        if (sturm_count(a, b, mid) > target) hi = mid; else lo = mid;
+    }
+    return 0.5 * (lo + hi);
+}
+
+// Lanczos in the S inner product started from the current packets (w0 = Psi_bra = S v0, v0 = Psi_ket): because
+// H'^T S = S H', the left vectors stay w_j = S v_j and the recurrence is the symmetric one; every step is one
+// dual product (H' v_j and H'^T w_j) of the hot kernel.  Ritz values lie inside the spectrum, hence `margin`
+// (fraction of the width added on both sides).  Vectors live on the host (O(N) work per step).
+int dyb_estimate_spectral_bounds(dyb_ctx* c, int n_iter, double margin, double* emin_out, double* emax_out) {
+    if (!c || n_iter < 2) return fail(DYB_EINVAL, "bad argument");
+    if (c->n_part < 1) return fail(DYB_EINVAL, "dyb_set_packets must be called first (the packets start the Lanczos run)");
+    if (c->M != c->N) return fail(DYB_EINVAL, "row-sharded contexts: pass bounds with dyb_set_spectral_bounds");
+    const int np = c->n_part; const size_t n = c->N;
+    std::vector<dyb_complex> w(n * np), v(n * np), wp(n * np, dyb_complex{0, 0}), vp(n * np, dyb_complex{0, 0}), hw(n * np), hv(n * np);
+    int rc = dyb_get_packets(c, np, w.data(), v.data());
+    if (rc) return rc;
+    auto dotc_re = [&](const dyb_complex* x, const dyb_complex* y) { double s = 0; for (size_t i = 0; i < n; ++i) s += x[i].re * y[i].re + x[i].im * y[i].im; return s; };
+    std::vector<std::vector<double>> al(np), be(np);
+    std::vector<double> beta(np, 0.0);
+    std::vector<bool> alive(np, true);
+    for (int p = 0; p < np; ++p) {
+        const double n0 = dotc_re(&w[p * n], &v[p * n]);
+        if (!(n0 > 0.0)) return fail(DYB_EINVAL, "<bra|ket> of particle %d is not positive: packets are not an S-dual pair", p);
+        const double sc = 1.0 / sqrt(n0);
+        for (size_t i = 0; i < n; ++i) { w[p * n + i].re *= sc; w[p * n + i].im *= sc; v[p * n + i].re *= sc; v[p * n + i].im *= sc; }
+    }
+    for (int j = 0; j < n_iter; ++j) {
+        if ((rc = dyb_dual_matvec(c, np, w.data(), v.data(), hw.data(), hv.data()))) return rc;
+        bool any = false;
+        for (int p = 0; p < np; ++p) {
+            if (!alive[p]) continue;
+            dyb_complex *W = &w[p * n], *V = &v[p * n], *WP = &wp[p * n], *VP = &vp[p * n], *HW = &hw[p * n], *HV = &hv[p * n];
+            const double a = dotc_re(W, HV);
+            al[p].push_back(a); be[p].push_back(beta[p]);
+            double b2 = 0.0;
+            for (size_t i = 0; i < n; ++i) {
+                const dyb_complex nv = {HV[i].re - a * V[i].re - beta[p] * VP[i].re, HV[i].im - a * V[i].im - beta[p] * VP[i].im};
+                const dyb_complex nw = {HW[i].re - a * W[i].re - beta[p] * WP[i].re, HW[i].im - a * W[i].im - beta[p] * WP[i].im};
+                VP[i] = V[i]; WP[i] = W[i]; V[i] = nv; W[i] = nw;
+                b2 += nw.re * nv.re + nw.im * nv.im;
+            }
+            if (!(b2 > 1e-28 * (1.0 + a * a))) { alive[p] = false; continue; }     // invariant subspace reached
+            beta[p] = sqrt(b2);
+            const double sc = 1.0 / beta[p];
+            for (size_t i = 0; i < n; ++i) { V[i].re *= sc; V[i].im *= sc; W[i].re *= sc; W[i].im *= sc; }
+            any = true;
+        }
+        if (!any) break;
+    }
+    double lo = 1e300, hi = -1e300;
+    for (int p = 0; p < np; ++p) {
+        if (al[p].empty()) continue;
+        lo = std::min(lo, tridiag_eig(al[p], be[p], 0)); hi = std::max(hi, tridiag_eig(al[p], be[p], 1));
+    }
+    if (!(hi > lo)) return fail(DYB_EINVAL, "Lanczos produced a degenerate interval");
+    const double width = hi - lo;
+    c->emin = lo - margin * width; c->emax = hi + margin * width; c->have_bounds = true;
+    if (emin_out) *emin_out = c->emin;
+    if (emax_out) *emax_out = c->emax;
     return DYB_OK;
 }
 

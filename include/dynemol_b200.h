@@ -150,6 +150,14 @@ int  dyb_get_packets(dyb_ctx* ctx, int n_part, dyb_complex* bra, dyb_complex* ke
 int  dyb_propagate(dyb_ctx* ctx, int mode, double t_init, double t_max,
                    const double* tau, double* save_tau, dyb_trace* traces);
 
+/* Chebyshev mode (DYB_MODE_CHEBYSHEV): the reference's un-linked Chebyshev series (Chebyshev_gpu.cpp:347-485,
+ * 524-643) on the spectrally rescaled operator (H' - ebar)/de; needs bounds [emin, emax] that enclose the
+ * spectrum of H'.  Either pass them, or estimate them with n_iter Lanczos steps (each one pass of the dual
+ * product) started from the current packets; `margin` widens the Ritz interval by that fraction on both sides. */
+int  dyb_set_spectral_bounds(dyb_ctx* ctx, double emin, double emax);
+int  dyb_get_spectral_bounds(dyb_ctx* ctx, double* emin, double* emax);
+int  dyb_estimate_spectral_bounds(dyb_ctx* ctx, int n_iter, double margin, double* emin, double* emax);
+
 /* Post-step quantities on the device (ElHl_Chebyshev.f:269-283):
  *   AO_bra = S^-1 Psi_bra (un-conjugated, as the legacy symbol returns it); needs dyb_form_hprime.
  *   populations: out[(n_frag+2) x n_part] = [t, frag pops..., total] with DUAL_bra = conj(ket),

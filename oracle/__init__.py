@@ -251,6 +251,23 @@ def cheb_convergence(H, bra, ket, tau, norm_ref):
     return bool(ok), bra, ket, Cc, k_ref.value, k_exit.value
 
 
+def cheb_scaled_coefficient(tau: float, ebar: float, de: float) -> np.ndarray:
+    out = np.zeros(ORDER, dtype=np.complex128)
+    lib().orc_cheb_scaled_coefficient(C.c_double(tau), C.c_double(ebar), C.c_double(de), _cp(out))
+    return out
+
+
+def cheb_scaled_propagation(H, bra, ket, t_init, t_max, tau, ebar, de):
+    """Chebyshev mode of the product (rescaled Chebyshev_gpu.cpp:347-485).  Returns (bra, ket, tau_out, save_tau, Trace)."""
+    H = _fd(H); n = H.shape[0]
+    bra = _fz(bra); ket = _fz(ket)
+    tau_io = C.c_double(tau); save_tau = C.c_double(0.0)
+    tr = Trace()
+    lib().orc_cheb_scaled_propagation(C.c_int(n), _cp(H), C.c_int(n), _cp(bra), _cp(ket), C.c_double(t_init), C.c_double(t_max),
+                                      C.byref(tau_io), C.byref(save_tau), C.c_double(ebar), C.c_double(de), C.byref(tr))
+    return bra, ket, tau_io.value, save_tau.value, tr
+
+
 def num_threads() -> int:
     return lib().orc_num_threads()
 

@@ -589,6 +589,136 @@ int orc_cheb_convergence(int N, const double* H, int ldh, cplx* Psi_bra, cplx* P
     return ok;
 }
 
+// ===========================================================================
+// "Chebyshev mode" of the product = the reference's un-linked Chebyshev driver
+// (Chebyshev_gpu.cpp:347-485 chebyshev_gpu + :524-632 convergence_gpu) made valid
+// for any tau by the spectral rescaling the reference omits:
+//     Ht = (H' - ebar)/de ,  spectrum of Ht inside [-1,1]
+//     exp(-i tau H') = exp(-i ebar tau) * sum_k a_k(R) T_k(Ht),  R = de*tau,
+//     a_0 = J_0(R), a_k = 2 (-i)^k J_k(R)            (Chebyshev_gpu.cpp:636-643 with R for tau)
+// Control flow, order (25), tolerances and the tau schedule are the reference's
+// (identical to Taylor.f:35-127, which Chebyshev_gpu.cpp:396-470 mirrors).
+// Deliberate choices where the un-linked GPU code and the CPU oracle disagree
+// (follow the CPU): the term test uses the complex modulus
+// with "> tol means not converged" (Taylor.f:290-303), not Idamax + "<".
+// With ebar = 0, de = 1 this is the reference's series itself.
+// ===========================================================================
+static void cheb_scaled_coefficient(double tau, double ebar, double de, cplx* c)
+{
+    static const cplx pw[4] = { cplx(1, 0), cplx(0, -1), cplx(-1, 0), cplx(0, 1) };   // (-i)^k
+    const double R = de * tau;
+    const cplx ph = std::exp(cplx(0.0, -ebar * tau));
+    c[0] = jn(0, R) * ph;
+    for (int k = 1; k < ORDER; ++k) c[k] = (2.0 * jn(k, R)) * pw[k & 3] * ph;
+}
+
+static int cheb_scaled_kmax(const cplx* c, double R)
+{
+    for (int k = 6; k < ORDER; ++k)                                   // Chebyshev_gpu.cpp:565-574
+        if (std::abs(c[k] * orc_naked_bessel(k, R)) < 1.0e-20) return k;
+    return ORDER;
+}
+
+// y = Ht x  for op 'N' / 'T'
+static void apply_ht(char op, int N, const double* H, int ldh, double ebar, double de, const cplx* x, cplx* y)
+{
+    dzgemv(op, N, cplx(1.0, 0.0), H, ldh, x, y);
+    for (int i = 0; i < N; ++i) y[i] = (y[i] - ebar * x[i]) / de;
+}
+
+void orc_cheb_scaled_coefficient(double tau, double ebar, double de, cplx* c) { cheb_scaled_coefficient(tau, ebar, de, c); }
+
+int orc_cheb_scaled_convergence(int N, const double* H, int ldh, cplx* Psi_bra, cplx* Psi_ket, cplx* C, int* k_ref,
+                                double tau, double norm_ref, double ebar, double de, int* k_exit, orc_trace* tr)
+{
+    std::vector<cplx> b0(Psi_bra, Psi_bra + N), k0(Psi_ket, Psi_ket + N), b1(N), k1(N), b2(N), k2(N);
+    std::vector<cplx> sb(N), sk(N), nb(N), nk(N);
+    int ok = 0, kx = 0;
+    if (k_exit) *k_exit = 0;
+    cheb_scaled_coefficient(tau, ebar, de, C);
+    const int k_max = cheb_scaled_kmax(C, de * tau);
+    *k_ref = k_max;
+    apply_ht('T', N, H, ldh, ebar, de, b0.data(), b1.data());
+    apply_ht('N', N, H, ldh, ebar, de, k0.data(), k1.data());
+    if (tr) tr->n_matvec_pairs++;
+    for (int i = 0; i < N; ++i) { sb[i] = C[0] * b0[i] + C[1] * b1[i]; sk[i] = C[0] * k0[i] + C[1] * k1[i]; }
+    for (int k = 2; k < k_max; ++k) {
+        apply_ht('T', N, H, ldh, ebar, de, b1.data(), b2.data());
+        apply_ht('N', N, H, ldh, ebar, de, k1.data(), k2.data());
+        if (tr) tr->n_matvec_pairs++;
+        for (int i = 0; i < N; ++i) { b2[i] = 2.0 * b2[i] - b0[i]; k2[i] = 2.0 * k2[i] - k0[i]; }
+        for (int i = 0; i < N; ++i) { nb[i] = sb[i] + C[k] * b2[i]; nk[i] = sk[i] + C[k] * k2[i]; }
+        if (is_converged(N, nb.data(), sb.data(), ERROR_TOL) && is_converged(N, nk.data(), sk.data(), ERROR_TOL)) {
+            const double nrm = std::abs(dotc(N, nb.data(), nk.data()));
+            if (std::fabs(nrm - norm_ref) < NORM_ERROR) {
+                std::copy(nb.begin(), nb.end(), Psi_bra); std::copy(nk.begin(), nk.end(), Psi_ket);
+                ok = 1; kx = k; if (k_exit) *k_exit = k;
+                break;
+            }
+        }
+        sb.swap(nb); sk.swap(nk);
+        b0.swap(b1); b1.swap(b2); k0.swap(k1); k1.swap(k2);
+    }
+    if (tr) { tr->n_convergence_calls++; tr->last_k_ref = k_max; }
+    trace_event(tr, 1, kx, ok, tau);
+    return ok;
+}
+
+void orc_cheb_scaled_propagation(int N, const double* H, int ldh, cplx* Psi_bra, cplx* Psi_ket,
+                                 double t_init, double t_max, double* tau_io, double* save_tau,
+                                 double ebar, double de, orc_trace* tr)
+{
+    std::vector<cplx> C(ORDER);
+    std::vector<cplx> b0(N), k0(N), b1(N), k1(N), b2(N), k2(N), sb(N), sk(N);
+    double tau = *tau_io;
+    int k_ref = 0;
+    if (tr) std::memset(tr, 0, sizeof(*tr));
+    const double norm_ref = std::abs(dotc(N, Psi_bra, Psi_ket));
+    if (tr) tr->norm_ref = norm_ref;
+    for (;;) {                                                         // Chebyshev_gpu.cpp:388-393
+        int ok = orc_cheb_scaled_convergence(N, H, ldh, Psi_bra, Psi_ket, C.data(), &k_ref, tau, norm_ref, ebar, de, nullptr, tr);
+        if (ok) break;
+        tau *= 0.9;
+        if (tr) tr->n_first_shrink++;
+    }
+    *save_tau = tau;                                                   // :396
+    double t = t_init + tau * H_BAR;
+    if (t_max - t < tau * H_BAR) { tau = (t_max - t) / H_BAR; cheb_scaled_coefficient(tau, ebar, de, C.data()); }   // :399-403
+    while (t < t_max) {                                                // :407
+        std::copy(Psi_bra, Psi_bra + N, b0.begin()); std::copy(Psi_ket, Psi_ket + N, k0.begin());
+        apply_ht('T', N, H, ldh, ebar, de, b0.data(), b1.data());      // :418-419
+        apply_ht('N', N, H, ldh, ebar, de, k0.data(), k1.data());
+        if (tr) tr->n_matvec_pairs++;
+        for (int i = 0; i < N; ++i) { sb[i] = C[0] * b0[i] + C[1] * b1[i]; sk[i] = C[0] * k0[i] + C[1] * k1[i]; }
+        for (int k = 2; k < k_ref; ++k) {                              // :421-425
+            apply_ht('T', N, H, ldh, ebar, de, b1.data(), b2.data());
+            apply_ht('N', N, H, ldh, ebar, de, k1.data(), k2.data());
+            if (tr) tr->n_matvec_pairs++;
+            for (int i = 0; i < N; ++i) { b2[i] = 2.0 * b2[i] - b0[i]; k2[i] = 2.0 * k2[i] - k0[i]; }
+            for (int i = 0; i < N; ++i) { sb[i] += C[k] * b2[i]; sk[i] += C[k] * k2[i]; }
+            b0.swap(b1); b1.swap(b2); k0.swap(k1); k1.swap(k2);
+        }
+        const double nrm = std::abs(dotc(N, sb.data(), sk.data()));    // :443-444
+        if (tr) tr->n_substeps++;
+        if (std::fabs(nrm - norm_ref) < NORM_ERROR) {
+            std::copy(sb.begin(), sb.end(), Psi_bra); std::copy(sk.begin(), sk.end(), Psi_ket);
+            trace_event(tr, 2, k_ref, 1, tau);
+        } else {
+            trace_event(tr, 2, k_ref, 0, tau);
+            int ok = 0;
+            while (!ok) {                                              // :453-461
+                tau *= 0.975;
+                if (tr) tr->n_rescale++;
+                ok = orc_cheb_scaled_convergence(N, H, ldh, Psi_bra, Psi_ket, C.data(), &k_ref, tau, norm_ref, ebar, de, nullptr, tr);
+            }
+        }
+        t += tau * H_BAR;                                              // :464
+        if (t_max - t < tau * H_BAR) { tau = (t_max - t) / H_BAR; cheb_scaled_coefficient(tau, ebar, de, C.data()); }
+    }
+    *tau_io = tau;
+    if (tr) tr->final_tau = tau;
+}
+
 // introspection for the tests
 int    orc_order(void)      { return ORDER; }
 double orc_h_bar(void)      { return H_BAR; }

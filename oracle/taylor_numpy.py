@@ -142,3 +142,93 @@ def pop_slater(fragment, bra, ket, n_frag):
     out = [np.sum(prod[fragment == f]).real for f in range(n_frag)]
     out.append(np.sum(prod).real)
     return np.array(out)
+
+
+# ----------------------------------------------------------------------------- Chebyshev mode (product spec)
+def cheb_coefficient(tau, ebar, de):
+    """Chebyshev_gpu.cpp:636-643 with R = de*tau for tau and the phase of the spectral shift."""
+    from scipy.special import jv
+    R = de * tau
+    k = np.arange(ORDER)
+    c = 2.0 * jv(k, R) * (-1j) ** k * np.exp(-1j * ebar * tau)
+    c[0] *= 0.5
+    return c
+
+
+def _naked_bessel(n, x):
+    return float(1 << (n - 2)) * (x * x + 4.0) / x ** n      # Chebyshev_gpu.cpp:517
+
+
+def cheb_convergence(Hp, bra, ket, tau, norm_ref, ebar, de, log=None):
+    """Rescaled Chebyshev_gpu.cpp:524-632 with the CPU oracle's term test (see elhl_oracle.cpp)."""
+    C = cheb_coefficient(tau, ebar, de)
+    R = de * tau
+    k_max = ORDER
+    for k in range(6, ORDER):
+        if abs(C[k] * _naked_bessel(k, R)) < 1.0e-20:
+            k_max = k
+            break
+    ht = lambda x: (Hp @ x - ebar * x) / de
+    htT = lambda x: (Hp.T @ x - ebar * x) / de
+    b0, k0 = bra, ket
+    b1, k1 = htT(b0), ht(k0)
+    if log is not None:
+        log["matvec_pairs"] = log.get("matvec_pairs", 0) + 1
+    sb = C[0] * b0 + C[1] * b1; sk = C[0] * k0 + C[1] * k1
+    for k in range(2, k_max):
+        b2 = 2.0 * htT(b1) - b0; k2 = 2.0 * ht(k1) - k0
+        if log is not None:
+            log["matvec_pairs"] += 1
+        nb = sb + C[k] * b2; nk = sk + C[k] * k2
+        if _is_converged(nb, sb, ERROR) and _is_converged(nk, sk, ERROR):
+            if abs(abs(np.vdot(nb, nk)) - norm_ref) < NORM_ERROR:
+                return True, nb, nk, C, k_max, k
+        sb, sk = nb, nk
+        b0, b1, k0, k1 = b1, b2, k1, k2
+    return False, bra, ket, C, k_max, 0
+
+
+def cheb_propagation(Hp, bra, ket, t_init, t_max, tau, ebar, de, log=None):
+    """Rescaled Chebyshev_gpu.cpp:347-485 (same control flow as Taylor.f:35-127)."""
+    if log is None:
+        log = {}
+    log.setdefault("events", [])
+    norm_ref = abs(np.vdot(bra, ket))
+    while True:
+        ok, bra, ket, C, k_ref, k_exit = cheb_convergence(Hp, bra, ket, tau, norm_ref, ebar, de, log)
+        log["events"].append((1, k_exit, int(ok), tau))
+        if ok:
+            break
+        tau *= 0.9
+    save_tau = tau
+    t = t_init + tau * H_BAR
+    if t_max - t < tau * H_BAR:
+        tau = (t_max - t) / H_BAR
+        C = cheb_coefficient(tau, ebar, de)
+    ht = lambda x: (Hp @ x - ebar * x) / de
+    htT = lambda x: (Hp.T @ x - ebar * x) / de
+    while t < t_max:
+        b0, k0 = bra, ket
+        b1, k1 = htT(b0), ht(k0)
+        log["matvec_pairs"] = log.get("matvec_pairs", 0) + 1
+        sb = C[0] * b0 + C[1] * b1; sk = C[0] * k0 + C[1] * k1
+        for k in range(2, k_ref):
+            b2 = 2.0 * htT(b1) - b0; k2 = 2.0 * ht(k1) - k0
+            log["matvec_pairs"] += 1
+            sb = sb + C[k] * b2; sk = sk + C[k] * k2
+            b0, b1, k0, k1 = b1, b2, k1, k2
+        if abs(abs(np.vdot(sb, sk)) - norm_ref) < NORM_ERROR:
+            bra, ket = sb, sk
+            log["events"].append((2, k_ref, 1, tau))
+        else:
+            log["events"].append((2, k_ref, 0, tau))
+            ok = False
+            while not ok:
+                tau *= 0.975
+                ok, bra, ket, C, k_ref, k_exit = cheb_convergence(Hp, bra, ket, tau, norm_ref, ebar, de, log)
+                log["events"].append((1, k_exit, int(ok), tau))
+        t += tau * H_BAR
+        if t_max - t < tau * H_BAR:
+            tau = (t_max - t) / H_BAR
+            C = cheb_coefficient(tau, ebar, de)
+    return bra, ket, tau, save_tau

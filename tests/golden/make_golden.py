@@ -71,6 +71,35 @@ def propagation_case(name, N, dt, t_init=0.0):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
 
 
+def chebyshev_case(name, N, dt):
+    """Chebyshev mode of the product: the rescaled series (elhl_oracle.cpp orc_cheb_scaled_*), cross-checked with
+    the numpy transcription and expm; bounds = exact spectrum widened by 5% (stored in the fixture)."""
+    w = syn.make_workload(N)
+    Hp = oracle.sy_multiply(oracle.sy_invert(w.S), w.h)
+    e = np.linalg.eigvals(Hp).real
+    emin, emax = e.min(), e.max(); wd = emax - emin
+    emin -= 0.05 * wd; emax += 0.05 * wd
+    ebar, de = 0.5 * (emax + emin), 0.5 * (emax - emin)
+    tau0 = dt / tn.H_BAR
+    out = dict(N=N, dt=dt, t_init=0.0, t_max=dt, tau0=tau0, H_prime=Hp, Psi_bra0=w.Psi_bra, Psi_ket0=w.Psi_ket, emin=emin, emax=emax)
+    U = expm(-1j * tau0 * Hp)
+    for p, tag in enumerate(("el", "hl")):
+        b, k, tau_out, save_tau, tr = oracle.cheb_scaled_propagation(Hp, w.Psi_bra[:, p], w.Psi_ket[:, p], 0.0, dt, tau0, ebar, de)
+        log = {}
+        b2, k2, _, st2 = tn.cheb_propagation(Hp, w.Psi_bra[:, p].copy(), w.Psi_ket[:, p].copy(), 0.0, dt, tau0, ebar, de, log)
+        assert np.abs(b - b2).max() < 1e-11 and np.abs(k - k2).max() < 1e-11, (np.abs(b - b2).max(), np.abs(k - k2).max())
+        assert tr.n_events == len(log["events"]) and log["matvec_pairs"] == tr.n_matvec_pairs
+        assert [(e_[0], e_[1], e_[2]) for e_ in tr.events()] == [(e_[0], e_[1], e_[2]) for e_ in log["events"][:256]]
+        ek = np.abs(U @ w.Psi_ket[:, p] - k).max(); eb = np.abs(U.T @ w.Psi_bra[:, p] - b).max()
+        assert ek < 5e-7 and eb < 5e-7, (ek, eb)
+        evk, evt = events_array(tr)
+        out.update({f"{tag}_bra": b, f"{tag}_ket": k, f"{tag}_save_tau": save_tau, f"{tag}_events": evk, f"{tag}_event_tau": evt,
+                    f"{tag}_matvec_pairs": tr.n_matvec_pairs, f"{tag}_substeps": tr.n_substeps, f"{tag}_expm_err": max(ek, eb)})
+        print(f"  {name}/{tag}: pairs={tr.n_matvec_pairs} substeps={tr.n_substeps} conv_calls={tr.n_convergence_calls} "
+              f"rescale={tr.n_rescale} expm_err={max(ek, eb):.2e}")
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+
+
 def trajectory_case(name, N, dt, n_steps):
     """ElHl_Chebyshev.f:148-291 over n_steps nuclear steps with moving nuclei;
     per-step fragment populations (data_output.f:87-147) are the observable."""
@@ -102,3 +131,5 @@ if __name__ == "__main__":
     propagation_case("prop_N64_dt5e-4", 64, 5e-4)        # + the `rescaling tau` branch (Taylor.f:108-113)
     propagation_case("prop_N128_dt2e-5", 128, 2e-5)
     trajectory_case("traj_N64_dt2e-6_20steps", 64, 2e-6, 20)
+    chebyshev_case("cheb_N64_dt5e-4", 64, 5e-4)          # dt = 0.5 fs (BASELINE config), ~750 terms instead of ~18000
+    chebyshev_case("cheb_N128_dt5e-5", 128, 5e-5)
