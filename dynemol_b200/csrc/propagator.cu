@@ -914,11 +914,20 @@ int dyb_estimate_spectral_bounds(dyb_ctx* c, int n_iter, double margin, double* 
     std::vector<std::vector<double>> al(np), be(np);
     std::vector<double> beta(np, 0.0);
     std::vector<bool> alive(np, true);
+    // all Lanczos vectors are kept: without re-biorthogonalisation the two-sided recurrence loses the duality
+    // w_j = S v_j after ~35 steps and produces Ritz values far outside the spectrum
+    std::vector<std::vector<dyb_complex>> Wall(np), Vall(np);
+    auto dotc_c = [&](const dyb_complex* x, const dyb_complex* y, double& re, double& im) {
+        double sr = 0, si = 0;
+        for (size_t i = 0; i < n; ++i) { sr += x[i].re * y[i].re + x[i].im * y[i].im; si += x[i].re * y[i].im - x[i].im * y[i].re; }
+        re = sr; im = si;
+    };
     for (int p = 0; p < np; ++p) {
         const double n0 = dotc_re(&w[p * n], &v[p * n]);
         if (!(n0 > 0.0)) return fail(DYB_EINVAL, "<bra|ket> of particle %d is not positive: packets are not an S-dual pair", p);
         const double sc = 1.0 / sqrt(n0);
         for (size_t i = 0; i < n; ++i) { w[p * n + i].re *= sc; w[p * n + i].im *= sc; v[p * n + i].re *= sc; v[p * n + i].im *= sc; }
+        Wall[p].reserve((size_t)n_iter * n); Vall[p].reserve((size_t)n_iter * n);
     }
     for (int j = 0; j < n_iter; ++j) {
         if ((rc = dyb_dual_matvec(c, np, w.data(), v.data(), hw.data(), hv.data()))) return rc;
@@ -927,15 +936,24 @@ int dyb_estimate_spectral_bounds(dyb_ctx* c, int n_iter, double margin, double* 
             if (!alive[p]) continue;
             dyb_complex *W = &w[p * n], *V = &v[p * n], *WP = &wp[p * n], *VP = &vp[p * n], *HW = &hw[p * n], *HV = &hv[p * n];
             const double a = dotc_re(W, HV);
-            al[p].push_back(a); be[p].push_back(beta[p]);
-            double b2 = 0.0;
+            Wall[p].insert(Wall[p].end(), W, W + n); Vall[p].insert(Vall[p].end(), V, V + n);
             for (size_t i = 0; i < n; ++i) {
                 const dyb_complex nv = {HV[i].re - a * V[i].re - beta[p] * VP[i].re, HV[i].im - a * V[i].im - beta[p] * VP[i].im};
                 const dyb_complex nw = {HW[i].re - a * W[i].re - beta[p] * WP[i].re, HW[i].im - a * W[i].im - beta[p] * WP[i].im};
                 VP[i] = V[i]; WP[i] = W[i]; V[i] = nv; W[i] = nw;
-                b2 += nw.re * nv.re + nw.im * nv.im;
             }
-            if (!(b2 > 1e-28 * (1.0 + a * a))) { alive[p] = false; continue; }     // invariant subspace reached
+            for (int q = 0; q <= j; ++q) {                       // full two-sided Gram-Schmidt: w_q^H v' = 0, v_q^H w' = 0
+                const dyb_complex *Wq = &Wall[p][(size_t)q * n], *Vq = &Vall[p][(size_t)q * n];
+                double cr, ci, dr, di;
+                dotc_c(Wq, V, cr, ci); dotc_c(Vq, W, dr, di);
+                for (size_t i = 0; i < n; ++i) {
+                    V[i].re -= Vq[i].re * cr - Vq[i].im * ci; V[i].im -= Vq[i].re * ci + Vq[i].im * cr;
+                    W[i].re -= Wq[i].re * dr - Wq[i].im * di; W[i].im -= Wq[i].re * di + Wq[i].im * dr;
+                }
+            }
+            const double b2 = dotc_re(W, V);
+            if (!(b2 > 1e-24 * (1.0 + a * a))) { alive[p] = false; if (j == 0) { al[p].push_back(a); be[p].push_back(0.0); } continue; }
+            al[p].push_back(a); be[p].push_back(beta[p]);        // a step is only accepted once its successor is sound
             beta[p] = sqrt(b2);
             const double sc = 1.0 / beta[p];
             for (size_t i = 0; i < n; ++i) { V[i].re *= sc; V[i].im *= sc; W[i].re *= sc; W[i].im *= sc; }

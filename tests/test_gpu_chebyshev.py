@@ -54,10 +54,10 @@ def test_lanczos_bounds_and_half_femtosecond_step(api, oracle_mod):
     P = api.Propagator(N)
     P.upload_hprime(Hp)
     P.set_packets(w.Psi_bra, w.Psi_ket)
-    lo, hi = P.estimate_spectral_bounds(n_iter=60, margin=0.05)
+    lo, hi = P.estimate_spectral_bounds(n_iter=60, margin=0.02)
     width = e.max() - e.min()
     assert lo <= e.min() + 1e-6 * width and hi >= e.max() - 1e-6 * width, (lo, hi, e.min(), e.max())
-    assert hi - lo < 1.25 * width, "bounds should be tight, not Gershgorin-loose"
+    assert hi - lo < 1.10 * width, "bounds should be tight, not Gershgorin-loose"
     tau0 = dt / H_BAR
     save_tau, traces = P.propagate(0.0, dt, tau0, mode=api.MODE_CHEBYSHEV)
     bra, ket = P.get_packets()
