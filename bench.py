@@ -207,14 +207,50 @@ def run_ours_single(args):
         e2e = run_e2e(args, P, N, Psi_bra, Psi_ket)
     cpu = None if args.skip_cpu else cpu_baseline(np.asfortranarray(P.download_hprime()), Psi_bra, Psi_ket, tau, budget_s=args.cpu_budget)
 
+    n65536 = None
+    if N == 16384 and not args.skip_65k:
+        n65536 = single_gpu_65536(P, args)
+
     line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "synthetic EHT Hamiltonian N=%d basis, el+hole packets, 1xB200" % N, "basis": N,
                        "terms_per_step": TERMS_PER_STEP, "l2": "inputs larger than L2 (H' = %.2f GB per pass)" % (alg_bytes / 1e9),
                        "kernel_variant": args.kernel, "grid": info["grid"], "tiles": info["tiles"], "build": build_info},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "n65536_single_gpu": n65536}
     print(json.dumps(line))
+
+
+def single_gpu_65536(P_small, args):
+    """The strong-scaling denominator of BASELINE config 4 (N=65536 on ONE GPU, 34 GB of H'), measured in the same
+    run so that the --gpus 2/4/8 lines (which use N=65536) can be compared with it."""
+    import torch
+    from dynemol_b200 import api, sharded
+    try:
+        P_small.close()
+        torch.cuda.empty_cache()
+        N = 65536
+        free, _ = torch.cuda.mem_get_info()
+        if free < 8.0 * N * N * 1.05 + 8e9:
+            return {"skipped": "not enough free HBM"}
+        P = api.Propagator(N)
+        t0 = time.time(); sharded.fill_rows(P, N, 0, N, torch.device("cuda", 0)); gen = time.time() - t0
+        bra, ket = sharded.synthetic_packets(N)
+        P.set_packets(bra, ket)
+        tau = pick_tau(N)
+        for _ in range(2):
+            P.run_terms(tau, TERMS_PER_STEP)
+        steps = 5
+        ms, _ = P.run_terms(tau, TERMS_PER_STEP * steps)
+        ms2, kms = P.run_terms(tau, TERMS_PER_STEP * 2, per_kernel=True)
+        peak, _ = measured_peak_gbs()
+        ach = 8.0 * N * N / ((kms * 1e-3) / (TERMS_PER_STEP * 2)) / 1e9
+        P.close()
+        return {"value": round(TERMS_PER_STEP * steps / (ms * 1e-3), 2), "unit": UNIT, "steps": steps, "basis": N,
+                "operator": "Hueckel h surrogate (SURVEY.md 8d)", "kernel_GBs": round(ach, 1), "frac": round(ach / peak, 4), "gen_s": round(gen, 1)}
+    except Exception as e:  # the headline line must survive a failure of the side measurement
+        return {"error": repr(e)[:200]}
 
 
 def run_e2e(args, P, N, Psi_bra, Psi_ket):
@@ -304,6 +340,7 @@ def main():
     ap.add_argument("--ref-terms-per-step", type=int, default=2)
     ap.add_argument("--kernel", default="tma", choices=["tma", "ldg"])
     ap.add_argument("--no-ref1", action="store_true", help="multi-GPU: skip the 1-GPU same-workload reference on rank 0")
+    ap.add_argument("--skip-65k", action="store_true", help="N=1: skip the N=65536 single-GPU side measurement")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: no CPU baseline leg")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: no end-to-end leg")
     args = ap.parse_args()

@@ -53,7 +53,10 @@ void elhl(int n_part, const int* N, const double* h_S, const double* h_h, double
     dyb_ctx* c = ctx_for(*N);
     LCK(dyb_form_hprime(c, h_S, h_h, h_H), "dyb_form_hprime");                 // Taylor_gpu.cpp:676-700
     LCK(dyb_set_packets(c, n_part, h_PSI_bra, h_PSI_ket), "dyb_set_packets");  // :681-683
-    LCK(dyb_propagate(c, mode_from_env(), *t_init, *t_max, tau, save_tau, nullptr), "dyb_propagate");  // :707
+    const int mode = mode_from_env();
+    if (mode == DYB_MODE_CHEBYSHEV)            // the operator changes every nuclear step: re-estimate its spectral interval
+        LCK(dyb_estimate_spectral_bounds(c, 40, 0.05, nullptr, nullptr), "dyb_estimate_spectral_bounds");
+    LCK(dyb_propagate(c, mode, *t_init, *t_max, tau, save_tau, nullptr), "dyb_propagate");  // :707
     LCK(dyb_get_packets(c, n_part, h_PSI_bra, h_PSI_ket), "dyb_get_packets");  // :711-712
     LCK(dyb_ao_bra(c, n_part, h_AO_bra), "dyb_ao_bra");                        // :718-721
 }
@@ -84,7 +87,10 @@ void propagation_gpucaller_(const int* n, double* tau, double* save_tau, const d
     dyb_ctx* c = ctx_for(*n);
     LCK(dyb_upload_hprime(c, h_H, *n), "dyb_upload_hprime");                   // Taylor_gpu.cpp:317
     LCK(dyb_set_packets(c, 1, h_PSI_bra, h_PSI_ket), "dyb_set_packets");
-    LCK(dyb_propagate(c, mode_from_env(), *t_init, *t_max, tau, save_tau, nullptr), "dyb_propagate");
+    const int mode = mode_from_env();
+    if (mode == DYB_MODE_CHEBYSHEV)
+        LCK(dyb_estimate_spectral_bounds(c, 40, 0.05, nullptr, nullptr), "dyb_estimate_spectral_bounds");
+    LCK(dyb_propagate(c, mode, *t_init, *t_max, tau, save_tau, nullptr), "dyb_propagate");
     LCK(dyb_get_packets(c, 1, h_PSI_bra, h_PSI_ket), "dyb_get_packets");
 }
 
