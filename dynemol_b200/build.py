@@ -32,10 +32,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     host_cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-ccbin", host_cxx, "-Xcompiler", "-fPIC,-O2,-fvisibility=default", "-shared",
+           "-ccbin", host_cxx, "-Xcompiler", "-fPIC,-O2,-fvisibility=default,-fopenmp", "-shared",
            "-Xptxas", "-v" if verbose else "-O3",
            "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + \
-          ["-L" + CUDA_LIB, "-lcublas", "-lcusolver", "-Xlinker", "-rpath," + CUDA_LIB]
+          ["-L" + CUDA_LIB, "-lcublas", "-lcusolver", "-lgomp", "-Xlinker", "-rpath," + CUDA_LIB]
     if verbose:
         print(" ".join(cmd))
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -910,7 +910,14 @@ int dyb_estimate_spectral_bounds(dyb_ctx* c, int n_iter, double margin, double* 
     std::vector<dyb_complex> w(n * np), v(n * np), wp(n * np, dyb_complex{0, 0}), vp(n * np, dyb_complex{0, 0}), hw(n * np), hv(n * np);
     int rc = dyb_get_packets(c, np, w.data(), v.data());
     if (rc) return rc;
-    auto dotc_re = [&](const dyb_complex* x, const dyb_complex* y) { double s = 0; for (size_t i = 0; i < n; ++i) s += x[i].re * y[i].re + x[i].im * y[i].im; return s; };
+    // host loops are O(n_iter^2 N): threaded with OpenMP (static schedule + fixed thread count => reproducible sums)
+    const long nn = (long)n;
+    auto dotc_re = [&](const dyb_complex* x, const dyb_complex* y) {
+        double s = 0;
+        #pragma omp parallel for reduction(+ : s) schedule(static)
+        for (long i = 0; i < nn; ++i) s += x[i].re * y[i].re + x[i].im * y[i].im;
+        return s;
+    };
     std::vector<std::vector<double>> al(np), be(np);
     std::vector<double> beta(np, 0.0);
     std::vector<bool> alive(np, true);
@@ -919,7 +926,8 @@ int dyb_estimate_spectral_bounds(dyb_ctx* c, int n_iter, double margin, double* 
     std::vector<std::vector<dyb_complex>> Wall(np), Vall(np);
     auto dotc_c = [&](const dyb_complex* x, const dyb_complex* y, double& re, double& im) {
         double sr = 0, si = 0;
-        for (size_t i = 0; i < n; ++i) { sr += x[i].re * y[i].re + x[i].im * y[i].im; si += x[i].re * y[i].im - x[i].im * y[i].re; }
+        #pragma omp parallel for reduction(+ : sr, si) schedule(static)
+        for (long i = 0; i < nn; ++i) { sr += x[i].re * y[i].re + x[i].im * y[i].im; si += x[i].re * y[i].im - x[i].im * y[i].re; }
         re = sr; im = si;
     };
     for (int p = 0; p < np; ++p) {
@@ -937,16 +945,19 @@ int dyb_estimate_spectral_bounds(dyb_ctx* c, int n_iter, double margin, double* 
             dyb_complex *W = &w[p * n], *V = &v[p * n], *WP = &wp[p * n], *VP = &vp[p * n], *HW = &hw[p * n], *HV = &hv[p * n];
             const double a = dotc_re(W, HV);
             Wall[p].insert(Wall[p].end(), W, W + n); Vall[p].insert(Vall[p].end(), V, V + n);
-            for (size_t i = 0; i < n; ++i) {
-                const dyb_complex nv = {HV[i].re - a * V[i].re - beta[p] * VP[i].re, HV[i].im - a * V[i].im - beta[p] * VP[i].im};
-                const dyb_complex nw = {HW[i].re - a * W[i].re - beta[p] * WP[i].re, HW[i].im - a * W[i].im - beta[p] * WP[i].im};
+            const double bp = beta[p];
+            #pragma omp parallel for schedule(static)
+            for (long i = 0; i < nn; ++i) {
+                const dyb_complex nv = {HV[i].re - a * V[i].re - bp * VP[i].re, HV[i].im - a * V[i].im - bp * VP[i].im};
+                const dyb_complex nw = {HW[i].re - a * W[i].re - bp * WP[i].re, HW[i].im - a * W[i].im - bp * WP[i].im};
                 VP[i] = V[i]; WP[i] = W[i]; V[i] = nv; W[i] = nw;
             }
             for (int q = 0; q <= j; ++q) {                       // full two-sided Gram-Schmidt: w_q^H v' = 0, v_q^H w' = 0
                 const dyb_complex *Wq = &Wall[p][(size_t)q * n], *Vq = &Vall[p][(size_t)q * n];
                 double cr, ci, dr, di;
                 dotc_c(Wq, V, cr, ci); dotc_c(Vq, W, dr, di);
-                for (size_t i = 0; i < n; ++i) {
+                #pragma omp parallel for schedule(static)
+                for (long i = 0; i < nn; ++i) {
                     V[i].re -= Vq[i].re * cr - Vq[i].im * ci; V[i].im -= Vq[i].re * ci + Vq[i].im * cr;
                     W[i].re -= Wq[i].re * dr - Wq[i].im * di; W[i].im -= Wq[i].re * di + Wq[i].im * dr;
                 }
