@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdynemol_b200.so")
+LIB_PATH = os.environ.get("DYNEMOL_B200_LIB") or os.path.join(_HERE, "lib", "libdynemol_b200.so")   # override: tuning builds
 
 H_BAR = 6.58264e-4          # eV*ps (constants_m.f:23)
 MODE_TAYLOR, MODE_CHEBYSHEV = 0, 1

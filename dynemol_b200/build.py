@@ -26,12 +26,18 @@ def _stale() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, out: str | None = None) -> str:
+    """out: alternative output path (tuning variants built with DYB_NVCC_DEFS, loaded via DYNEMOL_B200_LIB)."""
+    global LIB
+    if out:
+        LIB = out
+        force = True
     if not force and not _stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     host_cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    extra = os.environ.get("DYB_NVCC_DEFS", "").split()      # e.g. "-DDYB_TILE_COLS=4 -DDYB_TMA_STAGES=3" (tuning experiments)
+    cmd = [NVCC] + extra + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-ccbin", host_cxx, "-Xcompiler", "-fPIC,-O2,-fvisibility=default,-fopenmp", "-shared",
            "-Xptxas", "-v" if verbose else "-O3",
            "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + \
@@ -47,4 +53,5 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    outs = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, out=outs[0] if outs else None))

@@ -14,14 +14,20 @@ namespace dyb {
 constexpr int SUB_ROWS     = 256;                  // rows per consumer warp
 constexpr int N_CWARPS     = 8;                    // consumer warps per CTA
 constexpr int PANEL_ROWS   = SUB_ROWS * N_CWARPS;  // 2048
-constexpr int TILE_COLS    = 2;                    // columns per tile (TMA box depth)
+#ifndef DYB_TILE_COLS
+#define DYB_TILE_COLS 4
+#endif
+#ifndef DYB_TMA_STAGES
+#define DYB_TMA_STAGES 3
+#endif
+constexpr int TILE_COLS    = DYB_TILE_COLS;        // columns per tile (TMA box depth): 2 or 4
 constexpr int ROW_ALIGN    = SUB_ROWS;             // ld is a multiple of this (zero padded rows)
 constexpr int NQ           = 4;                    // reals per index in a "quad" vector: el.re el.im hl.re hl.im
-constexpr int TMA_STAGES   = 6;
+constexpr int TMA_STAGES   = DYB_TMA_STAGES;
 constexpr int RED_SLOTS    = 2 * TMA_STAGES;
 
-constexpr int STAGE_H_BYTES  = TILE_COLS * PANEL_ROWS * 8;        // 32 KiB
-constexpr int STAGE_X_BYTES  = 128;                               // TILE_COLS*NQ*8 = 64 B, padded
+constexpr int STAGE_H_BYTES  = TILE_COLS * PANEL_ROWS * 8;        // 64 KiB
+constexpr int STAGE_X_BYTES  = 128;                               // TILE_COLS*NQ*8 = 64/128 B, padded
 constexpr int STAGE_BYTES    = STAGE_H_BYTES + STAGE_X_BYTES;
 constexpr int STAGE_TX_BYTES = STAGE_H_BYTES + TILE_COLS * NQ * 8;
 

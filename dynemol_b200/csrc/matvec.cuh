@@ -31,31 +31,56 @@ struct MatvecParams {
     const Ctrl* ctrl;      // may be null; all_latched => nothing to do
 };
 
-// Sum over the 32 lanes of v[0..7]; on return every lane holds the total of index (lane >> 2).
-// Butterfly with halving: 4+2+1 exchanged values, then two plain butterflies.  Fixed order => deterministic.
-__device__ __forceinline__ double transpose_reduce8(const double (&v)[8], int lane) {
-    const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
-    double a[4];
+// Sum over the 32 lanes of v[0..NV-1] (NV = 8 or 16); on return every lane holds the total of index
+// lane >> (NV == 8 ? 2 : 1).  Butterfly with halving (NV/2 + NV/4 + ... exchanged values), then plain
+// butterflies for the remaining lane bits.  Fixed order => deterministic.
+template <int NV>
+__device__ __forceinline__ double transpose_reduce(const double (&v)[NV], int lane) {
+    static_assert(NV == 8 || NV == 16, "NV");
+    double a[NV / 2];
+    {
+        const bool hi = lane & 16;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const double keep = b16 ? v[4 + i] : v[i];
-        const double send = b16 ? v[i] : v[4 + i];
-        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        for (int i = 0; i < NV / 2; ++i) {
+            const double keep = hi ? v[NV / 2 + i] : v[i];
+            const double send = hi ? v[i] : v[NV / 2 + i];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
     }
-    double b[2];
+    double b[NV / 4];
+    {
+        const bool hi = lane & 8;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const double keep = b8 ? a[2 + i] : a[i];
-        const double send = b8 ? a[i] : a[2 + i];
-        b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        for (int i = 0; i < NV / 4; ++i) {
+            const double keep = hi ? a[NV / 4 + i] : a[i];
+            const double send = hi ? a[i] : a[NV / 4 + i];
+            b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
     }
-    const double keep = b4 ? b[1] : b[0];
-    const double send = b4 ? b[0] : b[1];
-    double c = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    c += __shfl_xor_sync(0xffffffffu, c, 2);
-    c += __shfl_xor_sync(0xffffffffu, c, 1);
-    return c;
+    double c[NV / 8];
+    {
+        const bool hi = lane & 4;
+#pragma unroll
+        for (int i = 0; i < NV / 8; ++i) {
+            const double keep = hi ? b[NV / 8 + i] : b[i];
+            const double send = hi ? b[i] : b[NV / 8 + i];
+            c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    double d;
+    if constexpr (NV == 16) {
+        const bool hi = lane & 2;
+        const double keep = hi ? c[1] : c[0];
+        const double send = hi ? c[0] : c[1];
+        d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    } else {
+        d = c[0] + __shfl_xor_sync(0xffffffffu, c[0], 2);
+    }
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    return d;
 }
+constexpr int RED_SHIFT = (TILE_COLS * NQ == 16) ? 1 : 2;      // lane -> value index
+constexpr int RED_MASK  = (1 << RED_SHIFT) - 1;
 
 // Per-thread state of a consumer: 8 rows (m = 0..3, e = 0..1) x 4 right-hand sides.
 struct ConsumerRegs {
@@ -132,7 +157,10 @@ __device__ __forceinline__ void fma_column(ConsumerRegs& r, const double2 (&h)[4
 // cap every thread at 168 registers (16384 per sub-partition); 8 warps leave 255.
 // =================================================================================================
 constexpr int TMA_THREADS = N_CWARPS * 32;   // 256
-constexpr int RETIRE_LAG  = 2;               // tiles between computing a tile and retiring it
+#ifndef DYB_RETIRE_LAG
+#define DYB_RETIRE_LAG 1
+#endif
+constexpr int RETIRE_LAG  = DYB_RETIRE_LAG;  // tiles between computing a tile and retiring it
 
 struct TmaSmem {
     // dynamic shared memory carve-up
@@ -220,9 +248,9 @@ dual_matvec_tma_kernel(const __grid_constant__ CUtensorMap tmap, const MatvecPar
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) pv[c * NQ + q] = p[q];
             }
-            const double tot = transpose_reduce8(pv, lane);
-            if ((lane & 3) == 0)
-                red[rslot * (N_CWARPS * TILE_COLS * NQ) + w * (TILE_COLS * NQ) + (lane >> 2)] = tot;
+            const double tot = transpose_reduce<TILE_COLS * NQ>(pv, lane);
+            if ((lane & RED_MASK) == 0)
+                red[rslot * (N_CWARPS * TILE_COLS * NQ) + w * (TILE_COLS * NQ) + (lane >> RED_SHIFT)] = tot;
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_empty[s]);      // release: stage reads and red[] writes are done
 
@@ -320,8 +348,8 @@ dual_matvec_ldg_kernel(const MatvecParams P)
 #pragma unroll
             for (int q = 0; q < NQ; ++q) pv[c * NQ + q] = p[q];
         }
-        const double tot = transpose_reduce8(pv, lane);
-        if ((lane & 3) == 0) red[j & 1][w][lane >> 2] = tot;
+        const double tot = transpose_reduce<TILE_COLS * NQ>(pv, lane);
+        if ((lane & RED_MASK) == 0) red[j & 1][w][lane >> RED_SHIFT] = tot;
         __syncthreads();
         if (threadIdx.x < TILE_COLS * NQ) {
             double sum = red[j & 1][0][threadIdx.x];

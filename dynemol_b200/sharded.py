@@ -122,7 +122,7 @@ def bench_main(args):
                 "config": {"workload": "synthetic EHT Hamiltonian N=%d basis, row-sharded H' over %d GPUs, NCCL reduce-scatter(bra)+all-gather(ket) per term" % (N, world),
                            "basis": N, "rows_per_gpu": m, "terms_per_step": B.TERMS_PER_STEP,
                            "l2": "inputs larger than L2 (%.2f GB of H' per GPU per pass)" % (per_gpu_bytes / 1e9),
-                           "operator": "Hueckel h as H' surrogate (SURVEY.md 8d)", "grid": info["grid"], "gen_s": round(gen_s, 1)},
+                           "operator": "Hueckel h + dense decaying tail, surrogate for S^-1 h (SURVEY.md 8d)", "grid": info["grid"], "gen_s": round(gen_s, 1)},
                 "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                              "traffic": None, "kernel": "whole term incl. collectives, per GPU", "peak_source": peak_src,
                              "alg_bytes_per_launch": per_gpu_bytes},
