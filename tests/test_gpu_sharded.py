@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 8])
 def test_sharded_propagation_matches_oracle(world):
     from dynemol_b200 import api
     if api.device_count() < world:
