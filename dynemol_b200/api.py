@@ -73,13 +73,14 @@ lib = _load()
 
 # every symbol include/dynemol_b200.h declares (checked by the CPU test-suite)
 DECLARED_SYMBOLS = [
-    "propagationelhl_gpucaller_", "propagationelhl2_gpucaller_", "propagation_gpucaller_", "nakedbessel_",
+    "propagationelhl_gpucaller_", "propagationelhl2_gpucaller_", "propagation_gpucaller_", "nakedbessel_", "ehrenfestkernel_gpu_",
     "gpu_init_", "gpu_finalize_", "gpu_pin_", "gpu_unpin_",
     "dyb_last_error", "dyb_version", "dyb_device_count", "dyb_create", "dyb_destroy", "dyb_set_kernel",
     "dyb_get_info", "dyb_upload_hprime", "dyb_upload_hprime_device", "dyb_upload_hprime_rows_device", "dyb_hprime_device", "dyb_form_hprime", "dyb_form_hprime_device",
     "dyb_download_hprime", "dyb_set_packets", "dyb_get_packets", "dyb_propagate", "dyb_ao_bra",
     "dyb_populations", "dyb_run_terms", "dyb_dual_matvec", "dyb_sync", "dyb_launch_count",
     "dyb_comm_unique_id", "dyb_comm_init", "dyb_set_spectral_bounds", "dyb_get_spectral_bounds", "dyb_estimate_spectral_bounds",
+    "dyb_quasiparticle_energies", "dyb_ehrenfest_kernel",
 ]
 
 
@@ -237,6 +238,19 @@ class Propagator:
         assert len(unique_id) == 128
         _check(lib.dyb_comm_init(self._h, C.c_int(rank), C.c_int(world), C.c_char_p(unique_id)))
 
+    def quasiparticle_energies(self):
+        """ElHl_Chebyshev.f:329-371 on the device: complex energy per particle."""
+        out = np.zeros(4)
+        _check(lib.dyb_quasiparticle_energies(self._h, C.c_int(self.n_part), _p(out)))
+        return (out[0::2] + 1j * out[1::2])[: self.n_part]
+
+    def ehrenfest_kernel(self, A, X):
+        """K = X o A - H' A with the resident H' (diabatic-Ehren.f:115-119)."""
+        A = _fd(A); X = _fd(X)
+        K = np.empty((self.N, self.N), dtype=np.float64, order="F")
+        _check(lib.dyb_ehrenfest_kernel(self._h, _p(A), _p(X), _p(K)))
+        return K
+
     def sync(self):
         _check(lib.dyb_sync(self._h))
 
@@ -282,6 +296,14 @@ def legacy_propagation(H, PSI_bra, PSI_ket, t_init, t_max, tau):
     lib.propagation_gpucaller_(C.byref(n), C.byref(tau_c), C.byref(sv), _ref(t_init, C.c_double), _ref(t_max, C.c_double),
                                _p(PSI_bra), _p(PSI_ket), _p(H))
     return PSI_bra, PSI_ket, sv.value
+
+
+def legacy_ehrenfestkernel(H, A, X):
+    """call EhrenfestKernel_gpu( N, H_prime, A_ad_nd, X_ij, Kernel ) -- diabatic-Ehren.f:115."""
+    H = _fd(H); A = _fd(A); X = _fd(X); N = H.shape[0]
+    K = np.empty((N, N), dtype=np.float64, order="F")
+    lib.ehrenfestkernel_gpu_(C.byref(C.c_int(N)), _p(H), _p(A), _p(X), _p(K))
+    return K
 
 
 def nakedbessel(n: int, x: float) -> float:

@@ -94,6 +94,14 @@ void propagation_gpucaller_(const int* n, double* tau, double* save_tau, const d
     LCK(dyb_get_packets(c, 1, h_PSI_bra, h_PSI_ket), "dyb_get_packets");
 }
 
+// Taylor_gpu.cpp:743-797, called from diabatic-Ehren.f:115 on the "kernel" MPI rank with H' received from rank 0
+void ehrenfestkernel_gpu_(const int* N, const double* h_H, const double* h_A, const double* h_X, double* h_K)
+{
+    dyb_ctx* c = ctx_for(*N);
+    LCK(dyb_upload_hprime(c, h_H, *N), "dyb_upload_hprime");
+    LCK(dyb_ehrenfest_kernel(c, h_A, h_X, h_K), "dyb_ehrenfest_kernel");
+}
+
 // Chebyshev_gpu.cpp:517:  2^(n-2) * (x^2 + 4) / x^n
 double nakedbessel_(const int* n, const double* x)
 {

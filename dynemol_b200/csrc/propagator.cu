@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -645,15 +646,13 @@ static int ensure_solver(dyb_ctx* c) {
 // (Cholesky; LU with partial pivoting if S is not numerically SPD, as the reference's GPU flavour
 // GPU_Interface.cpp:910-929) and the N right-hand sides are solved in place: fewer flops, no explicit
 // inverse, same result to O(cond(S) eps).  The factor is kept for AO_bra = S^-1 Psi_bra.
-static int factor_and_solve(dyb_ctx* c) {
+static int factor_and_solve(dyb_ctx* c, const std::function<int()>& reload_S) {
     const int64_t n = c->N;
     size_t wd = 0, wh = 0;
     int* d_info = reinterpret_cast<int*>(c->scal + 32);
     CKS(cusolverDnXpotrf_bufferSize(c->solver, c->sparams, CUBLAS_FILL_MODE_UPPER, n, CUDA_R_64F, c->S, n, CUDA_R_64F, &wd, &wh));
     void* d_work = nullptr; std::vector<char> h_work(wh ? wh : 1);
     if (wd) CK(cudaMalloc(&d_work, wd));
-    // keep a copy of S in case Cholesky fails and LU is needed: only the upper triangle is overwritten by
-    // potrf('U'), the strictly lower triangle still holds S -> S can be rebuilt by mirroring it.
     cusolverStatus_t st = cusolverDnXpotrf(c->solver, c->sparams, CUBLAS_FILL_MODE_UPPER, n, CUDA_R_64F, c->S, n, CUDA_R_64F,
                                            d_work, wd, h_work.data(), wh, d_info);
     int info = 0;
@@ -664,7 +663,21 @@ static int factor_and_solve(dyb_ctx* c) {
         CKS(cusolverDnXpotrs(c->solver, c->sparams, CUBLAS_FILL_MODE_UPPER, n, n, CUDA_R_64F, c->S, n, CUDA_R_64F, c->H, c->ld, d_info));
         c->factor_is_lu = false;
     } else {
-        return fail(DYB_ESINGULAR, "overlap matrix is not positive definite (potrf info=%d)", info);
+        // S is not numerically positive definite: LU with partial pivoting, the route of the reference's GPU
+        // flavour (magma_dgetrf_gpu/dgetri_gpu, GPU_Interface.cpp:910-929).  potrf destroyed part of S: reload it.
+        int rc = reload_S();
+        if (rc) return rc;
+        if (!c->ipiv) CK(cudaMalloc(&c->ipiv, sizeof(int64_t) * n));
+        CKS(cusolverDnXgetrf_bufferSize(c->solver, c->sparams, n, n, CUDA_R_64F, c->S, n, CUDA_R_64F, &wd, &wh));
+        d_work = nullptr; h_work.resize(wh ? wh : 1);
+        if (wd) CK(cudaMalloc(&d_work, wd));
+        st = cusolverDnXgetrf(c->solver, c->sparams, n, n, CUDA_R_64F, c->S, n, c->ipiv, CUDA_R_64F, d_work, wd, h_work.data(), wh, d_info);
+        if (st == CUSOLVER_STATUS_SUCCESS) { CK(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+        if (d_work) cudaFree(d_work);
+        if (st != CUSOLVER_STATUS_SUCCESS) return fail(DYB_ECUDA, "cusolverDnXgetrf status %d", (int)st);
+        if (info != 0) return fail(DYB_ESINGULAR, "overlap matrix is singular (getrf info=%d)", info);
+        CKS(cusolverDnXgetrs(c->solver, c->sparams, CUBLAS_OP_N, n, n, CUDA_R_64F, c->S, n, c->ipiv, CUDA_R_64F, c->H, c->ld, d_info));
+        c->factor_is_lu = true;
     }
     c->have_factor = true;
     return DYB_OK;
@@ -677,9 +690,10 @@ int dyb_form_hprime(dyb_ctx* c, const double* h_S, const double* h_h, double* h_
     int rc = ensure_solver(c);
     if (rc) return rc;
     const size_t n = c->N;
-    CK(cudaMemcpyAsync(c->S, h_S, n * n * 8, cudaMemcpyHostToDevice, c->stream));
+    auto load_S = [&]() -> int { CK(cudaMemcpyAsync(c->S, h_S, n * n * 8, cudaMemcpyHostToDevice, c->stream)); return DYB_OK; };
+    if ((rc = load_S())) return rc;
     CK(cudaMemcpy2DAsync(c->H, (size_t)c->ld * 8, h_h, n * 8, n * 8, n, cudaMemcpyHostToDevice, c->stream));
-    if ((rc = factor_and_solve(c))) return rc;
+    if ((rc = factor_and_solve(c, load_S))) return rc;
     if (h_H_out) CK(cudaMemcpy2DAsync(h_H_out, n * 8, c->H, (size_t)c->ld * 8, n * 8, n, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return DYB_OK;
@@ -692,9 +706,10 @@ int dyb_form_hprime_device(dyb_ctx* c, const void* d_S, int64_t lds, const void*
     int rc = ensure_solver(c);
     if (rc) return rc;
     const size_t n = c->N;
-    CK(cudaMemcpy2DAsync(c->S, n * 8, d_S, (size_t)lds * 8, n * 8, n, cudaMemcpyDeviceToDevice, c->stream));
+    auto load_S = [&]() -> int { CK(cudaMemcpy2DAsync(c->S, n * 8, d_S, (size_t)lds * 8, n * 8, n, cudaMemcpyDeviceToDevice, c->stream)); return DYB_OK; };
+    if ((rc = load_S())) return rc;
     CK(cudaMemcpy2DAsync(c->H, (size_t)c->ld * 8, d_h, (size_t)ldh * 8, n * 8, n, cudaMemcpyDeviceToDevice, c->stream));
-    if ((rc = factor_and_solve(c))) return rc;
+    if ((rc = factor_and_solve(c, load_S))) return rc;
     CK(cudaStreamSynchronize(c->stream));
     return DYB_OK;
 }
@@ -1006,7 +1021,8 @@ int dyb_ao_bra(dyb_ctx* c, int n_part, dyb_complex* h_AO_bra) {
         CKB(cublasDcopy(c->blas, (int)n, c->io + (size_t)p * 2 * n + 1, 2, rhs + (size_t)(2 * p + 1) * n, 1));
     }
     int* d_info = reinterpret_cast<int*>(c->scal + 32);
-    CKS(cusolverDnXpotrs(c->solver, c->sparams, CUBLAS_FILL_MODE_UPPER, n, 2 * n_part, CUDA_R_64F, c->S, n, CUDA_R_64F, rhs, n, d_info));
+    if (c->factor_is_lu) CKS(cusolverDnXgetrs(c->solver, c->sparams, CUBLAS_OP_N, n, 2 * n_part, CUDA_R_64F, c->S, n, c->ipiv, CUDA_R_64F, rhs, n, d_info));
+    else CKS(cusolverDnXpotrs(c->solver, c->sparams, CUBLAS_FILL_MODE_UPPER, n, 2 * n_part, CUDA_R_64F, c->S, n, CUDA_R_64F, rhs, n, d_info));
     for (int p = 0; p < n_part; ++p) {
         CKB(cublasDcopy(c->blas, (int)n, rhs + (size_t)(2 * p) * n, 1, c->io + (size_t)p * 2 * n, 2));
         CKB(cublasDcopy(c->blas, (int)n, rhs + (size_t)(2 * p + 1) * n, 1, c->io + (size_t)p * 2 * n + 1, 2));
@@ -1014,6 +1030,61 @@ int dyb_ao_bra(dyb_ctx* c, int n_part, dyb_complex* h_AO_bra) {
     CK(cudaMemcpyAsync(h_AO_bra, c->io, (size_t)n * n_part * sizeof(dyb_complex), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return DYB_OK;
+}
+
+// QuasiParticleEnergies (ElHl_Chebyshev.f:329-371): erg(p) = sum_ij AO_bra(i,p) h(i,j) AO_ket(j,p) with
+// AO_bra = conj(S^-1 Psi_bra), AO_ket = Psi_ket (ElHl_Chebyshev.f:274-276).  Because S^-1 is real symmetric,
+//   erg = (S^-1 Psi_bra)^H h Psi_ket = Psi_bra^H (S^-1 h) Psi_ket = dotc(Psi_bra, H' Psi_ket):
+// one more dual product of the hot kernel and a dot product, no second pass over h.  out = (re,im) per particle.
+int dyb_quasiparticle_energies(dyb_ctx* c, int n_part, double* out_reim) {
+    if (!c || !out_reim || n_part < 1 || n_part > 2) return fail(DYB_EINVAL, "bad argument");
+    if (c->M != c->N) return fail(DYB_EINVAL, "full-matrix contexts only");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = launch_matvec(c, c->psi_k, c->psi_b, false))) return rc;
+    EpiParams E = epi_params(c, 0, 0, 1);
+    slab_reduce_kernel<<<(2 * c->M + 255) / 256, 256, 0, c->stream>>>(E);        // vk[1] = H' Psi_ket
+    c->launches++;
+    CK(cudaGetLastError());
+    dotc_kernel<<<1, 1024, 0, c->stream>>>(c->M, c->psi_b, c->vk[1], c->scal);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c->h_scal, c->scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 2 * n_part; ++i) out_reim[i] = c->h_scal[i];
+    return DYB_OK;
+}
+
+// Diabatic-Ehrenfest kernel (diabatic-Ehren.f:115-119; Taylor_gpu.cpp:743-797 ehrenfestkernel_gpu_):
+//   K = X o A - H' A      (o = element-wise product; A = (rho + rho^T)/2, X = X_ij, both host-built)
+// with the H' ALREADY RESIDENT from the propagation of this step: no 8 N^2 B upload of H' (the reference ships it
+// to another MPI rank and uploads it again).  O(N^3) DGEMM through cuBLAS; the Hadamard-minus is fused in one pass.
+__global__ void hadamard_minus_kernel(size_t n_elem, const double* __restrict__ X, const double* __restrict__ A, double* __restrict__ K) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_elem) K[i] = X[i] * A[i] - K[i];
+}
+
+int dyb_ehrenfest_kernel(dyb_ctx* c, const double* h_A, const double* h_X, double* h_K) {
+    if (!c || !h_A || !h_X || !h_K) return fail(DYB_EINVAL, "NULL argument");
+    if (c->M != c->N) return fail(DYB_EINVAL, "full-matrix contexts only");
+    CK(cudaSetDevice(c->device));
+    const size_t n = c->N, bytes = n * n * 8;
+    double *A = nullptr, *X = nullptr, *K = nullptr;
+    CK(cudaMalloc(&A, bytes)); CK(cudaMalloc(&X, bytes)); CK(cudaMalloc(&K, bytes));
+    int rc = DYB_OK;
+    do {
+        if (!c->blas) { if (cublasCreate(&c->blas) != CUBLAS_STATUS_SUCCESS || cublasSetStream(c->blas, c->stream) != CUBLAS_STATUS_SUCCESS) { rc = fail(DYB_ECUDA, "cublasCreate failed"); break; } }
+        if (cudaMemcpyAsync(A, h_A, bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+            cudaMemcpyAsync(X, h_X, bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { rc = fail(DYB_ECUDA, "H2D of A/X failed"); break; }
+        const double one = 1.0, zero = 0.0;
+        if (cublasDgemm(c->blas, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, (int)n, (int)n, &one, c->H, (int)c->ld, A, (int)n, &zero, K, (int)n) != CUBLAS_STATUS_SUCCESS) { rc = fail(DYB_ECUDA, "cublasDgemm failed"); break; }
+        hadamard_minus_kernel<<<(unsigned)((n * n + 255) / 256), 256, 0, c->stream>>>(n * n, X, A, K);
+        c->launches++;
+        if (cudaGetLastError() != cudaSuccess || cudaMemcpyAsync(h_K, K, bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = fail(DYB_ECUDA, "Ehrenfest kernel failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+    } while (0);
+    cudaFree(A); cudaFree(X); cudaFree(K);
+    return rc;
 }
 
 int dyb_populations(dyb_ctx* c, int n_part, int n_frag, const int32_t* fragment, double t, double* out) {

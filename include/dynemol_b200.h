@@ -69,6 +69,9 @@ void propagation_gpucaller_(const int* n, double* tau, double* save_tau,
                             const double* t_init, const double* t_max,
                             dyb_complex* h_PSI_bra, dyb_complex* h_PSI_ket, const double* h_H);
 
+/* Replaces Taylor_gpu.cpp:743-797 (called from diabatic-Ehren.f:115): K = X o A - H' A, all host N x N col-major. */
+void ehrenfestkernel_gpu_(const int* N, const double* h_H, const double* h_A, const double* h_X, double* h_K);
+
 /* Replaces Chebyshev_gpu.cpp:517-519. */
 double nakedbessel_(const int* n, const double* x);
 
@@ -164,6 +167,11 @@ int  dyb_estimate_spectral_bounds(dyb_ctx* ctx, int n_iter, double margin, doubl
  *   DUAL_ket = bra (data_output.f:87-147,242-263); fragment[i] in 0..n_frag-1 or -1. */
 int  dyb_ao_bra(dyb_ctx* ctx, int n_part, dyb_complex* h_AO_bra);
 int  dyb_populations(dyb_ctx* ctx, int n_part, int n_frag, const int32_t* fragment, double t, double* out);
+/* QuasiParticleEnergies (ElHl_Chebyshev.f:329-371) = dotc(Psi_bra, H' Psi_ket) per particle; out = (re,im) pairs. */
+int  dyb_quasiparticle_energies(dyb_ctx* ctx, int n_part, double* out_reim);
+/* Diabatic-Ehrenfest kernel K = X o A - H' A (diabatic-Ehren.f:115-119) with the H' resident in the context;
+ * A, X, K host N x N col-major. */
+int  dyb_ehrenfest_kernel(dyb_ctx* ctx, const double* h_A, const double* h_X, double* h_K);
 
 /* Raw recursion for benchmarks and kernel-level parity: run n_terms el+hole series
  * terms (one pass over H' each, fused epilogue, no host decisions) starting from the
