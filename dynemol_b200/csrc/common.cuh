@@ -127,6 +127,12 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with programmaticStreamSerialization may start while its
+// predecessor in the stream is still running; it must execute pdl_wait() before touching anything the
+// predecessor writes.  pdl_launch_dependents() lets the successor start being scheduled from this point on.
+__device__ __forceinline__ void pdl_wait()              { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // streaming 128-bit global load that does not allocate in L1 (H' is read exactly once per term)
 __device__ __forceinline__ double2 ldg_stream(const double* p) {
     double2 v;

@@ -97,6 +97,9 @@ epilogue_kernel(const EpiParams E)
     __shared__ double wpart[EPI_THREADS / 32][8];
     __shared__ int    is_last;
 
+    pdl_launch_dependents();        // the next dual product may start its H' prefetch while we run
+    pdl_wait();                     // slabs of the dual product that precedes us are complete and visible
+
     const int idx = blockIdx.x * EPI_THREADS + threadIdx.x;
     const int i = idx >> 2, pp = (idx >> 1) & 1, side = idx & 1;
     const PartPass pa = E.pass.part[pp];

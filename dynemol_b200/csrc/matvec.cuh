@@ -177,18 +177,22 @@ struct TileCursor {
     __device__ __forceinline__ void next(int TPP) { if (++ct == TPP) { ct = 0; ++panel; } }
 };
 
-__device__ __forceinline__ void issue_tile(uint8_t* smem, uint64_t* bar_full, const CUtensorMap* tmap, const MatvecParams& P,
-                                           int stage, const TileCursor& tc, uint64_t policy) {
-    uint8_t* dst = smem + (size_t)stage * STAGE_BYTES;
+// A stage is filled by two async copies that complete on the same mbarrier: the H' tile (TMA tensor load) and the
+// x_ket values of the tile's columns (bulk copy).  They can be issued at different times: the H' part does not
+// depend on the previous kernel's output, the x_ket part does.
+__device__ __forceinline__ void issue_tile_h(uint8_t* smem, uint64_t* bar_full, const CUtensorMap* tmap,
+                                             int stage, const TileCursor& tc, uint64_t policy) {
     mbar_arrive_expect_tx(&bar_full[stage], STAGE_TX_BYTES);
-    tma_load_3d(dst, tmap, &bar_full[stage], 0, tc.panel * N_CWARPS, tc.ct * TILE_COLS, policy);
-    bulk_load_1d(dst + STAGE_H_BYTES, P.Xk + (size_t)tc.ct * TILE_COLS * NQ, TILE_COLS * NQ * 8, &bar_full[stage]);
+    tma_load_3d(smem + (size_t)stage * STAGE_BYTES, tmap, &bar_full[stage], 0, tc.panel * N_CWARPS, tc.ct * TILE_COLS, policy);
+}
+__device__ __forceinline__ void issue_tile_x(uint8_t* smem, uint64_t* bar_full, const MatvecParams& P, int stage, const TileCursor& tc) {
+    bulk_load_1d(smem + (size_t)stage * STAGE_BYTES + STAGE_H_BYTES, P.Xk + (size_t)tc.ct * TILE_COLS * NQ, TILE_COLS * NQ * 8, &bar_full[stage]);
 }
 
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 dual_matvec_tma_kernel(const __grid_constant__ CUtensorMap tmap, const MatvecParams P)
 {
-    if (P.ctrl != nullptr && P.ctrl->all_latched) return;          // series already decided: skip the pass
+    pdl_launch_dependents();        // the epilogue of this term may be queued behind us right away
 
     // 128 B alignment is all the un-swizzled TMA destinations need; plain pointer arithmetic on the
     // __shared__ array keeps the address space visible to the compiler (LDS/STS, not generic LD/ST)
@@ -209,11 +213,22 @@ dual_matvec_tma_kernel(const __grid_constant__ CUtensorMap tmap, const MatvecPar
         prefetch_tensormap(&tmap);
         for (int s = 0; s < TMA_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], N_CWARPS); }
         fence_barrier_init();
-        // prologue: fill the ring
+        // prologue: start filling the ring with H' tiles -- they do not depend on the previous kernel, so under
+        // programmatic dependent launch this overlaps the tail of the preceding epilogue
         TileCursor tc = {panel0, ct0};
-        for (int i = 0; i < TMA_STAGES && i < nt; ++i) { issue_tile(smem, bar_full, &tmap, P, i, tc, policy); tc.next(P.TPP); }
+        for (int i = 0; i < TMA_STAGES && i < nt; ++i) { issue_tile_h(smem, bar_full, &tmap, i, tc, policy); tc.next(P.TPP); }
+    }
+    pdl_wait();                     // from here on the previous kernel's vectors / control block are visible
+    if (threadIdx.x == 0) {
+        TileCursor tc = {panel0, ct0};
+        for (int i = 0; i < TMA_STAGES && i < nt; ++i) { issue_tile_x(smem, bar_full, P, i, tc); tc.next(P.TPP); }
     }
     __syncthreads();
+    if (P.ctrl != nullptr && P.ctrl->all_latched) {                // series already decided: skip the pass,
+        if (threadIdx.x == 0)                                      // but never exit with copies in flight to our smem
+            for (int i = 0; i < TMA_STAGES && i < nt; ++i) mbar_wait(&bar_full[i], 0u);
+        return;
+    }
 
     ConsumerRegs r;
     zero_acc(r);
@@ -275,7 +290,7 @@ dual_matvec_tma_kernel(const __grid_constant__ CUtensorMap tmap, const MatvecPar
                     for (int ww = 1; ww < N_CWARPS; ++ww) sum += rs[ww * TILE_COLS * NQ];
                     P.bra_slab[((size_t)ret.panel * P.Ncpad + (size_t)ret.ct * TILE_COLS) * NQ + lane] = sum;
                 }
-                if (lane == 0 && jr + TMA_STAGES < nt) issue_tile(smem, bar_full, &tmap, P, sr, nxt, policy);
+                if (lane == 0 && jr + TMA_STAGES < nt) { issue_tile_h(smem, bar_full, &tmap, sr, nxt, policy); issue_tile_x(smem, bar_full, P, sr, nxt); }
                 __syncwarp();
             }
             ret.next(P.TPP); nxt.next(P.TPP);
@@ -307,6 +322,8 @@ __device__ __forceinline__ void ldg_tile(double2 (&h)[TILE_COLS][4], const Matve
 __global__ void __launch_bounds__(LDG_THREADS, 1)
 dual_matvec_ldg_kernel(const MatvecParams P)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     if (P.ctrl != nullptr && P.ctrl->all_latched) return;
     __shared__ double red[2][N_CWARPS][TILE_COLS * NQ];
 

@@ -87,6 +87,7 @@ struct dyb_ctx {
     int T = 0;
     size_t Lq = 0;                       // quad vector length (indices)
     int variant = DYB_KERNEL_TMA;
+    bool use_pdl = true;                 // programmatic dependent launch between the dual product and the epilogue
     cudaStream_t stream = nullptr;
     CUtensorMap tmap;
     bool have_tmap = false;
@@ -190,15 +191,28 @@ static MatvecParams matvec_params(dyb_ctx* c, const double* xk, const double* xb
     return P;
 }
 
+// Both hot kernels are launched with programmatic stream serialization (PDL): the successor may begin while the
+// predecessor drains; each kernel executes griddepcontrol.wait before it touches the predecessor's output.
+static cudaLaunchConfig_t pdl_config(dyb_ctx* c, unsigned grid, unsigned block, size_t smem, cudaLaunchAttribute* attr) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+    attr->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr->val.programmaticStreamSerializationAllowed = c->use_pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cfg;
+}
+
 static int launch_matvec(dyb_ctx* c, const double* xk, const double* xb, bool use_ctrl) {
     const MatvecParams P = matvec_params(c, xk, xb, use_ctrl);
+    cudaLaunchAttribute attr;
     if (c->variant == DYB_KERNEL_LDG) {
-        dual_matvec_ldg_kernel<<<c->grid, LDG_THREADS, 0, c->stream>>>(P);
+        cudaLaunchConfig_t cfg = pdl_config(c, c->grid, LDG_THREADS, 0, &attr);
+        CK(cudaLaunchKernelEx(&cfg, dual_matvec_ldg_kernel, P));
     } else {
-        dual_matvec_tma_kernel<<<c->grid, TMA_THREADS, TmaSmem::total, c->stream>>>(c->tmap, P);
+        cudaLaunchConfig_t cfg = pdl_config(c, c->grid, TMA_THREADS, TmaSmem::total, &attr);
+        CK(cudaLaunchKernelEx(&cfg, dual_matvec_tma_kernel, c->tmap, P));
     }
     c->launches++;
-    CK(cudaGetLastError());
     return DYB_OK;
 }
 
@@ -220,9 +234,10 @@ static EpiParams epi_params(dyb_ctx* c, int cur, int prv, int nxt) {
 static int epi_grid(const dyb_ctx* c) { return (4 * c->M + EPI_THREADS - 1) / EPI_THREADS; }
 
 static int launch_epilogue(dyb_ctx* c, const EpiParams& E) {
-    epilogue_kernel<<<epi_grid(c), EPI_THREADS, 0, c->stream>>>(E);
+    cudaLaunchAttribute attr;
+    cudaLaunchConfig_t cfg = pdl_config(c, epi_grid(c), EPI_THREADS, 0, &attr);
+    CK(cudaLaunchKernelEx(&cfg, epilogue_kernel, E));
     c->launches++;
-    CK(cudaGetLastError());
     return DYB_OK;
 }
 
@@ -558,6 +573,7 @@ int dyb_create(dyb_ctx** out, int device, int N, int row0, int n_rows) {
     CKCU(cudaDeviceSynchronize());     // the zero fills above ran on the legacy stream; c->stream is non-blocking
 #undef CKC
 #undef CKCU
+    if (const char* e = getenv("DYNEMOL_B200_PDL")) c->use_pdl = (e[0] != '0');
     *out = c;
     return DYB_OK;
 }
