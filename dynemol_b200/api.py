@@ -79,7 +79,7 @@ DECLARED_SYMBOLS = [
     "dyb_get_info", "dyb_upload_hprime", "dyb_upload_hprime_device", "dyb_upload_hprime_rows_device", "dyb_hprime_device", "dyb_form_hprime", "dyb_form_hprime_device",
     "dyb_download_hprime", "dyb_set_packets", "dyb_get_packets", "dyb_propagate", "dyb_ao_bra",
     "dyb_populations", "dyb_run_terms", "dyb_dual_matvec", "dyb_sync", "dyb_launch_count",
-    "dyb_comm_unique_id", "dyb_comm_init", "dyb_set_spectral_bounds", "dyb_get_spectral_bounds", "dyb_estimate_spectral_bounds",
+    "dyb_comm_unique_id", "dyb_comm_init", "dyb_comm_p2p_handle", "dyb_comm_p2p_open", "dyb_set_spectral_bounds", "dyb_get_spectral_bounds", "dyb_estimate_spectral_bounds",
     "dyb_quasiparticle_energies", "dyb_ehrenfest_kernel",
 ]
 
@@ -136,7 +136,7 @@ class Propagator:
     def info(self) -> dict:
         buf = (C.c_int64 * 16)()
         _check(lib.dyb_get_info(self._h, buf))
-        keys = ["N", "ld", "n_rows", "grid", "tiles", "segments", "sm_count", "smem_bytes", "variant", "panels", "tiles_per_panel", "passes_last"]
+        keys = ["N", "ld", "n_rows", "grid", "tiles", "segments", "sm_count", "smem_bytes", "variant", "panels", "tiles_per_panel", "passes_last", "p2p"]
         return {k: int(buf[i]) for i, k in enumerate(keys)}
 
     # ---- operator
@@ -250,6 +250,14 @@ class Propagator:
         K = np.empty((self.N, self.N), dtype=np.float64, order="F")
         _check(lib.dyb_ehrenfest_kernel(self._h, _p(A), _p(X), _p(K)))
         return K
+
+    def comm_p2p_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        _check(lib.dyb_comm_p2p_handle(self._h, buf))
+        return buf.raw
+
+    def comm_p2p_open(self, handles: bytes):
+        _check(lib.dyb_comm_p2p_open(self._h, C.c_char_p(handles)))
 
     def sync(self):
         _check(lib.dyb_sync(self._h))

@@ -133,6 +133,23 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* tmap) {
 __device__ __forceinline__ void pdl_wait()              { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ---- cross-GPU flags over NVLink peer memory (system scope) -------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// bounded spin: a peer that never arrives must not hang the GPU (trap after ~2 s)
+__device__ __forceinline__ void wait_flag_ge(const unsigned long long* p, unsigned long long target) {
+    for (long long it = 0; ld_acquire_sys(p) < target; ++it) {
+        __nanosleep(64);
+        if (it > (1ll << 22)) { printf("dynemol_b200: peer flag timeout (have %llu, want %llu)\n", ld_acquire_sys(p), target); __trap(); }
+    }
+}
+
 // streaming 128-bit global load that does not allocate in L1 (H' is read exactly once per term)
 __device__ __forceinline__ double2 ldg_stream(const double* p) {
     double2 v;

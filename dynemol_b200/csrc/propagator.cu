@@ -116,6 +116,13 @@ struct dyb_ctx {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
     double *rs_send = nullptr, *rs_recv = nullptr, *scal_all = nullptr, *full_tmp = nullptr;
+    // fused peer-memory exchange (NVLink P2P through CUDA IPC): one shared buffer per rank
+    bool p2p = false;
+    char* comm_buf = nullptr;            // [rs_send x2 | ket vectors x3 | scalar tables x2 | ready flags | done flags]
+    char* peer_base[MAX_PEERS] = {nullptr};
+    size_t off_rs[2] = {0, 0}, off_vk[3] = {0, 0, 0}, off_scal[2] = {0, 0}, off_ready = 0, off_done = 0, comm_bytes = 0;
+    unsigned long long epoch = 0;
+    bool vk_in_comm = false;
 };
 
 static int ensure_device(int device) {
@@ -249,6 +256,38 @@ static int run_term(dyb_ctx* c, const EpiParams& E, int cur, int nxt, bool use_c
     if ((rc = launch_matvec(c, c->vk[cur], c->vb[cur], use_ctrl))) return rc;
     if (c->world == 1) return launch_epilogue(c, E);
     const int n2 = 2 * c->N;
+    if (c->p2p) {
+        // fused exchange over NVLink peer memory: local panel sum -> publish -> one kernel does reduce-scatter (peer
+        // loads), epilogue, all-gather (peer stores), scalar exchange and the replicated decision
+        const unsigned long long epoch = ++c->epoch;
+        const int par = (int)(epoch & 1);
+        double* my_rs = reinterpret_cast<double*>(c->comm_buf + c->off_rs[par]);
+        bra_panel_reduce_kernel<<<(n2 + 255) / 256, 256, 0, c->stream>>>(c->N, c->NP, c->Ncpad, c->bra_slab, my_rs);
+        c->launches++;
+        CK(cudaGetLastError());
+        PeerTable T;
+        memset(&T, 0, sizeof T);
+        T.world = c->world; T.rank = c->rank; T.epoch = epoch;
+        for (int r = 0; r < c->world; ++r) {
+            char* pb = c->peer_base[r];
+            T.rs_send[r]  = reinterpret_cast<const double*>(pb + c->off_rs[par]);
+            T.ket_next[r] = reinterpret_cast<double*>(pb + c->off_vk[nxt]);
+            T.scal_all[r] = reinterpret_cast<double*>(pb + c->off_scal[par]);
+            T.ready[r]    = reinterpret_cast<unsigned long long*>(pb + c->off_ready) + c->rank;
+            T.done[r]     = reinterpret_cast<unsigned long long*>(pb + c->off_done) + c->rank;
+        }
+        T.my_ready = reinterpret_cast<const unsigned long long*>(c->comm_buf + c->off_ready);
+        T.my_done  = reinterpret_cast<const unsigned long long*>(c->comm_buf + c->off_done);
+        signal_ready_kernel<<<1, 32, 0, c->stream>>>(T);
+        c->launches++;
+        CK(cudaGetLastError());
+        EpiParams E2 = E;
+        E2.defer_decision = 0;
+        epilogue_p2p_kernel<<<epi_grid(c), EPI_THREADS, 0, c->stream>>>(E2, T);
+        c->launches++;
+        CK(cudaGetLastError());
+        return DYB_OK;
+    }
     bra_panel_reduce_kernel<<<(n2 + 255) / 256, 256, 0, c->stream>>>(c->N, c->NP, c->Ncpad, c->bra_slab, c->rs_send);
     c->launches++;
     CK(cudaGetLastError());
@@ -517,6 +556,9 @@ int dyb_destroy(dyb_ctx* c) {
     double** bufs[] = {&c->H, &c->S, &c->psi_b, &c->psi_k, &c->sum_b, &c->sum_k, &c->vb[0], &c->vb[1], &c->vb[2],
                        &c->vk[0], &c->vk[1], &c->vk[2], &c->ket_slab, &c->bra_slab, &c->blockpart, &c->scal, &c->io};
     for (auto b : bufs) if (*b) cudaFree(*b);
+    if (c->p2p) for (int r = 0; r < c->world; ++r) if (r != c->rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
+    if (c->vk_in_comm) c->vk[0] = c->vk[1] = c->vk[2] = nullptr;       // they live inside comm_buf
+    if (c->comm_buf) cudaFree(c->comm_buf);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     for (double** b : {&c->rs_send, &c->rs_recv, &c->scal_all, &c->full_tmp}) if (*b) cudaFree(*b);
     if (c->ipiv) cudaFree(c->ipiv);
@@ -590,7 +632,7 @@ int dyb_get_info(dyb_ctx* c, int64_t* o) {
     if (!c || !o) return fail(DYB_EINVAL, "NULL argument");
     memset(o, 0, 16 * sizeof(int64_t));
     o[0] = c->N; o[1] = c->ld; o[2] = c->M; o[3] = c->grid; o[4] = c->T; o[5] = c->n_seg; o[6] = c->sm_count;
-    o[7] = TmaSmem::total; o[8] = c->variant; o[9] = c->NP; o[10] = c->TPP; o[11] = c->passes_last;
+    o[7] = TmaSmem::total; o[8] = c->variant; o[9] = c->NP; o[10] = c->TPP; o[11] = c->passes_last; o[12] = c->p2p ? 1 : 0;
     return DYB_OK;
 }
 
@@ -797,6 +839,54 @@ int dyb_comm_unique_id(char* out128) {
     ncclUniqueId id;
     CKN(g_nccl.GetUniqueId(&id));
     memcpy(out128, id.internal, NCCL_UNIQUE_ID_BYTES);
+    return DYB_OK;
+}
+
+// ---- fused peer-memory exchange: every rank exports one IPC buffer, then maps the peers' buffers --------------
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int dyb_comm_p2p_handle(dyb_ctx* c, char* out64) {
+    if (!c || !out64) return fail(DYB_EINVAL, "NULL argument");
+    if (!c->comm || c->world < 2) return fail(DYB_EINVAL, "dyb_comm_init (world >= 2) must come first");
+    if (c->world > MAX_PEERS) return fail(DYB_EINVAL, "at most %d ranks", MAX_PEERS);
+    CK(cudaSetDevice(c->device));
+    if (!c->comm_buf) {
+        const size_t vec = align_up(c->Lq * NQ * sizeof(double), 4096);
+        size_t off = 0;
+        for (int i = 0; i < 2; ++i) { c->off_rs[i] = off; off += vec; }
+        for (int i = 0; i < 3; ++i) { c->off_vk[i] = off; off += vec; }
+        for (int i = 0; i < 2; ++i) { c->off_scal[i] = off; off += align_up((size_t)c->world * 8 * sizeof(double), 4096); }
+        c->off_ready = off; off += 4096;
+        c->off_done = off;  off += 4096;
+        c->comm_bytes = off;
+        CK(cudaMalloc(&c->comm_buf, off));
+        CK(cudaMemset(c->comm_buf, 0, off));
+        CK(cudaDeviceSynchronize());
+        // the rotating ket vectors move into the shared buffer: the peers store their slices straight into them
+        CK(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < 3; ++i) { if (c->vk[i]) cudaFree(c->vk[i]); c->vk[i] = reinterpret_cast<double*>(c->comm_buf + c->off_vk[i]); }
+        c->vk_in_comm = true;
+    }
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->comm_buf));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(out64, &h, 64);
+    return DYB_OK;
+}
+
+int dyb_comm_p2p_open(dyb_ctx* c, const char* handles /* world x 64 bytes, rank order */) {
+    if (!c || !handles) return fail(DYB_EINVAL, "NULL argument");
+    if (!c->comm_buf) return fail(DYB_EINVAL, "dyb_comm_p2p_handle must come first");
+    CK(cudaSetDevice(c->device));
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank) { c->peer_base[r] = c->comm_buf; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * 64, 64);
+        void* ptr = nullptr;
+        CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_base[r] = static_cast<char*>(ptr);
+    }
+    c->p2p = true;
     return DYB_OK;
 }
 

@@ -42,8 +42,16 @@ def init_sharded(N: int, dist, local_rank: int):
     world, rank = dist.get_world_size(), dist.get_rank()
     row0, m = shard_rows(N, world, rank)
     P = api.Propagator(N, device=local_rank, row0=row0, n_rows=m)
-    uid = broadcast_unique_id(dist, api.comm_unique_id, device=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    uid = broadcast_unique_id(dist, api.comm_unique_id, device=dev)
     P.comm_init(rank, world, uid)
+    if world <= 8 and os.environ.get("DYNEMOL_B200_P2P", "1") != "0":
+        # fused exchange over NVLink peer memory: all-gather the 64-byte CUDA-IPC handles, map the peers
+        mine = torch.tensor(list(P.comm_p2p_handle()), dtype=torch.uint8, device=dev)
+        allh = torch.empty(64 * world, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine)
+        P.comm_p2p_open(bytes(allh.cpu().tolist()))
+        dist.barrier()
     return P, row0, m
 
 
@@ -119,7 +127,10 @@ def bench_main(args):
         line = {"metric": B.METRIC, "value": round(value, 2), "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "synthetic EHT Hamiltonian N=%d basis, row-sharded H' over %d GPUs, NCCL reduce-scatter(bra)+all-gather(ket) per term" % (N, world),
+                "config": {"workload": "synthetic EHT Hamiltonian N=%d basis, row-sharded H' over %d GPUs, %s per term" % (
+                               N, world, "fused NVLink peer-memory exchange (reduce-scatter by peer loads, all-gather by peer stores) inside the epilogue kernel"
+                               if info.get("p2p") else "NCCL reduce-scatter(bra)+all-gather(ket)"),
+                           "exchange": "p2p-fused" if info.get("p2p") else "nccl",
                            "basis": N, "rows_per_gpu": m, "terms_per_step": B.TERMS_PER_STEP,
                            "l2": "inputs larger than L2 (%.2f GB of H' per GPU per pass)" % (per_gpu_bytes / 1e9),
                            "operator": "Hueckel h + dense decaying tail, surrogate for S^-1 h (SURVEY.md 8d)", "grid": info["grid"], "gen_s": round(gen_s, 1)},

@@ -192,6 +192,12 @@ int  dyb_dual_matvec(dyb_ctx* ctx, int n_part, const dyb_complex* xb, const dyb_
  * partials are reduce-scattered and the new ket slices all-gathered with NCCL over NVLink. */
 int  dyb_comm_unique_id(char* out128);
 int  dyb_comm_init(dyb_ctx* ctx, int rank, int world, const char* id128);
+/* Optional, after dyb_comm_init: fused exchange over NVLink peer memory.  Every rank exports one CUDA-IPC buffer
+ * (64-byte handle), the host layer all-gathers the handles (rank order), every rank maps its peers.  From then on
+ * each term's reduce-scatter (bra) and all-gather (ket) happen INSIDE the epilogue kernel as peer loads/stores,
+ * with st.release.sys / ld.acquire.sys epoch flags instead of NCCL launches. */
+int  dyb_comm_p2p_handle(dyb_ctx* ctx, char* out64);
+int  dyb_comm_p2p_open(dyb_ctx* ctx, const char* handles);
 
 int  dyb_sync(dyb_ctx* ctx);
 int64_t dyb_launch_count(dyb_ctx* ctx);   /* kernels of THIS library launched so far */

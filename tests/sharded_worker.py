@@ -38,7 +38,7 @@ def main():
     mark('propagated')
     bra, ket = P.get_packets()
     mark('packets read')
-    out = {"rank": rank, "ok": True}
+    out = {"rank": rank, "ok": True, "p2p": int(P.info()["p2p"])}
     if rank == 0:
         import oracle
         worst = 0.0
