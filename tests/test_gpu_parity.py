@@ -225,3 +225,63 @@ def test_full_size_properties(api):
     ref_b = torch.complex(Hm.t() @ at.real, Hm.t() @ at.imag).cpu().numpy()
     assert relerr(yb_, ref_k) < 1e-12 and relerr(ya, ref_b) < 1e-12
     P.close()
+
+
+# ----------------------------------------------------------------------------- edge cases of the driver
+@pytest.mark.parametrize("N", [5, 130, 259])
+def test_propagate_ragged_sizes_random_operator(api, oracle_mod, N):
+    """N not a multiple of anything (padding rows/columns, partial TMA boxes, a single partial panel) with a generic
+    non-symmetric operator similar to a real-spectrum one (H' = A^-1 D A)."""
+    rng = np.random.default_rng(N)
+    A = rng.normal(size=(N, N)) + 3.0 * np.eye(N)
+    D = np.diag(rng.uniform(-20.0, 60.0, size=N))
+    Hp = np.asfortranarray(np.linalg.solve(A, D @ A))
+    ket = rng.normal(size=(N, 2)) + 1j * rng.normal(size=(N, 2))
+    M = A.T @ A                                            # bra = M ket makes <bra|ket> > 0 and H'^T M = M H' ... not needed exactly
+    bra = M @ ket
+    nrm = np.sqrt(np.abs(np.einsum("ip,ip->p", np.conj(bra), ket)))
+    ket = np.asfortranarray(ket / nrm); bra = np.asfortranarray(bra / nrm)
+    dt = 3e-6; tau0 = dt / H_BAR
+    P = api.Propagator(N)
+    P.upload_hprime(Hp)
+    P.set_packets(bra, ket)
+    save_tau, traces = P.propagate(0.0, dt, tau0)
+    gb, gk = P.get_packets()
+    for p in range(2):
+        b, k, _, st, tr = oracle_mod.propagation(Hp, bra[:, p], ket[:, p], 0.0, dt, tau0)
+        assert events3(traces[p]) == events3(tr) and save_tau[p] == st
+        assert relerr(gb[:, p], b) < REL_TOL and relerr(gk[:, p], k) < REL_TOL
+    P.close()
+
+
+def test_propagate_zero_length_slice_still_takes_one_step(api, oracle_mod):
+    """t_max == t_init: the reference still runs the first Convergence and advances by tau (Taylor.f:65-81)."""
+    N = 64
+    w = syn.make_workload(N)
+    Hp = oracle_mod.sy_multiply(oracle_mod.sy_invert(w.S), w.h)
+    P = api.Propagator(N)
+    P.upload_hprime(Hp)
+    P.set_packets(w.Psi_bra[:, 0], w.Psi_ket[:, 0])
+    tau0 = 1e-4
+    save_tau, traces = P.propagate(1.0, 1.0, tau0)
+    gb, gk = P.get_packets()
+    b, k, _, st, tr = oracle_mod.propagation(Hp, w.Psi_bra[:, 0], w.Psi_ket[:, 0], 1.0, 1.0, tau0)
+    assert events3(traces[0]) == events3(tr) and save_tau[0] == st and traces[0].n_substeps == 0
+    assert relerr(gb[:, 0], b) < REL_TOL and relerr(gk[:, 0], k) < REL_TOL
+    assert not np.array_equal(gk[:, 0], w.Psi_ket[:, 0])
+    P.close()
+
+
+def test_bad_arguments_are_reported(api):
+    P = api.Propagator(32)
+    with pytest.raises(api.DynemolB200Error) as e:
+        P.propagate(0.0, 1e-6, 1e-3)                         # no packets yet
+    assert e.value.code == api.EINVAL
+    P.set_packets(np.ones((32, 2), complex), np.ones((32, 2), complex))
+    with pytest.raises(api.DynemolB200Error) as e:
+        P.ao_bra()                                           # needs the factor of S from dyb_form_hprime
+    assert "dyb_form_hprime" in str(e.value)
+    with pytest.raises(api.DynemolB200Error) as e:
+        P.propagate(0.0, 1e-6, 1e-3, mode=api.MODE_CHEBYSHEV)   # no spectral bounds
+    assert "spectral bounds" in str(e.value)
+    P.close()

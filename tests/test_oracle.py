@@ -177,3 +177,41 @@ def test_chebyshev_variant_small_tau(oracle_mod):
     c = oracle_mod.cheb_coefficient(tau)
     from scipy.special import jv
     assert np.allclose(c[0], jv(0, tau)) and np.allclose(c[3], 2 * jv(3, tau) * (-1j) ** 3)
+
+
+# ---------------------------------------------------------------------------------- Chebyshev mode (product spec)
+@pytest.mark.parametrize("name", ["cheb_N64_dt5e-4", "cheb_N128_dt5e-5"])
+def test_scaled_chebyshev_oracle_reproduces_golden(oracle_mod, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    Hp = g["H_prime"]; emin, emax = float(g["emin"]), float(g["emax"])
+    ebar, de = 0.5 * (emax + emin), 0.5 * (emax - emin)
+    for p, tag in enumerate(("el", "hl")):
+        b, k, _, st, tr = oracle_mod.cheb_scaled_propagation(Hp, g["Psi_bra0"][:, p], g["Psi_ket0"][:, p],
+                                                             float(g["t_init"]), float(g["t_max"]), float(g["tau0"]), ebar, de)
+        assert np.abs(b - g[f"{tag}_bra"]).max() < 1e-14 and np.abs(k - g[f"{tag}_ket"]).max() < 1e-14
+        assert tr.n_matvec_pairs == int(g[f"{tag}_matvec_pairs"]) and st == float(g[f"{tag}_save_tau"])
+
+
+def test_scaled_chebyshev_vs_numpy_and_expm(oracle_mod):
+    N, dt = 48, 2e-4
+    w = syn.make_workload(N)
+    Hp = _hprime(oracle_mod, w)
+    e = np.linalg.eigvals(Hp).real
+    lo, hi = e.min() - 0.05 * (e.max() - e.min()), e.max() + 0.05 * (e.max() - e.min())
+    ebar, de = 0.5 * (hi + lo), 0.5 * (hi - lo)
+    tau0 = dt / tn.H_BAR
+    U = expm(-1j * tau0 * Hp)
+    b, k, _, st, tr = oracle_mod.cheb_scaled_propagation(Hp, w.Psi_bra[:, 0], w.Psi_ket[:, 0], 0.0, dt, tau0, ebar, de)
+    log = {}
+    b2, k2, _, st2 = tn.cheb_propagation(Hp, w.Psi_bra[:, 0].copy(), w.Psi_ket[:, 0].copy(), 0.0, dt, tau0, ebar, de, log)
+    assert np.abs(b - b2).max() < 1e-11 and np.abs(k - k2).max() < 1e-11 and st == st2
+    assert [(x[0], x[1], x[2]) for x in tr.events()] == [(x[0], x[1], x[2]) for x in log["events"]][:256]
+    assert np.abs(U @ w.Psi_ket[:, 0] - k).max() < 1e-7 and np.abs(U.T @ w.Psi_bra[:, 0] - b).max() < 1e-7
+    # far fewer dual products than the Taylor series for the same step
+    _, _, _, _, tr_t = oracle_mod.propagation(Hp, w.Psi_bra[:, 0], w.Psi_ket[:, 0], 0.0, dt, tau0)
+    assert tr.n_matvec_pairs * 5 < tr_t.n_matvec_pairs
+    # with ebar = 0, de = 1 the scaled series IS the reference's un-linked series (Chebyshev_gpu.cpp:524-632)
+    tau = 0.3 / np.abs(e).max()
+    ok, b1, k1, C1, kr1, kx1 = oracle_mod.cheb_convergence(Hp, w.Psi_bra[:, 0], w.Psi_ket[:, 0], tau, 1.0)
+    b3, k3, _, _, tr3 = oracle_mod.cheb_scaled_propagation(Hp, w.Psi_bra[:, 0], w.Psi_ket[:, 0], 0.0, tau * tn.H_BAR, tau, 0.0, 1.0)
+    assert ok and tr3.events()[0][1] == kx1 and np.array_equal(b1, b3) and np.array_equal(k1, k3)
