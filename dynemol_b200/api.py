@@ -76,7 +76,7 @@ DECLARED_SYMBOLS = [
     "propagationelhl_gpucaller_", "propagationelhl2_gpucaller_", "propagation_gpucaller_", "nakedbessel_", "ehrenfestkernel_gpu_",
     "gpu_init_", "gpu_finalize_", "gpu_pin_", "gpu_unpin_",
     "dyb_last_error", "dyb_version", "dyb_device_count", "dyb_create", "dyb_destroy", "dyb_set_kernel",
-    "dyb_get_info", "dyb_upload_hprime", "dyb_upload_hprime_device", "dyb_upload_hprime_rows_device", "dyb_hprime_device", "dyb_form_hprime", "dyb_form_hprime_device",
+    "dyb_get_info", "dyb_upload_hprime", "dyb_upload_hprime_device", "dyb_upload_hprime_rows_device", "dyb_hprime_device", "dyb_form_hprime", "dyb_form_hprime_device", "dyb_form_hprime_from_overlap",
     "dyb_download_hprime", "dyb_set_packets", "dyb_get_packets", "dyb_propagate", "dyb_ao_bra",
     "dyb_populations", "dyb_run_terms", "dyb_dual_matvec", "dyb_sync", "dyb_launch_count",
     "dyb_comm_unique_id", "dyb_comm_init", "dyb_comm_p2p_handle", "dyb_comm_p2p_open", "dyb_set_spectral_bounds", "dyb_get_spectral_bounds", "dyb_estimate_spectral_bounds",
@@ -163,6 +163,14 @@ class Propagator:
         S = _fd(S); h = _fd(h)
         out = np.empty((self.N, self.N), dtype=np.float64, order="F") if want_hprime else None
         _check(lib.dyb_form_hprime(self._h, _p(S), _p(h), _p(out) if want_hprime else None))
+        return out
+
+    def form_hprime_from_overlap(self, S, IP, k_WH, V_shift, want_hprime: bool = True):
+        """Build_Huckel on the device (h = X o S) followed by H' = S^-1 h; only S is uploaded."""
+        S = _fd(S); IP = np.ascontiguousarray(IP, dtype=np.float64); k_WH = np.ascontiguousarray(k_WH, dtype=np.float64)
+        V_shift = np.ascontiguousarray(V_shift, dtype=np.float64)
+        out = np.empty((self.N, self.N), dtype=np.float64, order="F") if want_hprime else None
+        _check(lib.dyb_form_hprime_from_overlap(self._h, _p(S), _p(IP), _p(k_WH), _p(V_shift), _p(out) if want_hprime else None))
         return out
 
     def form_hprime_device(self, d_S: int, lds: int, d_h: int, ldh: int):

@@ -553,11 +553,11 @@ int dyb_destroy(dyb_ctx* c) {
     if (!c) return DYB_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->vk_in_comm) c->vk[0] = c->vk[1] = c->vk[2] = nullptr;       // they live inside comm_buf, freed below
     double** bufs[] = {&c->H, &c->S, &c->psi_b, &c->psi_k, &c->sum_b, &c->sum_k, &c->vb[0], &c->vb[1], &c->vb[2],
                        &c->vk[0], &c->vk[1], &c->vk[2], &c->ket_slab, &c->bra_slab, &c->blockpart, &c->scal, &c->io};
     for (auto b : bufs) if (*b) cudaFree(*b);
     if (c->p2p) for (int r = 0; r < c->world; ++r) if (r != c->rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
-    if (c->vk_in_comm) c->vk[0] = c->vk[1] = c->vk[2] = nullptr;       // they live inside comm_buf
     if (c->comm_buf) cudaFree(c->comm_buf);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     for (double** b : {&c->rs_send, &c->rs_recv, &c->scal_all, &c->full_tmp}) if (*b) cudaFree(*b);
@@ -704,18 +704,23 @@ static int ensure_solver(dyb_ctx* c) {
 // (Cholesky; LU with partial pivoting if S is not numerically SPD, as the reference's GPU flavour
 // GPU_Interface.cpp:910-929) and the N right-hand sides are solved in place: fewer flops, no explicit
 // inverse, same result to O(cond(S) eps).  The factor is kept for AO_bra = S^-1 Psi_bra.
+struct DevScratch {                         // freed on every exit path
+    void* p = nullptr;
+    ~DevScratch() { if (p) cudaFree(p); }
+};
+
 static int factor_and_solve(dyb_ctx* c, const std::function<int()>& reload_S) {
     const int64_t n = c->N;
+    c->have_factor = false;
     size_t wd = 0, wh = 0;
     int* d_info = reinterpret_cast<int*>(c->scal + 32);
     CKS(cusolverDnXpotrf_bufferSize(c->solver, c->sparams, CUBLAS_FILL_MODE_UPPER, n, CUDA_R_64F, c->S, n, CUDA_R_64F, &wd, &wh));
-    void* d_work = nullptr; std::vector<char> h_work(wh ? wh : 1);
-    if (wd) CK(cudaMalloc(&d_work, wd));
+    DevScratch w1; std::vector<char> h_work(wh ? wh : 1);
+    if (wd) CK(cudaMalloc(&w1.p, wd));
     cusolverStatus_t st = cusolverDnXpotrf(c->solver, c->sparams, CUBLAS_FILL_MODE_UPPER, n, CUDA_R_64F, c->S, n, CUDA_R_64F,
-                                           d_work, wd, h_work.data(), wh, d_info);
+                                           w1.p, wd, h_work.data(), wh, d_info);
     int info = 0;
     if (st == CUSOLVER_STATUS_SUCCESS) { CK(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
-    if (d_work) cudaFree(d_work);
     if (st != CUSOLVER_STATUS_SUCCESS) return fail(DYB_ECUDA, "cusolverDnXpotrf status %d", (int)st);
     if (info == 0) {
         CKS(cusolverDnXpotrs(c->solver, c->sparams, CUBLAS_FILL_MODE_UPPER, n, n, CUDA_R_64F, c->S, n, CUDA_R_64F, c->H, c->ld, d_info));
@@ -727,11 +732,10 @@ static int factor_and_solve(dyb_ctx* c, const std::function<int()>& reload_S) {
         if (rc) return rc;
         if (!c->ipiv) CK(cudaMalloc(&c->ipiv, sizeof(int64_t) * n));
         CKS(cusolverDnXgetrf_bufferSize(c->solver, c->sparams, n, n, CUDA_R_64F, c->S, n, CUDA_R_64F, &wd, &wh));
-        d_work = nullptr; h_work.resize(wh ? wh : 1);
-        if (wd) CK(cudaMalloc(&d_work, wd));
-        st = cusolverDnXgetrf(c->solver, c->sparams, n, n, CUDA_R_64F, c->S, n, c->ipiv, CUDA_R_64F, d_work, wd, h_work.data(), wh, d_info);
+        DevScratch w2; h_work.resize(wh ? wh : 1);
+        if (wd) CK(cudaMalloc(&w2.p, wd));
+        st = cusolverDnXgetrf(c->solver, c->sparams, n, n, CUDA_R_64F, c->S, n, c->ipiv, CUDA_R_64F, w2.p, wd, h_work.data(), wh, d_info);
         if (st == CUSOLVER_STATUS_SUCCESS) { CK(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
-        if (d_work) cudaFree(d_work);
         if (st != CUSOLVER_STATUS_SUCCESS) return fail(DYB_ECUDA, "cusolverDnXgetrf status %d", (int)st);
         if (info != 0) return fail(DYB_ESINGULAR, "overlap matrix is singular (getrf info=%d)", info);
         CKS(cusolverDnXgetrs(c->solver, c->sparams, CUBLAS_OP_N, n, n, CUDA_R_64F, c->S, n, c->ipiv, CUDA_R_64F, c->H, c->ld, d_info));
@@ -751,6 +755,51 @@ int dyb_form_hprime(dyb_ctx* c, const double* h_S, const double* h_h, double* h_
     auto load_S = [&]() -> int { CK(cudaMemcpyAsync(c->S, h_S, n * n * 8, cudaMemcpyHostToDevice, c->stream)); return DYB_OK; };
     if ((rc = load_S())) return rc;
     CK(cudaMemcpy2DAsync(c->H, (size_t)c->ld * 8, h_h, n * 8, n * 8, n, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = factor_and_solve(c, load_S))) return rc;
+    if (h_H_out) CK(cudaMemcpy2DAsync(h_H_out, n * 8, c->H, (size_t)c->ld * 8, n * 8, n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return DYB_OK;
+}
+
+// Build_Huckel on the device (ElHl_Chebyshev.f:296-323, X_ij of hamiltonians.f:33-63): h(i,j) = X_ij * S(i,j), computed
+// from the upper triangle of S and mirrored like the reference's loop (j = 1..N, i = 1..j).  With this only S and
+// three per-orbital vectors cross PCIe instead of S and h.
+__global__ void build_huckel_kernel(int n, const double* __restrict__ S, const double* __restrict__ IP,
+                                    const double* __restrict__ kWH, const double* __restrict__ Vs, double* __restrict__ h, long long ldh)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= n) return;
+    const int a = min(i, j), b = max(i, j);
+    const double s = S[(size_t)a + (size_t)b * n];
+    double x;
+    if (i == j) x = IP[i] + Vs[i];
+    else {
+        const double c1 = IP[a] - IP[b], c2 = IP[a] + IP[b];
+        const double c3 = (c1 / c2) * (c1 / c2);
+        const double c4 = (Vs[a] + Vs[b]) * 0.5;
+        const double kw = (kWH[a] + kWH[b]) * 0.5;
+        const double keff = kw + c3 + c3 * c3 * (1.0 - kw);
+        x = keff * c2 * 0.5 + c4;
+    }
+    h[(size_t)i + (size_t)j * ldh] = x * s;
+}
+
+int dyb_form_hprime_from_overlap(dyb_ctx* c, const double* h_S, const double* IP, const double* k_WH, const double* V_shift, double* h_H_out) {
+    if (!c || !h_S || !IP || !k_WH || !V_shift) return fail(DYB_EINVAL, "NULL argument");
+    if (c->M != c->N) return fail(DYB_EINVAL, "full-matrix contexts only");
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_solver(c);
+    if (rc) return rc;
+    const size_t n = c->N;
+    auto load_S = [&]() -> int { CK(cudaMemcpyAsync(c->S, h_S, n * n * 8, cudaMemcpyHostToDevice, c->stream)); return DYB_OK; };
+    if ((rc = load_S())) return rc;
+    double* par = c->io;                                            // 3 n doubles of the 8 n staging buffer
+    CK(cudaMemcpyAsync(par, IP, n * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(par + n, k_WH, n * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(par + 2 * n, V_shift, n * 8, cudaMemcpyHostToDevice, c->stream));
+    build_huckel_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)n), 256, 0, c->stream>>>((int)n, c->S, par, par + n, par + 2 * n, c->H, c->ld);
+    c->launches++;
+    CK(cudaGetLastError());
     if ((rc = factor_and_solve(c, load_S))) return rc;
     if (h_H_out) CK(cudaMemcpy2DAsync(h_H_out, n * 8, c->H, (size_t)c->ld * 8, n * 8, n, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -1175,8 +1224,9 @@ int dyb_ehrenfest_kernel(dyb_ctx* c, const double* h_A, const double* h_X, doubl
     if (c->M != c->N) return fail(DYB_EINVAL, "full-matrix contexts only");
     CK(cudaSetDevice(c->device));
     const size_t n = c->N, bytes = n * n * 8;
-    double *A = nullptr, *X = nullptr, *K = nullptr;
-    CK(cudaMalloc(&A, bytes)); CK(cudaMalloc(&X, bytes)); CK(cudaMalloc(&K, bytes));
+    DevScratch bA, bX, bK;
+    CK(cudaMalloc(&bA.p, bytes)); CK(cudaMalloc(&bX.p, bytes)); CK(cudaMalloc(&bK.p, bytes));
+    double *A = static_cast<double*>(bA.p), *X = static_cast<double*>(bX.p), *K = static_cast<double*>(bK.p);
     int rc = DYB_OK;
     do {
         if (!c->blas) { if (cublasCreate(&c->blas) != CUBLAS_STATUS_SUCCESS || cublasSetStream(c->blas, c->stream) != CUBLAS_STATUS_SUCCESS) { rc = fail(DYB_ECUDA, "cublasCreate failed"); break; } }
@@ -1189,7 +1239,6 @@ int dyb_ehrenfest_kernel(dyb_ctx* c, const double* h_A, const double* h_X, doubl
         if (cudaGetLastError() != cudaSuccess || cudaMemcpyAsync(h_K, K, bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
             cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = fail(DYB_ECUDA, "Ehrenfest kernel failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
     } while (0);
-    cudaFree(A); cudaFree(X); cudaFree(K);
     return rc;
 }
 

@@ -142,6 +142,10 @@ int  dyb_upload_hprime_rows_device(dyb_ctx* ctx, const void* d_rows, int64_t lda
 int  dyb_hprime_device(dyb_ctx* ctx, void** d_ptr, int64_t* ld);
 int  dyb_form_hprime(dyb_ctx* ctx, const double* h_S, const double* h_h, double* h_H_out /* may be NULL */);
 int  dyb_form_hprime_device(dyb_ctx* ctx, const void* d_S, int64_t lds, const void* d_h, int64_t ldh);
+/* Same, with the Hueckel matrix built on the device: h(i,j) = X_ij(IP, k_WH, V_shift) * S(i,j)
+ * (Build_Huckel, ElHl_Chebyshev.f:296-323; X_ij, hamiltonians.f:33-63) so that only S crosses PCIe. */
+int  dyb_form_hprime_from_overlap(dyb_ctx* ctx, const double* h_S, const double* IP, const double* k_WH,
+                                  const double* V_shift, double* h_H_out /* may be NULL */);
 int  dyb_download_hprime(dyb_ctx* ctx, double* h_H, int64_t lda);
 
 /* Wavepackets: n_part (1 or 2) columns of N complex, col-major. */

@@ -69,3 +69,20 @@ def test_formation_lu_fallback_for_indefinite_overlap(api):
     P.set_packets(w.Psi_bra, w.Psi_ket)
     assert relerr(P.ao_bra(), np.linalg.solve(S, w.Psi_bra)) < 1e-10
     P.close()
+
+
+def test_build_huckel_on_device(api, oracle_mod):
+    """Build_Huckel (ElHl_Chebyshev.f:296-323) on the device: same H' as uploading the host-built h."""
+    N = 256
+    w = syn.make_workload(N)
+    P = api.Propagator(N)
+    Hp_a = P.form_hprime(w.S, w.h)
+    Hp_b = P.form_hprime_from_overlap(w.S, w.IP, w.k_WH, w.V_shift)
+    assert relerr(Hp_b, Hp_a) < 1e-13
+    # V_shift and k_WH really enter: perturb them and compare with the oracle's Build_Huckel
+    rng = np.random.default_rng(2)
+    V = rng.normal(scale=0.3, size=N); K = w.k_WH + rng.uniform(-0.2, 0.2, size=N)
+    h2 = oracle_mod.build_huckel(w.IP, K, V, w.S)
+    Hp_c = P.form_hprime_from_overlap(w.S, w.IP, K, V)
+    assert relerr(Hp_c, np.linalg.solve(w.S, h2)) < 1e-11
+    P.close()
