@@ -61,6 +61,20 @@ def lattice(n_atoms: int, seed: int):
     return pos, species
 
 
+def li2s_lattice(nx: int, ny: int, nz: int, a: float = 5.72, jitter: float = 0.05, seed: int = 2592):
+    """Anti-fluorite Li2S supercell (BASELINE config 1, examples/Li2S-crystal: 1728 Li + 864 S = 2592 atoms for
+    6x6x6 cells, N = 10368 orbitals with this 4-orbital model).  S on the fcc sites, Li on the eight (1/4,1/4,1/4)-type
+    sites of every conventional cell; small thermal jitter.  species: 0 = S-like, 1 = Li-like."""
+    fcc = np.array([[0, 0, 0], [0, .5, .5], [.5, 0, .5], [.5, .5, 0]])
+    tet = np.array([[x, y, z] for x in (.25, .75) for y in (.25, .75) for z in (.25, .75)])
+    cell = np.concatenate([fcc, tet]); sp = np.array([0] * 4 + [1] * 8)
+    shifts = np.array([[i, j, k] for i in range(nx) for j in range(ny) for k in range(nz)], dtype=np.float64)
+    pos = (shifts[:, None, :] + cell[None, :, :]).reshape(-1, 3) * a
+    species = np.tile(sp, shifts.shape[0])
+    rng = np.random.default_rng(seed)
+    return pos + rng.normal(0.0, jitter, size=pos.shape), species
+
+
 def orbital_params(species: np.ndarray):
     n_atoms = species.shape[0]
     IP = np.empty(4 * n_atoms)
@@ -189,14 +203,12 @@ def huckel_rows_torch(S_rows, r0: int, IPt, Kt, Vt):
     return h
 
 
-def make_S_h_torch(N: int, device, zeta: float = ZETA, row_block: int = 512):
-    """Same recipe on the GPU with torch (input generation is plumbing, not the product): returns (symmetric)
-    S and h as torch float64 tensors of shape (N,N), plus pos/species/IP arrays (numpy)."""
+def S_h_torch_from_positions(pos_np, species, device, zeta: float = ZETA, row_block: int = 512):
+    """S and h on the GPU for an arbitrary geometry (same recipe as overlap_numpy / x_matrix)."""
     import torch
-    pos_np, species = lattice(N // 4, 1234 + N)
     IP, k_WH, V_shift = orbital_params(species)
     pos = torch.tensor(pos_np, device=device, dtype=torch.float64)
-    n_atoms = pos.shape[0]
+    n_atoms = pos.shape[0]; N = 4 * n_atoms
     IPt = torch.tensor(IP, device=device); Kt = torch.tensor(k_WH, device=device); Vt = torch.tensor(V_shift, device=device)
     S = torch.empty((N, N), device=device, dtype=torch.float64)
     h = torch.empty_like(S)
@@ -209,6 +221,13 @@ def make_S_h_torch(N: int, device, zeta: float = ZETA, row_block: int = 512):
         a1 = min(n_atoms, a0 + row_block)
         h[4 * a0:4 * a1, :] = huckel_rows_torch(S[4 * a0:4 * a1, :], 4 * a0, IPt, Kt, Vt)
     return S, h, dict(pos=pos_np, species=species, IP=IP, k_WH=k_WH, V_shift=V_shift)
+
+
+def make_S_h_torch(N: int, device, zeta: float = ZETA, row_block: int = 512):
+    """The jittered-cubic-lattice workload of make_workload() built on the GPU with torch (input generation is
+    plumbing, not the product): (symmetric) S and h as torch float64 (N,N) tensors plus the numpy metadata."""
+    pos_np, species = lattice(N // 4, 1234 + N)
+    return S_h_torch_from_positions(pos_np, species, device, zeta, row_block)
 
 
 def make_h_shard_colmajor_torch(N: int, row0: int, n_rows: int, device, zeta: float = ZETA, row_block: int = 256,

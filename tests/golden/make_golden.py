@@ -130,6 +130,6 @@ if __name__ == "__main__":
     propagation_case("prop_N64_dt5e-6", 64, 5e-6)        # first-loop shrink + steady loop + last-substep shrink
     propagation_case("prop_N64_dt5e-4", 64, 5e-4)        # + the `rescaling tau` branch (Taylor.f:108-113)
     propagation_case("prop_N128_dt2e-5", 128, 2e-5)
-    trajectory_case("traj_N64_dt2e-6_20steps", 64, 2e-6, 20)
+    trajectory_case("traj_N64_dt2e-6_100steps", 64, 2e-6, 100)   # north_star: populations within 1e-9 over 100 nuclear steps
     chebyshev_case("cheb_N64_dt5e-4", 64, 5e-4)          # dt = 0.5 fs (BASELINE config), ~750 terms instead of ~18000
     chebyshev_case("cheb_N128_dt5e-5", 128, 5e-5)

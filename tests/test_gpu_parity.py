@@ -159,9 +159,9 @@ def test_legacy_propagationelhl_symbols(api, oracle_mod):
 
 
 def test_trajectory_populations_match_golden(api, golden_dir):
-    """20 nuclear steps with moving nuclei: S,h rebuilt on the host each step (reference path), everything
-    else through the library; per-fragment el/hole populations within 1e-9 of the oracle's."""
-    g = np.load(os.path.join(golden_dir, "traj_N64_dt2e-6_20steps.npz"))
+    """100 nuclear steps with moving nuclei (north_star: populations within 1e-9 over a 100-step trajectory): S,h
+    rebuilt on the host each step (reference path), everything else through the library."""
+    g = np.load(os.path.join(golden_dir, "traj_N64_dt2e-6_100steps.npz"))
     N, dt, n_steps = int(g["N"]), float(g["dt"]), int(g["n_steps"])
     pos, species = syn.lattice(N // 4, 1234 + N)
     S0, _ = syn.workload_at(pos, species)
@@ -284,4 +284,36 @@ def test_bad_arguments_are_reported(api):
     with pytest.raises(api.DynemolB200Error) as e:
         P.propagate(0.0, 1e-6, 1e-3, mode=api.MODE_CHEBYSHEV)   # no spectral bounds
     assert "spectral bounds" in str(e.value)
+    P.close()
+
+
+def test_li2s_crystal_size_step(api, oracle_mod):
+    """BASELINE config 1 (examples/Li2S-crystal: 1728 Li + 864 S, N = 10368 with the 4-orbital model): anti-fluorite
+    supercell geometry, S and h from the synthetic EHT recipe, H' formed on the device, one short Taylor step for
+    electron and hole against the CPU oracle at full size: identical decisions, 1e-10 wavepackets."""
+    import torch
+    pos, species = syn.li2s_lattice(6, 6, 6)
+    N = 4 * pos.shape[0]
+    assert N == 10368
+    S_t, h_t, meta = syn.S_h_torch_from_positions(pos, species, torch.device("cuda", 0), zeta=0.45)
+    P = api.Propagator(N)
+    P.form_hprime_device(S_t.data_ptr(), N, h_t.data_ptr(), N)
+    Hp = P.download_hprime()
+    S = S_t.cpu().numpy(); h = h_t.cpu().numpy()
+    del S_t, h_t
+    torch.cuda.empty_cache()
+    resid = np.abs(S @ Hp[:, :64] - h[:, :64]).max() / np.abs(h).max()      # S H' = h on a column block
+    assert resid < 1e-12
+    C, Psi_bra, Psi_ket = syn.packets(np.asfortranarray(S), N)
+    P.set_packets(Psi_bra, Psi_ket)
+    dt = 4e-7; tau0 = dt / H_BAR
+    save_tau, traces = P.propagate(0.0, dt, tau0)
+    gb, gk = P.get_packets()
+    e = P.quasiparticle_energies()
+    for p in range(2):
+        b, k, _, st, tr = oracle_mod.propagation(Hp, Psi_bra[:, p], Psi_ket[:, p], 0.0, dt, tau0)
+        assert events3(traces[p]) == events3(tr) and save_tau[p] == st
+        assert relerr(gb[:, p], b) < REL_TOL and relerr(gk[:, p], k) < REL_TOL
+        assert abs(abs(np.vdot(gb[:, p], gk[:, p])) - 1.0) < 1e-7
+        assert abs(e[p] - np.vdot(b, Hp @ k)) < 1e-8 * abs(e[p])
     P.close()

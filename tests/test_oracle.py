@@ -122,7 +122,7 @@ def test_elhl_step_matches_composition(oracle_mod):
 
 
 def test_golden_trajectory(oracle_mod, golden_dir):
-    g = np.load(os.path.join(golden_dir, "traj_N64_dt2e-6_20steps.npz"))
+    g = np.load(os.path.join(golden_dir, "traj_N64_dt2e-6_100steps.npz"))
     N, dt, n_steps = int(g["N"]), float(g["dt"]), 5        # first 5 of the 20 golden steps keep the CPU suite fast
     pos, species = syn.lattice(N // 4, 1234 + N)
     S0, _ = syn.workload_at(pos, species)
