@@ -87,48 +87,132 @@ __device__ __forceinline__ void apply_decision(Ctrl* c, const PassParams& pass, 
 }
 
 constexpr int EPI_THREADS = 256;
-constexpr int EPI_ROWS_PER_BLOCK = EPI_THREADS / 4;    // 4 threads per row: (particle, side)
+// threads per row = 4 (particle, side) x SL slab lanes; SL = 1 when few slabs contribute to a row (large N: ~20 segments
+// per panel), SL = 4 when many do (small N: every CTA of the grid is a segment of the same panel)
+constexpr int EPI_SL_WIDE = 4;
 
-// thread layout: idx = 4*i + 2*pp + side ; side 0 = ket, 1 = bra.  The two sides of one (row, particle) sit in
-// neighbouring lanes and exchange their new sums with one shuffle for the <bra|ket> product.
+// =================================================================================================
+// Row-sharded H', fused exchange + epilogue over NVLink peer memory (replaces ncclReduceScatter + epilogue +
+// ncclAllGather + decide):
+//   * bra:  y_bra[owned rows] = sum over ranks (fixed order) of the ranks' bra partial vectors, read straight from
+//           the peers' HBM (P2P loads)                                                  == reduce-scatter
+//   * ket:  the new ket slice is stored into EVERY rank's next ket vector (P2P stores)  == all-gather
+//   * the 8 per-rank scalars are stored into every rank's table; after a flag handshake the last block of every
+//           rank combines them in rank order and takes the (identical) decision.
+// Flags are monotonically increasing 64-bit epochs written with st.release.sys into the peers' memory.
+// =================================================================================================
+constexpr int MAX_PEERS = 8;
+
+struct PeerTable {
+    int world, rank;
+    const double* rs_send[MAX_PEERS];          // peers' bra partial vectors (this term's parity), full length
+    double*       ket_next[MAX_PEERS];         // peers' next ket vector (global index)
+    double*       scal_all[MAX_PEERS];         // peers' scalar tables (this term's parity): [world][8]
+    unsigned long long* ready[MAX_PEERS];      // peers' "bra partials of rank r are ready" flags: slot [my rank]
+    unsigned long long* done[MAX_PEERS];       // peers' "rank r finished its exchange" flags: slot [my rank]
+    const unsigned long long* my_ready;        // my own flag arrays [world], written by the peers
+    const unsigned long long* my_done;
+    unsigned long long epoch;
+};
+
+__global__ void signal_ready_kernel(const PeerTable T)
+{
+    // stream order guarantees the bra partial vector of this rank is complete; publish it to every peer
+    if (threadIdx.x < T.world) { __threadfence_system(); st_release_sys(T.ready[threadIdx.x], T.epoch); }
+}
+
+// strided slab sum: lane `sl` of SL adds slabs sl, sl+SL, ... (batches of 8 independent loads), fixed order
+template <int SL>
+__device__ __forceinline__ Cx slab_sum_strided(const double* __restrict__ base, size_t stride, int n, int sl) {
+    double re = 0.0, im = 0.0;
+    for (int s = sl; s < n; s += 8 * SL) {
+        double2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (s + SL * u < n) v[u] = __ldcg(reinterpret_cast<const double2*>(base + (size_t)(s + SL * u) * stride));
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (s + SL * u < n) { re += v[u].x; im += v[u].y; }
+    }
+    return {re, im};
+}
+
+// One kernel, two flavours.  P2P = false: single GPU, or the NCCL path of the row-sharded mode (bra partials arrive
+// reduce-scattered in a one-slab buffer).  P2P = true: the exchange itself happens here (see the banner above).
+// Thread layout: idx = ((row*2 + particle)*2 + side)*SL + slab-lane; side 0 = ket, 1 = bra.  The SL slab lanes split
+// the slab (or peer) sum and merge it with shuffles; the two sides of a (row, particle) meet with one more shuffle
+// for the <bra|ket> product.
+template <bool P2P, int SL>
 __global__ void __launch_bounds__(EPI_THREADS)
-epilogue_kernel(const EpiParams E)
+epilogue_kernel_t(const EpiParams E, const PeerTable T)
 {
     __shared__ double wpart[EPI_THREADS / 32][8];
     __shared__ int    is_last;
 
-    pdl_launch_dependents();        // the next dual product may start its H' prefetch while we run
-    pdl_wait();                     // slabs of the dual product that precedes us are complete and visible
+    if constexpr (P2P) {
+        if (threadIdx.x < T.world) wait_flag_ge(T.my_ready + threadIdx.x, T.epoch);     // all ranks' bra partials are visible
+        __syncthreads();
+    } else {
+        pdl_launch_dependents();        // the next dual product may start its H' prefetch while we run
+        pdl_wait();                     // slabs of the dual product that precedes us are complete and visible
+    }
 
     const int idx = blockIdx.x * EPI_THREADS + threadIdx.x;
-    const int i = idx >> 2, pp = (idx >> 1) & 1, side = idx & 1;
+    constexpr int LSL = (SL == 4) ? 2 : 0;
+    static_assert(SL == 1 || SL == 4, "SL");
+    const int i = idx >> (LSL + 2), pp = (idx >> (LSL + 1)) & 1, side = (idx >> LSL) & 1, sl = idx & (SL - 1);
     const PartPass pa = E.pass.part[pp];
     const bool live = (i < E.M) && pa.active && !E.ctrl->part[pp].latched;
 
+    // ---- H' x (ket: this rank's segments; bra: panels / peers), split over the four slab lanes
+    Cx hx = {0.0, 0.0};
+    const size_t ob = (size_t)i * NQ + 2 * pp;                           // owned-row slot (bra vectors, both sums)
+    const size_t og = ((size_t)E.row0 + i) * NQ + 2 * pp;                // global-index slot (ket vectors, peers' partials)
+    if (live) {
+        if (side == 0) {
+            const int panel = i / PANEL_ROWS, il = i % PANEL_ROWS;
+            const int s0 = E.pseg_start[panel], s1 = E.pseg_start[panel + 1];
+            hx = slab_sum_strided<SL>(E.ket_slab + (((size_t)s0 * PANEL_ROWS + il) * NQ + 2 * pp), (size_t)PANEL_ROWS * NQ, s1 - s0, sl);
+        } else if constexpr (P2P) {                                      // reduce-scatter by peer loads
+            double2 v[MAX_PEERS];
+#pragma unroll
+            for (int r = 0; r < MAX_PEERS; ++r) if (r * SL + sl < T.world && r < MAX_PEERS / SL) v[r] = __ldcg(reinterpret_cast<const double2*>(T.rs_send[r * SL + sl] + og));
+#pragma unroll
+            for (int r = 0; r < MAX_PEERS; ++r) if (r * SL + sl < T.world && r < MAX_PEERS / SL) { hx.re += v[r].x; hx.im += v[r].y; }
+        } else {
+            hx = slab_sum_strided<SL>(E.bra_slab + (((size_t)E.bra_col0 + i) * NQ + 2 * pp), (size_t)E.Ncpad * NQ, E.n_bra_slabs, sl);
+        }
+    }
+#pragma unroll
+    for (int off = 1; off < SL; off <<= 1) {
+        hx.re += __shfl_xor_sync(0xffffffffu, hx.re, off); hx.im += __shfl_xor_sync(0xffffffffu, hx.im, off);
+    }
+
+    // ---- recurrence, accumulation, term size: slab lane 0 of every (row, particle, side)
     double mx = 0.0;            // |new - old| of this thread's side
     Cx nw = {0.0, 0.0};         // new running sum of this thread's side
-    if (live) {
-        const Cx hx = side ? reduce_bra(E, i, pp) : reduce_ket(E, i, pp);
-        const Cx alpha = {pa.alpha_re, pa.alpha_im};
-        Cx y = cmul(alpha, hx);
-        const size_t ob = (size_t)i * NQ + 2 * pp;                       // owned-row slot (bra vectors, both sums)
-        const size_t og = ((size_t)E.row0 + i) * NQ + 2 * pp;            // global-column slot (ket vectors)
+    if (live && sl == 0) {
+        Cx y = cmul({pa.alpha_re, pa.alpha_im}, hx);
         const size_t ov = side ? ob : og;
         const double* cur = side ? E.cur_b : E.cur_k;
         const double* prv = side ? E.prv_b : E.prv_k;
-        double* nxt = side ? E.nxt_b : E.nxt_k;
         double* sum = side ? E.sum_b : E.sum_k;
         if (pa.three_term) {
-            const Cx beta = {pa.beta_re, pa.beta_im};
             const double2 c = *reinterpret_cast<const double2*>(cur + ov);
-            const Cx bc = cmul(beta, {c.x, c.y});
+            const Cx bc = cmul({pa.beta_re, pa.beta_im}, {c.x, c.y});
             y.re += bc.re; y.im += bc.im;
             if (pa.gamma != 0.0) {                     // first Chebyshev term has no x_prev (buffer may hold anything)
                 const double2 pv = *reinterpret_cast<const double2*>(prv + ov);
                 y.re += pa.gamma * pv.x; y.im += pa.gamma * pv.y;
             }
         }
-        *reinterpret_cast<double2*>(nxt + ov) = make_double2(y.re, y.im);
+        if (side) {
+            *reinterpret_cast<double2*>(E.nxt_b + ob) = make_double2(y.re, y.im);
+        } else if constexpr (P2P) {                                      // all-gather by peer stores
+#pragma unroll
+            for (int r = 0; r < MAX_PEERS; ++r)
+                if (r < T.world) *reinterpret_cast<double2*>(T.ket_next[r] + og) = make_double2(y.re, y.im);
+        } else {
+            *reinterpret_cast<double2*>(E.nxt_k + og) = make_double2(y.re, y.im);
+        }
         Cx t = y;
         if (pa.scale_term) t = cmul({pa.c_re, pa.c_im}, y);
         const double2 so = *reinterpret_cast<const double2*>(sum + ob);
@@ -136,26 +220,24 @@ epilogue_kernel(const EpiParams E)
         *reinterpret_cast<double2*>(sum + ob) = make_double2(nw.re, nw.im);
         mx = hypot(nw.re - so.x, nw.im - so.y);                          // abs(new - old)      (Taylor.f:300)
     }
-    // partner lane (other side of the same row/particle); idle threads carry zeros
-    const double ore = __shfl_xor_sync(0xffffffffu, nw.re, 1), oim = __shfl_xor_sync(0xffffffffu, nw.im, 1);
-    const double omx = __shfl_xor_sync(0xffffffffu, mx, 1);
+    // partner lane = other side of the same (row, particle); idle lanes carry zeros
+    const double ore = __shfl_xor_sync(0xffffffffu, nw.re, SL), oim = __shfl_xor_sync(0xffffffffu, nw.im, SL);
+    const double omx = __shfl_xor_sync(0xffffffffu, mx, SL);
     double mb = 0.0, mk = 0.0, dr = 0.0, di = 0.0;
-    if (side == 0) {                                                     // ket lane owns the pair's contribution
+    if (side == 0 && sl == 0) {                                          // the ket lane owns the pair's contribution
         mk = mx; mb = omx;
         dr = ore * nw.re + oim * nw.im;                                  // conj(bra)*ket, dotc (Taylor.f:62,103,197)
         di = ore * nw.im - oim * nw.re;
     }
-    // reduce over lanes of equal particle (lane bit 1), sides already merged (lane bit 0)
+    // the rows of the warp (lane bits above the particle bit); particles (lane bit 2*SL) stay separate
 #pragma unroll
-    for (int off = 4; off < 32; off <<= 1) {
-        mb = fmax(mb, __shfl_xor_sync(0xffffffffu, mb, off));
-        mk = fmax(mk, __shfl_xor_sync(0xffffffffu, mk, off));
-        dr += __shfl_xor_sync(0xffffffffu, dr, off);
-        di += __shfl_xor_sync(0xffffffffu, di, off);
+    for (int off = 4 * SL; off < 32; off <<= 1) {
+        mb = fmax(mb, __shfl_xor_sync(0xffffffffu, mb, off)); mk = fmax(mk, __shfl_xor_sync(0xffffffffu, mk, off));
+        dr += __shfl_xor_sync(0xffffffffu, dr, off);          di += __shfl_xor_sync(0xffffffffu, di, off);
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0 || lane == 2) {
-        const int p = lane >> 1;
+    if (lane == 0 || lane == 2 * SL) {
+        const int p = lane / (2 * SL);
         wpart[warp][p * 4 + 0] = mb; wpart[warp][p * 4 + 1] = mk; wpart[warp][p * 4 + 2] = dr; wpart[warp][p * 4 + 3] = di;
     }
     __syncthreads();
@@ -165,7 +247,8 @@ epilogue_kernel(const EpiParams E)
         for (int w2 = 1; w2 < EPI_THREADS / 32; ++w2) v = ((t & 3) < 2) ? fmax(v, wpart[w2][t]) : v + wpart[w2][t];
         E.blockpart[(size_t)blockIdx.x * 8 + t] = v;
     }
-    __threadfence();
+    if constexpr (P2P) __threadfence_system();   // this block's peer stores (ket slices) are performed system-wide
+    else __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned ticket = atomicAdd(&E.ctrl->block_counter, 1u);
@@ -174,11 +257,11 @@ epilogue_kernel(const EpiParams E)
     __syncthreads();
     if (!is_last) return;
 
-    // ---- last block: final scalars (fixed strided order + fixed tree => deterministic), then the decision
-    //      the host used to take per term
+    // ---- last block: final scalars (fixed strided order + fixed tree => deterministic), then the decision the
+    //      host used to take per term
     __threadfence();
+    __shared__ double fin[EPI_THREADS][8];
     {
-        __shared__ double fin[EPI_THREADS][8];
         double v[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         for (unsigned bb = threadIdx.x; bb < gridDim.x; bb += EPI_THREADS) {
             const double2* bp = reinterpret_cast<const double2*>(E.blockpart + (size_t)bb * 8);
@@ -199,17 +282,38 @@ epilogue_kernel(const EpiParams E)
             }
             __syncthreads();
         }
-        if (threadIdx.x < 8) wpart[0][threadIdx.x] = fin[0][threadIdx.x];
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (E.defer_decision) {
+    if constexpr (P2P) {
+        // my 8 scalars into slot [rank] of every peer's table, handshake, rank-ordered combination
+        if (threadIdx.x < 8 * T.world) {
+            const int r = threadIdx.x >> 3, t = threadIdx.x & 7;
+            T.scal_all[r][(size_t)T.rank * 8 + t] = fin[0][t];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < T.world) {
+            st_release_sys(T.done[threadIdx.x], T.epoch);                // "rank `rank` is done" on every peer
+            wait_flag_ge(T.my_done + threadIdx.x, T.epoch);              // and wait until every peer is done
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double v[8];
+            const double* tab = T.scal_all[T.rank];
+            for (int t = 0; t < 8; ++t) {
+                double a = __ldcg(tab + t);
+                for (int r = 1; r < T.world; ++r) { const double b = __ldcg(tab + (size_t)r * 8 + t); a = ((t & 3) < 2) ? fmax(a, b) : a + b; }
+                v[t] = a;
+            }
+            apply_decision(E.ctrl, E.pass, v);
+        }
+    } else if (threadIdx.x == 0) {
+        if (E.defer_decision) {                  // NCCL path of the row-sharded mode: decide after the all-gather
 #pragma unroll
-            for (int t = 0; t < 8; ++t) E.scal_out[t] = wpart[0][t];
+            for (int t = 0; t < 8; ++t) E.scal_out[t] = fin[0][t];
             E.ctrl->block_counter = 0u;
             __threadfence();
         } else {
-            apply_decision(E.ctrl, E.pass, wpart[0]);
+            apply_decision(E.ctrl, E.pass, fin[0]);
         }
     }
 }
@@ -282,176 +386,6 @@ __global__ void decide_kernel(int world, const double* __restrict__ scal_all, Ct
         v[t] = a;
     }
     apply_decision(ctrl, pass, v);
-}
-
-// =================================================================================================
-// Row-sharded H', fused exchange + epilogue over NVLink peer memory (replaces ncclReduceScatter + epilogue +
-// ncclAllGather + decide):
-//   * bra:  y_bra[owned rows] = sum over ranks (fixed order) of the ranks' bra partial vectors, read straight from
-//           the peers' HBM (P2P loads)                                                  == reduce-scatter
-//   * ket:  the new ket slice is stored into EVERY rank's next ket vector (P2P stores)  == all-gather
-//   * the 8 per-rank scalars are stored into every rank's table; after a flag handshake the last block of every
-//           rank combines them in rank order and takes the (identical) decision.
-// Flags are monotonically increasing 64-bit epochs written with st.release.sys into the peers' memory.
-// =================================================================================================
-constexpr int MAX_PEERS = 8;
-
-struct PeerTable {
-    int world, rank;
-    const double* rs_send[MAX_PEERS];          // peers' bra partial vectors (this term's parity), full length
-    double*       ket_next[MAX_PEERS];         // peers' next ket vector (global index)
-    double*       scal_all[MAX_PEERS];         // peers' scalar tables (this term's parity): [world][8]
-    unsigned long long* ready[MAX_PEERS];      // peers' "bra partials of rank r are ready" flags: slot [my rank]
-    unsigned long long* done[MAX_PEERS];       // peers' "rank r finished its exchange" flags: slot [my rank]
-    const unsigned long long* my_ready;        // my own flag arrays [world], written by the peers
-    const unsigned long long* my_done;
-    unsigned long long epoch;
-};
-
-__global__ void signal_ready_kernel(const PeerTable T)
-{
-    // stream order guarantees the bra partial vector of this rank is complete; publish it to every peer
-    if (threadIdx.x < T.world) { __threadfence_system(); st_release_sys(T.ready[threadIdx.x], T.epoch); }
-}
-
-__global__ void __launch_bounds__(EPI_THREADS)
-epilogue_p2p_kernel(const EpiParams E, const PeerTable T)
-{
-    __shared__ double wpart[EPI_THREADS / 32][8];
-    __shared__ int    is_last;
-
-    if (threadIdx.x < T.world) wait_flag_ge(T.my_ready + threadIdx.x, T.epoch);     // all ranks' bra partials are visible
-    __syncthreads();
-
-    const int idx = blockIdx.x * EPI_THREADS + threadIdx.x;
-    const int i = idx >> 2, pp = (idx >> 1) & 1, side = idx & 1;
-    const PartPass pa = E.pass.part[pp];
-    const bool live = (i < E.M) && pa.active && !E.ctrl->part[pp].latched;
-
-    double mx = 0.0;
-    Cx nw = {0.0, 0.0};
-    if (live) {
-        const size_t ob = (size_t)i * NQ + 2 * pp;
-        const size_t og = ((size_t)E.row0 + i) * NQ + 2 * pp;
-        Cx hx;
-        if (side) {                                                      // reduce-scatter by peer loads, rank order
-            double re = 0.0, im = 0.0;
-            double2 v[MAX_PEERS];
-#pragma unroll
-            for (int r = 0; r < MAX_PEERS; ++r) if (r < T.world) v[r] = __ldcg(reinterpret_cast<const double2*>(T.rs_send[r] + og));
-#pragma unroll
-            for (int r = 0; r < MAX_PEERS; ++r) if (r < T.world) { re += v[r].x; im += v[r].y; }
-            hx = {re, im};
-        } else {
-            hx = reduce_ket(E, i, pp);
-        }
-        Cx y = cmul({pa.alpha_re, pa.alpha_im}, hx);
-        const size_t ov = side ? ob : og;
-        const double* cur = side ? E.cur_b : E.cur_k;
-        const double* prv = side ? E.prv_b : E.prv_k;
-        double* sum = side ? E.sum_b : E.sum_k;
-        if (pa.three_term) {
-            const double2 c = *reinterpret_cast<const double2*>(cur + ov);
-            const Cx bc = cmul({pa.beta_re, pa.beta_im}, {c.x, c.y});
-            y.re += bc.re; y.im += bc.im;
-            if (pa.gamma != 0.0) {
-                const double2 pv = *reinterpret_cast<const double2*>(prv + ov);
-                y.re += pa.gamma * pv.x; y.im += pa.gamma * pv.y;
-            }
-        }
-        if (side) {
-            *reinterpret_cast<double2*>(E.nxt_b + ob) = make_double2(y.re, y.im);
-        } else {                                                         // all-gather by peer stores
-#pragma unroll
-            for (int r = 0; r < MAX_PEERS; ++r)
-                if (r < T.world) *reinterpret_cast<double2*>(T.ket_next[r] + og) = make_double2(y.re, y.im);
-        }
-        Cx t = y;
-        if (pa.scale_term) t = cmul({pa.c_re, pa.c_im}, y);
-        const double2 so = *reinterpret_cast<const double2*>(sum + ob);
-        nw = {so.x + t.re, so.y + t.im};
-        *reinterpret_cast<double2*>(sum + ob) = make_double2(nw.re, nw.im);
-        mx = hypot(nw.re - so.x, nw.im - so.y);
-    }
-    const double ore = __shfl_xor_sync(0xffffffffu, nw.re, 1), oim = __shfl_xor_sync(0xffffffffu, nw.im, 1);
-    const double omx = __shfl_xor_sync(0xffffffffu, mx, 1);
-    double mb = 0.0, mk = 0.0, dr = 0.0, di = 0.0;
-    if (side == 0) { mk = mx; mb = omx; dr = ore * nw.re + oim * nw.im; di = ore * nw.im - oim * nw.re; }
-#pragma unroll
-    for (int off = 4; off < 32; off <<= 1) {
-        mb = fmax(mb, __shfl_xor_sync(0xffffffffu, mb, off));
-        mk = fmax(mk, __shfl_xor_sync(0xffffffffu, mk, off));
-        dr += __shfl_xor_sync(0xffffffffu, dr, off);
-        di += __shfl_xor_sync(0xffffffffu, di, off);
-    }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0 || lane == 2) {
-        const int p = lane >> 1;
-        wpart[warp][p * 4 + 0] = mb; wpart[warp][p * 4 + 1] = mk; wpart[warp][p * 4 + 2] = dr; wpart[warp][p * 4 + 3] = di;
-    }
-    __syncthreads();
-    if (threadIdx.x < 8) {
-        const int t = threadIdx.x;
-        double v = wpart[0][t];
-        for (int w2 = 1; w2 < EPI_THREADS / 32; ++w2) v = ((t & 3) < 2) ? fmax(v, wpart[w2][t]) : v + wpart[w2][t];
-        E.blockpart[(size_t)blockIdx.x * 8 + t] = v;
-    }
-    __threadfence_system();                      // this block's peer stores (ket slices) are performed system-wide
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned ticket = atomicAdd(&E.ctrl->block_counter, 1u);
-        is_last = (ticket == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return;
-
-    // ---- last block of this rank: local scalars -> every peer's table, handshake, rank-ordered decision
-    __threadfence();
-    {
-        __shared__ double fin[EPI_THREADS][8];
-        double v[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        for (unsigned bb = threadIdx.x; bb < gridDim.x; bb += EPI_THREADS) {
-            const double2* bp = reinterpret_cast<const double2*>(E.blockpart + (size_t)bb * 8);
-            const double2 a0 = __ldcg(bp), a1 = __ldcg(bp + 1), a2 = __ldcg(bp + 2), a3 = __ldcg(bp + 3);
-            v[0] = fmax(v[0], a0.x); v[1] = fmax(v[1], a0.y); v[2] += a1.x; v[3] += a1.y;
-            v[4] = fmax(v[4], a2.x); v[5] = fmax(v[5], a2.y); v[6] += a3.x; v[7] += a3.y;
-        }
-#pragma unroll
-        for (int t = 0; t < 8; ++t) fin[threadIdx.x][t] = v[t];
-        __syncthreads();
-        for (int st = EPI_THREADS / 2; st > 0; st >>= 1) {
-            if (threadIdx.x < st) {
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    const double a = fin[threadIdx.x][t], b = fin[threadIdx.x + st][t];
-                    fin[threadIdx.x][t] = ((t & 3) < 2) ? fmax(a, b) : a + b;
-                }
-            }
-            __syncthreads();
-        }
-        // my 8 scalars into slot [rank] of every peer's table
-        if (threadIdx.x < 8 * T.world) {
-            const int r = threadIdx.x >> 3, t = threadIdx.x & 7;
-            T.scal_all[r][(size_t)T.rank * 8 + t] = fin[0][t];
-        }
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < T.world) {
-        st_release_sys(T.done[threadIdx.x], T.epoch);                    // "rank `rank` is done" on every peer
-        wait_flag_ge(T.my_done + threadIdx.x, T.epoch);                  // and wait until every peer is done
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double v[8];
-        const double* tab = T.scal_all[T.rank];
-        for (int t = 0; t < 8; ++t) {
-            double a = __ldcg(tab + t);
-            for (int r = 1; r < T.world; ++r) { const double b = __ldcg(tab + (size_t)r * 8 + t); a = ((t & 3) < 2) ? fmax(a, b) : a + b; }
-            v[t] = a;
-        }
-        apply_decision(E.ctrl, E.pass, v);
-    }
 }
 
 // ---- plain slab reduction into quad vectors (kernel-level parity entry dyb_dual_matvec)

@@ -238,12 +238,17 @@ static EpiParams epi_params(dyb_ctx* c, int cur, int prv, int nxt) {
     memset(&E.pass, 0, sizeof E.pass);
     return E;
 }
-static int epi_grid(const dyb_ctx* c) { return (4 * c->M + EPI_THREADS - 1) / EPI_THREADS; }
+// slab lanes of the epilogue: wide (4) when many segments contribute to every row (small N), else 1
+static int epi_sl(const dyb_ctx* c) { return (c->n_seg > 32 * c->NP) ? EPI_SL_WIDE : 1; }
+static int epi_grid(const dyb_ctx* c) { return (4 * epi_sl(c) * c->M + EPI_THREADS - 1) / EPI_THREADS; }
 
 static int launch_epilogue(dyb_ctx* c, const EpiParams& E) {
     cudaLaunchAttribute attr;
     cudaLaunchConfig_t cfg = pdl_config(c, epi_grid(c), EPI_THREADS, 0, &attr);
-    CK(cudaLaunchKernelEx(&cfg, epilogue_kernel, E));
+    PeerTable none;
+    memset(&none, 0, sizeof none);
+    if (epi_sl(c) == 1) CK(cudaLaunchKernelEx(&cfg, epilogue_kernel_t<false, 1>, E, none));
+    else CK(cudaLaunchKernelEx(&cfg, epilogue_kernel_t<false, EPI_SL_WIDE>, E, none));
     c->launches++;
     return DYB_OK;
 }
@@ -283,7 +288,8 @@ static int run_term(dyb_ctx* c, const EpiParams& E, int cur, int nxt, bool use_c
         CK(cudaGetLastError());
         EpiParams E2 = E;
         E2.defer_decision = 0;
-        epilogue_p2p_kernel<<<epi_grid(c), EPI_THREADS, 0, c->stream>>>(E2, T);
+        if (epi_sl(c) == 1) epilogue_kernel_t<true, 1><<<epi_grid(c), EPI_THREADS, 0, c->stream>>>(E2, T);
+        else epilogue_kernel_t<true, EPI_SL_WIDE><<<epi_grid(c), EPI_THREADS, 0, c->stream>>>(E2, T);
         c->launches++;
         CK(cudaGetLastError());
         return DYB_OK;
