@@ -257,7 +257,7 @@ def run_e2e(args, P, N, Psi_bra, Psi_ket):
     """The reference-facing call sequence with HOST buffers (propagation_gpucaller_ semantics, Taylor_gpu.cpp:295-330):
     H' and the packets start in pinned host memory; H2D, a full propagation of one nuclear step and D2H are inside the
     timed region.  Default: Chebyshev mode, dt = 0.5 fs (BASELINE config 3), tau carried over from the previous step
-    like ElHl_Chebyshev.f:182-184; the spectral interval is re-estimated (40 Lanczos passes) inside every call."""
+    like ElHl_Chebyshev.f:182-184; the spectral interval is re-estimated (24 Lanczos passes) inside every call."""
     import torch
     from dynemol_b200 import api
     Hp_host = torch.empty((N, N), dtype=torch.float64, pin_memory=True)
@@ -272,7 +272,7 @@ def run_e2e(args, P, N, Psi_bra, Psi_ket):
         P.upload_hprime(Hp_np)                                      # 8 N^2 bytes H2D
         P.set_packets(Psi_bra, Psi_ket)
         if cheb:
-            P.estimate_spectral_bounds(40, 0.05)
+            P.estimate_spectral_bounds(24, 0.05)
         save_tau, _ = P.propagate(0.0, dt_e2e, tau, mode=mode)
         P.get_packets()
         return save_tau, P.info()["passes_last"]
@@ -288,9 +288,9 @@ def run_e2e(args, P, N, Psi_bra, Psi_ket):
     return {"value": round(passes / t_e2e, 2), "unit": UNIT,
             "h2d_bytes_per_step": int(8 * N * N + 2 * 2 * 16 * N), "d2h_bytes_per_step": int(2 * 2 * 16 * N),
             "call": "upload_hprime(host)+set_packets(host)+%spropagate(%s, dt=%g ps)+get_packets(host)"
-                    % ("estimate_spectral_bounds(40)+" if cheb else "", "Chebyshev" if cheb else "Taylor", dt_e2e),
+                    % ("estimate_spectral_bounds(24)+" if cheb else "", "Chebyshev" if cheb else "Taylor", dt_e2e),
             "terms_per_call": passes // e2e_steps, "s_per_call": round(t_e2e / e2e_steps, 4),
-            "note": "series terms only; the 40 Lanczos passes per call are timed but not counted" if cheb else ""}
+            "note": "series terms only; the 24 Lanczos passes per call are timed but not counted" if cheb else ""}
 
 
 def cpu_baseline(Hp_np, Psi_bra, Psi_ket, tau, budget_s=15.0):

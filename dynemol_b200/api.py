@@ -75,7 +75,7 @@ lib = _load()
 DECLARED_SYMBOLS = [
     "propagationelhl_gpucaller_", "propagationelhl2_gpucaller_", "propagation_gpucaller_", "nakedbessel_", "ehrenfestkernel_gpu_",
     "gpu_init_", "gpu_finalize_", "gpu_pin_", "gpu_unpin_",
-    "dyb_last_error", "dyb_version", "dyb_device_count", "dyb_create", "dyb_destroy", "dyb_set_kernel",
+    "dyb_last_error", "dyb_version", "dyb_device_count", "dyb_plan", "dyb_create", "dyb_destroy", "dyb_set_kernel",
     "dyb_get_info", "dyb_upload_hprime", "dyb_upload_hprime_device", "dyb_upload_hprime_rows_device", "dyb_hprime_device", "dyb_form_hprime", "dyb_form_hprime_device", "dyb_form_hprime_from_overlap",
     "dyb_download_hprime", "dyb_set_packets", "dyb_get_packets", "dyb_propagate", "dyb_ao_bra",
     "dyb_populations", "dyb_run_terms", "dyb_dual_matvec", "dyb_sync", "dyb_launch_count",
@@ -105,6 +105,18 @@ def comm_unique_id() -> bytes:
     buf = C.create_string_buffer(128)
     _check(lib.dyb_comm_unique_id(buf))
     return buf.raw
+
+
+def plan(N: int, n_rows: int | None = None, sm_count: int = 148) -> dict:
+    """Launch plan of the dual product (host arithmetic only, works without a GPU)."""
+    n_rows = N if n_rows is None else n_rows
+    out = (C.c_int64 * 8)()
+    _check(lib.dyb_plan(C.c_int(N), C.c_int(n_rows), C.c_int(sm_count), out, None, None))
+    d = dict(zip(["panels", "tiles_per_panel", "tiles", "grid", "segments", "tile_cols", "panel_rows", "padded_cols"], [int(v) for v in out]))
+    seg_base = (C.c_int32 * d["grid"])(); pseg = (C.c_int32 * (d["panels"] + 1))()
+    _check(lib.dyb_plan(C.c_int(N), C.c_int(n_rows), C.c_int(sm_count), out, seg_base, pseg))
+    d["seg_base"] = list(seg_base); d["pseg_start"] = list(pseg)
+    return d
 
 
 def device_count() -> int:

@@ -55,7 +55,7 @@ void elhl(int n_part, const int* N, const double* h_S, const double* h_h, double
     LCK(dyb_set_packets(c, n_part, h_PSI_bra, h_PSI_ket), "dyb_set_packets");  // :681-683
     const int mode = mode_from_env();
     if (mode == DYB_MODE_CHEBYSHEV)            // the operator changes every nuclear step: re-estimate its spectral interval
-        LCK(dyb_estimate_spectral_bounds(c, 40, 0.05, nullptr, nullptr), "dyb_estimate_spectral_bounds");
+        LCK(dyb_estimate_spectral_bounds(c, 24, 0.05, nullptr, nullptr), "dyb_estimate_spectral_bounds");
     LCK(dyb_propagate(c, mode, *t_init, *t_max, tau, save_tau, nullptr), "dyb_propagate");  // :707
     LCK(dyb_get_packets(c, n_part, h_PSI_bra, h_PSI_ket), "dyb_get_packets");  // :711-712
     LCK(dyb_ao_bra(c, n_part, h_AO_bra), "dyb_ao_bra");                        // :718-721
@@ -89,7 +89,7 @@ void propagation_gpucaller_(const int* n, double* tau, double* save_tau, const d
     LCK(dyb_set_packets(c, 1, h_PSI_bra, h_PSI_ket), "dyb_set_packets");
     const int mode = mode_from_env();
     if (mode == DYB_MODE_CHEBYSHEV)
-        LCK(dyb_estimate_spectral_bounds(c, 40, 0.05, nullptr, nullptr), "dyb_estimate_spectral_bounds");
+        LCK(dyb_estimate_spectral_bounds(c, 24, 0.05, nullptr, nullptr), "dyb_estimate_spectral_bounds");
     LCK(dyb_propagate(c, mode, *t_init, *t_max, tau, save_tau, nullptr), "dyb_propagate");
     LCK(dyb_get_packets(c, 1, h_PSI_bra, h_PSI_ket), "dyb_get_packets");
 }

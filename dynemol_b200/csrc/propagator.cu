@@ -158,28 +158,43 @@ static int build_tensor_map(dyb_ctx* c) {
     return DYB_OK;
 }
 
-static int build_plan(dyb_ctx* c) {
-    c->NP    = (c->M + PANEL_ROWS - 1) / PANEL_ROWS;
-    c->TPP   = (c->N + TILE_COLS - 1) / TILE_COLS;
-    c->Ncpad = c->TPP * TILE_COLS;
-    c->T     = c->NP * c->TPP;
-    c->grid  = std::min(c->sm_count, c->T);
-    std::vector<int> seg_base(c->grid, 0), pcount(c->NP, 0);
+// Launch plan of the dual product (pure host arithmetic, also exported as dyb_plan for the CPU test-suite):
+// tiles are dealt to CTAs as contiguous ranges of the panel-major tile list; a CTA range may straddle panel
+// boundaries, each (CTA, panel) piece is a "segment" with its own ket slab; segments are globally ordered by panel.
+struct Plan {
+    int NP = 0, TPP = 0, Ncpad = 0, T = 0, grid = 0, n_seg = 0;
+    std::vector<int> seg_base, pseg_start;
+};
+static Plan make_plan(int N, int M, int sm_count) {
+    Plan p;
+    p.NP    = (M + PANEL_ROWS - 1) / PANEL_ROWS;
+    p.TPP   = (N + TILE_COLS - 1) / TILE_COLS;
+    p.Ncpad = p.TPP * TILE_COLS;
+    p.T     = p.NP * p.TPP;
+    p.grid  = std::min(sm_count, p.T);
+    p.seg_base.assign(p.grid, 0);
+    std::vector<int> pcount(p.NP, 0);
     int seg = 0;
-    for (int b = 0; b < c->grid; ++b) {
-        const long long t0 = ((long long)c->T * b) / c->grid, t1 = ((long long)c->T * (b + 1)) / c->grid;
-        seg_base[b] = seg;
+    for (int b = 0; b < p.grid; ++b) {
+        const long long t0 = ((long long)p.T * b) / p.grid, t1 = ((long long)p.T * (b + 1)) / p.grid;
+        p.seg_base[b] = seg;
         if (t1 <= t0) continue;
-        const int p0 = (int)(t0 / c->TPP), p1 = (int)((t1 - 1) / c->TPP);
-        for (int p = p0; p <= p1; ++p) { pcount[p]++; seg++; }
+        const int p0 = (int)(t0 / p.TPP), p1 = (int)((t1 - 1) / p.TPP);
+        for (int q = p0; q <= p1; ++q) { pcount[q]++; seg++; }
     }
-    c->n_seg = seg;
-    std::vector<int> pstart(c->NP + 1, 0);
-    for (int p = 0; p < c->NP; ++p) pstart[p + 1] = pstart[p] + pcount[p];
+    p.n_seg = seg;
+    p.pseg_start.assign(p.NP + 1, 0);
+    for (int q = 0; q < p.NP; ++q) p.pseg_start[q + 1] = p.pseg_start[q] + pcount[q];
+    return p;
+}
+
+static int build_plan(dyb_ctx* c) {
+    const Plan p = make_plan(c->N, c->M, c->sm_count);
+    c->NP = p.NP; c->TPP = p.TPP; c->Ncpad = p.Ncpad; c->T = p.T; c->grid = p.grid; c->n_seg = p.n_seg;
     CK(cudaMalloc(&c->seg_base, sizeof(int) * c->grid));
     CK(cudaMalloc(&c->pseg_start, sizeof(int) * (c->NP + 1)));
-    CK(cudaMemcpy(c->seg_base, seg_base.data(), sizeof(int) * c->grid, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(c->pseg_start, pstart.data(), sizeof(int) * (c->NP + 1), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->seg_base, p.seg_base.data(), sizeof(int) * c->grid, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->pseg_start, p.pseg_start.data(), sizeof(int) * (c->NP + 1), cudaMemcpyHostToDevice));
     return DYB_OK;
 }
 
@@ -548,6 +563,18 @@ extern "C" {
 
 const char* dyb_last_error(void) { return g_err.c_str(); }
 const char* dyb_version(void) { return "dynemol_b200 0.1 (sm_100a)"; }
+
+// Host-only: the launch plan for an N-column, n_rows-row operator on a GPU with sm_count SMs (no device needed).
+// out8 = {panels, tiles_per_panel, tiles, grid, segments, tile_cols, panel_rows, Ncpad}; seg_base[grid] and
+// pseg_start[panels+1] are filled when non-NULL (sized by the caller from a first call).
+int dyb_plan(int N, int n_rows, int sm_count, int64_t* out8, int32_t* seg_base, int32_t* pseg_start) {
+    if (N <= 0 || n_rows <= 0 || sm_count <= 0 || !out8) return fail(DYB_EINVAL, "bad argument");
+    const Plan p = make_plan(N, n_rows, sm_count);
+    out8[0] = p.NP; out8[1] = p.TPP; out8[2] = p.T; out8[3] = p.grid; out8[4] = p.n_seg; out8[5] = TILE_COLS; out8[6] = PANEL_ROWS; out8[7] = p.Ncpad;
+    if (seg_base) for (int b = 0; b < p.grid; ++b) seg_base[b] = p.seg_base[b];
+    if (pseg_start) for (int q = 0; q <= p.NP; ++q) pseg_start[q] = p.pseg_start[q];
+    return DYB_OK;
+}
 
 int dyb_device_count(void) {
     int n = 0;

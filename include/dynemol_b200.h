@@ -123,6 +123,9 @@ typedef struct dyb_ctx dyb_ctx;
 const char* dyb_last_error(void);
 const char* dyb_version(void);
 int  dyb_device_count(void);
+/* Host-only (no device needed): the launch plan of the dual product.  out8 = {panels, tiles_per_panel, tiles, grid,
+ * segments, tile_cols, panel_rows, padded_cols}; seg_base[grid] / pseg_start[panels+1] filled when non-NULL. */
+int  dyb_plan(int N, int n_rows, int sm_count, int64_t* out8, int32_t* seg_base, int32_t* pseg_start);
 
 /* One context = one GPU, one basis size.  n_rows/row0 select a row shard of H'
  * (single GPU: row0 = 0, n_rows = N).  The context owns all device buffers. */

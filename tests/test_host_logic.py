@@ -1,0 +1,66 @@
+"""CPU suite: host-side logic of the product that needs no GPU -- the launch plan of the dual product (tile ranges,
+segments, panel bookkeeping the fused epilogue relies on) and the synthetic workload generator."""
+import numpy as np
+import pytest
+
+from dynemol_b200 import synthetic as syn
+
+
+@pytest.fixture(scope="module")
+def api():
+    from dynemol_b200 import build
+    build.build()
+    from dynemol_b200 import api as a
+    return a
+
+
+@pytest.mark.parametrize("N,rows,sms", [(1, 1, 148), (5, 5, 148), (257, 257, 148), (2048, 2048, 148), (4100, 4100, 148),
+                                        (10368, 10368, 148), (16384, 16384, 148), (65536, 8192, 148), (65536, 65536, 148),
+                                        (30000, 30000, 132), (1000, 1000, 4)])
+def test_plan_covers_every_tile_once_and_orders_segments_by_panel(api, N, rows, sms):
+    p = api.plan(N, rows, sms)
+    TC, PR = p["tile_cols"], p["panel_rows"]
+    assert p["panels"] == -(-rows // PR) and p["tiles_per_panel"] == -(-N // TC)
+    assert p["tiles"] == p["panels"] * p["tiles_per_panel"] and p["grid"] == min(sms, p["tiles"])
+    assert p["padded_cols"] == p["tiles_per_panel"] * TC >= N
+    G, T, TPP = p["grid"], p["tiles"], p["tiles_per_panel"]
+    covered = 0; seg_panels = []
+    for b in range(G):
+        t0, t1 = T * b // G, T * (b + 1) // G
+        assert t1 - t0 in (T // G, T // G + 1), "tile ranges are balanced to +-1"
+        assert p["seg_base"][b] == len(seg_panels)
+        covered += t1 - t0
+        if t1 > t0:
+            seg_panels += list(range(t0 // TPP, (t1 - 1) // TPP + 1))
+    assert covered == T and len(seg_panels) == p["segments"]
+    assert seg_panels == sorted(seg_panels), "segments must be globally ordered by panel (epilogue sums a contiguous range)"
+    for q in range(p["panels"]):
+        a, e = p["pseg_start"][q], p["pseg_start"][q + 1]
+        assert e > a and all(x == q for x in seg_panels[a:e])
+    assert p["pseg_start"][-1] == p["segments"]
+
+
+def test_synthetic_workload_structure():
+    w = syn.make_workload(128)
+    assert np.array_equal(w.S, w.S.T) and np.allclose(np.diag(w.S), 1.0)
+    ev = np.linalg.eigvalsh(w.S)
+    assert ev[0] > 0 and ev[-1] / ev[0] < 1e3, "overlap must be SPD with cond(S) <= 1e3 (SURVEY.md 8d)"
+    assert np.array_equal(w.h, w.h.T) and np.allclose(np.diag(w.h), w.IP)
+    for p in range(2):                                      # packets: Psi_ket = C, Psi_bra = S C, <bra|ket> = 1
+        assert np.allclose(w.Psi_bra[:, p], w.S @ w.Psi_ket[:, p])
+        assert abs(np.vdot(w.Psi_bra[:, p], w.Psi_ket[:, p]) - 1.0) < 1e-12
+    assert set(np.unique(w.fragment)) == {0, 1, 2, 3}
+    pos, sp = syn.li2s_lattice(6, 6, 6)
+    assert pos.shape == (2592, 3) and (sp == 1).sum() == 1728 and (sp == 0).sum() == 864     # examples/Li2S-crystal
+
+
+def test_torch_generators_match_numpy():
+    torch = pytest.importorskip("torch")
+    N = 128
+    w = syn.make_workload(N)
+    S, h, _ = syn.make_S_h_torch(N, "cpu")
+    assert np.abs(S.numpy() - w.S).max() < 1e-14 and np.abs(h.numpy() - w.h).max() < 1e-13
+    shard = syn.make_h_shard_colmajor_torch(N, 32, 64, "cpu", dense_tail=False)
+    assert np.abs(shard.numpy().T - w.h[32:96, :]).max() < 1e-13
+    dense = syn.make_h_shard_colmajor_torch(N, 32, 64, "cpu")
+    assert (dense == 0).sum() == 0 and np.abs(dense.numpy().T - w.h[32:96, :]).max() <= 1e-3
