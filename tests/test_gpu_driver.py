@@ -1,0 +1,79 @@
+"""GPU suite: the slice_Cheb loop mirror (dynemol_b200/driver.py; Chebyshev_driver.f:94-169) -- a trajectory through
+the driver against the golden oracle trajectory, and stop/restart through Security_copy.dat against an oracle that is
+stopped and restarted the same way (ElHl_Chebyshev.f:377-433: after a restart tau starts again from tau_max)."""
+import os
+
+import numpy as np
+import pytest
+
+from dynemol_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from dynemol_b200 import api as a
+    assert a.device_count() > 0
+    return a
+
+
+def _setup(N):
+    pos, species = syn.lattice(N // 4, 1234 + N)
+    S0, _ = syn.workload_at(pos, species)
+    C, _, _ = syn.packets(S0, N)
+    return pos, species, S0, np.asfortranarray(C.astype(np.complex128))
+
+
+def test_driver_reproduces_golden_trajectory(api, golden_dir):
+    from dynemol_b200.driver import SliceChebDriver
+    g = np.load(os.path.join(golden_dir, "traj_N64_dt2e-6_100steps.npz"))
+    N, dt = int(g["N"]), float(g["dt"])
+    pos, species, S0, C = _setup(N)
+    drv = SliceChebDriver(N, syn.fragments(N), np.arange(N) // 4, 4, dt)
+    p0 = drv.preprocess(S0, C, C)                       # AO_bra = AO_ket = C (real FMO coefficients)
+    assert np.allclose(p0[5], 1.0, atol=1e-12)
+    for step in range(25):
+        S, h = syn.workload_at(syn.perturb_positions(pos, step), species)
+        out = drv.step(S, h)
+        assert np.abs(out["pops"] - g["pops"][step]).max() < 1e-9, step
+        assert [t.n_matvec_pairs for t in out["traces"]] == list(g["pairs"][step])
+    assert abs(drv.Net_Charge.sum()) < 1e-6             # electron and hole carry opposite unit charges
+    drv.close()
+
+
+def test_stop_and_restart_matches_oracle(api, oracle_mod, tmp_path):
+    from dynemol_b200.driver import SliceChebDriver
+    N, dt, n1, n2 = 64, 2e-6, 6, 4
+    pos, species, S0, C = _setup(N)
+    frag = syn.fragments(N)
+    geo = lambda step: syn.workload_at(syn.perturb_positions(pos, step), species)
+
+    drv = SliceChebDriver(N, frag, np.arange(N) // 4, 4, dt)
+    drv.preprocess(S0, C, C)
+    for step in range(n1):
+        drv.step(*geo(step))
+    path = str(tmp_path / "Security_copy.dat")
+    drv.security_copy(path)
+    drv.close()
+
+    drv2 = SliceChebDriver(N, frag, np.arange(N) // 4, 4, dt)
+    st = drv2.from_restart(path)                        # "mv Security_copy.dat Restart_copy.dat" + restart = .true.
+    assert st.it == n1 + 1 and abs(st.t - n1 * dt) < 1e-18
+
+    # oracle stopped and restarted the same way: Psi_bra = DUAL_ket, Psi_ket = AO_ket, first_call again
+    o = oracle_mod.ElHlState(S0.T @ C, C)
+    for step in range(n1):
+        last = oracle_mod.elhl_step(o, *geo(step), dt)
+    assert np.abs(st.DUAL_ket - last["DUAL_ket"]).max() < 1e-9 and np.abs(st.AO_ket - last["AO_ket"]).max() < 1e-9
+    o2 = oracle_mod.ElHlState(st.DUAL_ket, st.AO_ket)
+    o2.t, o2.it, o2.first_call = st.t, st.it, True
+    for step in range(n1, n1 + n2):
+        out = drv2.step(*geo(step))
+        ref = oracle_mod.elhl_step(o2, *geo(step), dt)
+        pops_ref = oracle_mod.populations(frag, ref["DUAL_bra"], ref["DUAL_ket"], ref["t"], 4)
+        assert np.abs(out["pops"] - pops_ref).max() < 1e-9
+        assert [t.n_matvec_pairs for t in out["traces"]] == [t.n_matvec_pairs for t in ref["traces"]]
+        erg_ref = oracle_mod.quasiparticle_energies(ref["AO_bra"], ref["AO_ket"], geo(step)[1])
+        assert np.abs(out["erg"] - erg_ref).max() < 1e-8 * np.abs(erg_ref).max()
+    drv2.close()
