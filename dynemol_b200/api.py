@@ -136,9 +136,13 @@ class Propagator:
         self.n_part = 0
 
     def close(self):
-        if getattr(self, "_h", None) and self._h.value:
-            lib.dyb_destroy(self._h)
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
             self._h = C.c_void_p()
+            try:
+                lib.dyb_destroy(h)
+            except Exception:          # interpreter shutdown: the library may already be gone
+                pass
 
     __del__ = close
 
