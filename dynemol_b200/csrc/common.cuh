@@ -11,8 +11,15 @@ namespace dyb {
 // A CTA owns a "panel" of PANEL_ROWS matrix rows at a time and sweeps tiles of TILE_COLS columns.
 // The panel is split into 8 sub-panels of 256 rows, one per consumer warp; inside a warp, lane l
 // owns rows 64*m + 2*l + {0,1}, m = 0..3 (four 128-bit loads per column, 8 rows per thread).
-constexpr int SUB_ROWS     = 256;                  // rows per consumer warp
-constexpr int N_CWARPS     = 8;                    // consumer warps per CTA
+#ifndef DYB_SUB_ROWS
+#define DYB_SUB_ROWS 256
+#endif
+#ifndef DYB_N_CWARPS
+#define DYB_N_CWARPS 8
+#endif
+constexpr int SUB_ROWS     = DYB_SUB_ROWS;         // rows per consumer warp (256: 8 rows per thread; 128: 4 rows per thread)
+constexpr int N_CWARPS     = DYB_N_CWARPS;         // consumer warps per CTA (8 with 256 rows, 16 with 128 rows)
+constexpr int MPT          = SUB_ROWS / 64;        // 128-bit loads per thread and column (two rows each)
 constexpr int PANEL_ROWS   = SUB_ROWS * N_CWARPS;  // 2048
 #ifndef DYB_TILE_COLS
 #define DYB_TILE_COLS 4

@@ -84,13 +84,13 @@ constexpr int RED_MASK  = (1 << RED_SHIFT) - 1;
 
 // Per-thread state of a consumer: 8 rows (m = 0..3, e = 0..1) x 4 right-hand sides.
 struct ConsumerRegs {
-    double acc[4][2][NQ];   // ket partial sums of the thread's 8 rows
-    double xb[4][2][NQ];    // bra input at the thread's 8 rows
+    double acc[MPT][2][NQ];   // ket partial sums of the thread's 2*MPT rows
+    double xb[MPT][2][NQ];    // bra input at the thread's 2*MPT rows
 };
 
 __device__ __forceinline__ void zero_acc(ConsumerRegs& r) {
 #pragma unroll
-    for (int m = 0; m < 4; ++m)
+    for (int m = 0; m < MPT; ++m)
 #pragma unroll
         for (int e = 0; e < 2; ++e)
 #pragma unroll
@@ -101,7 +101,7 @@ __device__ __forceinline__ void zero_acc(ConsumerRegs& r) {
 __device__ __forceinline__ void load_xb(ConsumerRegs& r, const double* __restrict__ Xb, long long panel, int w, int lane) {
     const double2* base = reinterpret_cast<const double2*>(Xb + ((panel * PANEL_ROWS + w * SUB_ROWS + 2 * lane) * NQ));
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
+    for (int m = 0; m < MPT; ++m) {
         const double2* p = base + m * (64 * NQ / 2);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
@@ -114,7 +114,7 @@ __device__ __forceinline__ void load_xb(ConsumerRegs& r, const double* __restric
 __device__ __forceinline__ void store_acc(const ConsumerRegs& r, double* __restrict__ ket_slab, long long seg, int w, int lane) {
     double2* base = reinterpret_cast<double2*>(ket_slab + ((seg * PANEL_ROWS + w * SUB_ROWS + 2 * lane) * NQ));
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
+    for (int m = 0; m < MPT; ++m) {
         double2* p = base + m * (64 * NQ / 2);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
@@ -126,7 +126,7 @@ __device__ __forceinline__ void store_acc(const ConsumerRegs& r, double* __restr
 
 // One column of the thread's 8 rows: 32 FMAs for the ket, 32 for the bra (two independent chains per
 // right-hand side -- even and odd rows -- summed at the end; fixed order, so still deterministic).
-__device__ __forceinline__ void fma_column(ConsumerRegs& r, const double2 (&h)[4], const double (&xk)[NQ], double (&p)[NQ]) {
+__device__ __forceinline__ void fma_column(ConsumerRegs& r, const double2 (&h)[MPT], const double (&xk)[NQ], double (&p)[NQ]) {
     double p1[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
@@ -134,7 +134,7 @@ __device__ __forceinline__ void fma_column(ConsumerRegs& r, const double2 (&h)[4
         p1[q] = h[0].y * r.xb[0][1][q];
     }
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
+    for (int m = 0; m < MPT; ++m) {
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
             r.acc[m][0][q] = fma(h[m].x, xk[q], r.acc[m][0][q]);
@@ -250,19 +250,25 @@ dual_matvec_tma_kernel(const __grid_constant__ CUtensorMap tmap, const MatvecPar
             const double2* sX = reinterpret_cast<const double2*>(stage + STAGE_H_BYTES);
 
             double pv[TILE_COLS * NQ];
+#ifdef DYB_NO_MATH      // ceiling experiment: stream the tiles, touch one value per stage, do no arithmetic
+#pragma unroll
+            for (int q = 0; q < TILE_COLS * NQ; ++q) pv[q] = 0.0;
+            r.acc[0][0][0] += sH[(size_t)w * SUB_ROWS + lane] + sX[0].x;
+#else
 #pragma unroll
             for (int c = 0; c < TILE_COLS; ++c) {
                 const double2 x01 = sX[c * 2], x23 = sX[c * 2 + 1];
                 const double xk[NQ] = {x01.x, x01.y, x23.x, x23.y};
                 const double2* hp = reinterpret_cast<const double2*>(sH + (size_t)(c * N_CWARPS + w) * SUB_ROWS) + lane;
-                double2 h[4];
+                double2 h[MPT];
 #pragma unroll
-                for (int m = 0; m < 4; ++m) h[m] = hp[m * 32];
+                for (int m = 0; m < MPT; ++m) h[m] = hp[m * 32];
                 double p[NQ];
                 fma_column(r, h, xk, p);
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) pv[c * NQ + q] = p[q];
             }
+#endif
             const double tot = transpose_reduce<TILE_COLS * NQ>(pv, lane);
             if ((lane & RED_MASK) == 0)
                 red[rslot * (N_CWARPS * TILE_COLS * NQ) + w * (TILE_COLS * NQ) + (lane >> RED_SHIFT)] = tot;
@@ -306,7 +312,7 @@ dual_matvec_tma_kernel(const __grid_constant__ CUtensorMap tmap, const MatvecPar
 // =================================================================================================
 constexpr int LDG_THREADS = N_CWARPS * 32;   // 256
 
-__device__ __forceinline__ void ldg_tile(double2 (&h)[TILE_COLS][4], const MatvecParams& P, int panel, int ct, int w, int lane) {
+__device__ __forceinline__ void ldg_tile(double2 (&h)[TILE_COLS][MPT], const MatvecParams& P, int panel, int ct, int w, int lane) {
     const long long rb = (long long)panel * PANEL_ROWS + (long long)w * SUB_ROWS;   // first row of this warp's sub-panel
     const bool rows_ok = rb < P.ld;                                           // ld is a multiple of 256
 #pragma unroll
@@ -315,7 +321,7 @@ __device__ __forceinline__ void ldg_tile(double2 (&h)[TILE_COLS][4], const Matve
         const bool ok = rows_ok && col < P.Nc;
         const double* src = P.H + col * P.ld + rb + 2 * lane;
 #pragma unroll
-        for (int m = 0; m < 4; ++m) h[c][m] = ok ? ldg_stream(src + m * 64) : make_double2(0.0, 0.0);
+        for (int m = 0; m < MPT; ++m) h[c][m] = ok ? ldg_stream(src + m * 64) : make_double2(0.0, 0.0);
     }
 }
 
@@ -338,17 +344,17 @@ dual_matvec_ldg_kernel(const MatvecParams P)
     int seg = P.seg_base[b];
     int panel = t0 / P.TPP, ct = t0 - panel * P.TPP;
 
-    double2 hbuf[TILE_COLS][4];
+    double2 hbuf[TILE_COLS][MPT];
     ldg_tile(hbuf, P, panel, ct, w, lane);
 
     for (int j = 0; j < nt; ++j) {
         if (j == 0 || ct == 0) load_xb(r, P.Xb, panel, w, lane);
 
-        double2 h[TILE_COLS][4];
+        double2 h[TILE_COLS][MPT];
 #pragma unroll
         for (int c = 0; c < TILE_COLS; ++c)
 #pragma unroll
-            for (int m = 0; m < 4; ++m) h[c][m] = hbuf[c][m];
+            for (int m = 0; m < MPT; ++m) h[c][m] = hbuf[c][m];
         if (j + 1 < nt) {                                                                 // prefetch next tile
             const bool wrap = (ct + 1 == P.TPP);
             ldg_tile(hbuf, P, wrap ? panel + 1 : panel, wrap ? 0 : ct + 1, w, lane);
