@@ -317,3 +317,31 @@ def test_li2s_crystal_size_step(api, oracle_mod):
         assert abs(abs(np.vdot(gb[:, p], gk[:, p])) - 1.0) < 1e-7
         assert abs(e[p] - np.vdot(b, Hp @ k)) < 1e-8 * abs(e[p])
     P.close()
+
+
+def test_legacy_symbol_at_headline_size(api):
+    """propagationelhl2_gpucaller_ at N = 16384 (BASELINE config 3) with host S, h exactly as the Fortran caller would
+    pass them.  The oracle cannot form S^-1 h at this size in test time, so the check is by properties that pin every
+    output: S H' = h, S AO_bra = PSI_bra, charge conservation to the algorithm's 1e-8, untouched AO_ket."""
+    import torch
+    N = 16384
+    S_t, h_t, _ = syn.make_S_h_torch(N, torch.device("cuda", 0))
+    S = np.asfortranarray(S_t.cpu().numpy()); h = np.asfortranarray(h_t.cpu().numpy())
+    del S_t, h_t
+    torch.cuda.empty_cache()
+    w = 64
+    C = np.zeros((N, 2)); C[0:w, 0] = np.random.default_rng(42).normal(size=w); C[w:2 * w, 1] = np.random.default_rng(43).normal(size=w)
+    SC = S @ C
+    C /= np.sqrt(np.einsum("ip,ip->p", C, SC)); SC = S @ C
+    dt = 1e-6
+    out = api.legacy_propagationelhl(S, h, SC.astype(np.complex128), C.astype(np.complex128), 0.0, dt, dt / H_BAR)
+    Hp = out["H_prime"]
+    cols = np.r_[0:16, N - 16:N]
+    assert np.abs(S @ Hp[:, cols] - h[:, cols]).max() / np.abs(h).max() < 1e-11                 # H' = S^-1 h
+    for p in range(2):
+        assert np.abs(S @ out["AO_bra"][:, p] - out["PSI_bra"][:, p]).max() < 1e-10             # AO_bra = S^-1 PSI_bra
+        assert abs(abs(np.vdot(out["PSI_bra"][:, p], out["PSI_ket"][:, p])) - 1.0) < 2e-8       # Taylor.f:104
+        assert np.abs(out["PSI_bra"][:, p] - S @ out["PSI_ket"][:, p]).max() < 1e-7             # bra stays S ket
+        assert out["save_tau"][p] > 0
+    assert np.isnan(out["AO_ket"]).all()
+    api.gpu_finalize()
