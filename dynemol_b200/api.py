@@ -79,7 +79,7 @@ DECLARED_SYMBOLS = [
     "dyb_get_info", "dyb_upload_hprime", "dyb_upload_hprime_device", "dyb_upload_hprime_rows_device", "dyb_hprime_device", "dyb_form_hprime", "dyb_form_hprime_device", "dyb_form_hprime_from_overlap",
     "dyb_download_hprime", "dyb_set_packets", "dyb_get_packets", "dyb_propagate", "dyb_ao_bra",
     "dyb_populations", "dyb_run_terms", "dyb_dual_matvec", "dyb_sync", "dyb_launch_count",
-    "dyb_comm_unique_id", "dyb_comm_init", "dyb_comm_p2p_handle", "dyb_comm_p2p_open", "dyb_set_spectral_bounds", "dyb_get_spectral_bounds", "dyb_estimate_spectral_bounds",
+    "dyb_comm_unique_id", "dyb_comm_init", "dyb_comm_p2p_handle", "dyb_comm_p2p_open", "dyb_comm_p2p_enable", "dyb_set_spectral_bounds", "dyb_get_spectral_bounds", "dyb_estimate_spectral_bounds",
     "dyb_quasiparticle_energies", "dyb_ehrenfest_kernel",
 ]
 
@@ -282,6 +282,9 @@ class Propagator:
 
     def comm_p2p_open(self, handles: bytes):
         _check(lib.dyb_comm_p2p_open(self._h, C.c_char_p(handles)))
+
+    def comm_p2p_enable(self, on: bool):
+        _check(lib.dyb_comm_p2p_enable(self._h, C.c_int(1 if on else 0)))
 
     def sync(self):
         _check(lib.dyb_sync(self._h))

@@ -972,6 +972,17 @@ int dyb_comm_p2p_open(dyb_ctx* c, const char* handles /* world x 64 bytes, rank 
     return DYB_OK;
 }
 
+// switch between the fused peer-memory exchange and the NCCL collectives (collective decision: every rank must pass
+// the same value); enabling needs a successful dyb_comm_p2p_open
+int dyb_comm_p2p_enable(dyb_ctx* c, int on) {
+    if (!c) return fail(DYB_EINVAL, "ctx is NULL");
+    if (on) {
+        for (int r = 0; r < c->world; ++r) if (!c->peer_base[r]) return fail(DYB_EINVAL, "peer %d is not mapped: call dyb_comm_p2p_open first", r);
+    }
+    c->p2p = on != 0;
+    return DYB_OK;
+}
+
 int dyb_comm_init(dyb_ctx* c, int rank, int world, const char* id128) {
     if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return fail(DYB_EINVAL, "bad argument");
     if (c->N % world != 0 || c->M != c->N / world || c->row0 != rank * c->M)

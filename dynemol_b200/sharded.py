@@ -46,11 +46,29 @@ def init_sharded(N: int, dist, local_rank: int):
     uid = broadcast_unique_id(dist, api.comm_unique_id, device=dev)
     P.comm_init(rank, world, uid)
     if world <= 8 and os.environ.get("DYNEMOL_B200_P2P", "1") != "0":
-        # fused exchange over NVLink peer memory: all-gather the 64-byte CUDA-IPC handles, map the peers
-        mine = torch.tensor(list(P.comm_p2p_handle()), dtype=torch.uint8, device=dev)
+        # fused exchange over NVLink peer memory: all-gather the 64-byte CUDA-IPC handles, map the peers.  If any rank
+        # cannot export or map (no peer access, IPC disabled in the container), EVERY rank falls back to NCCL.
+        ok = 1
+        try:
+            mine = torch.tensor(list(P.comm_p2p_handle()), dtype=torch.uint8, device=dev)
+        except api.DynemolB200Error as e:
+            ok = 0; mine = torch.zeros(64, dtype=torch.uint8, device=dev); err = e
         allh = torch.empty(64 * world, dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(allh, mine)
-        P.comm_p2p_open(bytes(allh.cpu().tolist()))
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            try:
+                P.comm_p2p_open(bytes(allh.cpu().tolist()))
+            except api.DynemolB200Error as e:
+                ok = 0; err = e
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        use_p2p = int(flag.item()) == 1
+        if not use_p2p:
+            P.comm_p2p_enable(False)
+            if rank == 0:
+                print("dynemol_b200: peer-memory exchange unavailable, using NCCL collectives", flush=True)
         dist.barrier()
     return P, row0, m
 

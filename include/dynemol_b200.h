@@ -205,6 +205,7 @@ int  dyb_comm_init(dyb_ctx* ctx, int rank, int world, const char* id128);
  * with st.release.sys / ld.acquire.sys epoch flags instead of NCCL launches. */
 int  dyb_comm_p2p_handle(dyb_ctx* ctx, char* out64);
 int  dyb_comm_p2p_open(dyb_ctx* ctx, const char* handles);
+int  dyb_comm_p2p_enable(dyb_ctx* ctx, int on);   /* collective: same value on every rank; 0 = NCCL collectives */
 
 int  dyb_sync(dyb_ctx* ctx);
 int64_t dyb_launch_count(dyb_ctx* ctx);   /* kernels of THIS library launched so far */
