@@ -120,7 +120,7 @@ def recorded_traffic(N):
 
 
 # ----------------------------------------------------------------------------------------------- workloads
-def build_single_gpu(N, device=0):
+def build_single_gpu(N, device=0, keep_host=False):
     """Synthetic EHT S, h on the device (input generation with torch = plumbing), H' = S^-1 h formed by the
     library (cuSOLVER potrf + potrs), packets on the host."""
     import torch
@@ -144,9 +144,14 @@ def build_single_gpu(N, device=0):
     Ct = Ct / nrm; SC = SC / nrm
     Psi_ket = np.asfortranarray(Ct.cpu().numpy().astype(np.complex128))
     Psi_bra = np.asfortranarray(SC.cpu().numpy().astype(np.complex128))
+    host = None
+    if keep_host:                                  # pinned host copies of S and h for the legacy-symbol end-to-end leg
+        Sh = torch.empty((N, N), dtype=torch.float64, pin_memory=True); hh = torch.empty((N, N), dtype=torch.float64, pin_memory=True)
+        Sh.copy_(S); hh.copy_(h)
+        host = (Sh, hh)
     del S, h, SC, Ct
     torch.cuda.empty_cache()
-    return P, Psi_bra, Psi_ket, {"gen_s": t1 - t0, "form_hprime_s": t2 - t1}
+    return P, Psi_bra, Psi_ket, {"gen_s": t1 - t0, "form_hprime_s": t2 - t1}, host
 
 
 def pick_tau(N):
@@ -165,9 +170,9 @@ def run_ours_single(args):
         P = api.Propagator(N)
         t0 = time.time(); sharded.fill_rows(P, N, 0, N, torch.device("cuda", 0)); build_info = {"gen_s": time.time() - t0, "operator": "Hueckel h + dense decaying tail (surrogate)"}
         Psi_bra, Psi_ket = sharded.synthetic_packets(N)
-        args.skip_e2e = True; args.skip_cpu = True
+        args.skip_e2e = True; args.skip_cpu = True; host_Sh = None
     else:
-        P, Psi_bra, Psi_ket, build_info = build_single_gpu(N)
+        P, Psi_bra, Psi_ket, build_info, host_Sh = build_single_gpu(N, keep_host=not args.skip_e2e)
     P.set_packets(Psi_bra, Psi_ket)
     if args.kernel == "ldg":
         P.set_kernel(api.KERNEL_LDG)
@@ -205,6 +210,12 @@ def run_ours_single(args):
         e2e = None
     else:
         e2e = run_e2e(args, P, N, Psi_bra, Psi_ket)
+        if host_Sh is not None:
+            try:
+                e2e["legacy_symbol"] = run_e2e_legacy(args, N, Psi_bra, Psi_ket, host_Sh)
+            except Exception as ex:     # side measurement: never lose the headline line
+                e2e["legacy_symbol"] = {"error": repr(ex)[:200]}
+            host_Sh = None
     cpu = None if args.skip_cpu else cpu_baseline(np.asfortranarray(P.download_hprime()), Psi_bra, Psi_ket, tau, budget_s=args.cpu_budget)
 
     n65536 = None
@@ -291,6 +302,28 @@ def run_e2e(args, P, N, Psi_bra, Psi_ket):
                     % ("estimate_spectral_bounds(24)+" if cheb else "", "Chebyshev" if cheb else "Taylor", dt_e2e),
             "terms_per_call": passes // e2e_steps, "s_per_call": round(t_e2e / e2e_steps, 4),
             "note": "series terms only; the 24 Lanczos passes per call are timed but not counted" if cheb else ""}
+
+
+def run_e2e_legacy(args, N, Psi_bra, Psi_ket, host_Sh):
+    """The PRIMARY boundary symbol (batched form): propagationelhl2_gpucaller_(N, S, h, H', AO_bra, AO_ket, PSI_bra,
+    PSI_ket, t_init, t_max, tau, save_tau) called by reference with pinned host S, h, exactly like ElHl_Chebyshev_GPU.f:
+    269-272 -- H2D of S and h (16 N^2 B), S^-1 h on the device, Chebyshev step of dt = 0.5 fs, D2H of H' (8 N^2 B), of the
+    packets and of AO_bra, all inside the timed call.  The O(N^3) formation dominates; terms/s is the same metric."""
+    from dynemol_b200 import api
+    os.environ["DYNEMOL_B200_MODE"] = "chebyshev"
+    S = host_Sh[0].numpy().T; h = host_Sh[1].numpy().T              # symmetric: Fortran-ordered views of the pinned buffers
+    dt = 5e-4; tau_max = dt / H_BAR
+    # per-call pass count is not returned by the void symbol: take it from the native API on the same operator and step
+    out = api.legacy_propagationelhl(S, h, Psi_bra, Psi_ket, 0.0, dt, tau_max, copy_inputs=False)   # first nuclear step (untimed)
+    tau = np.minimum(tau_max, 1.15 * out["save_tau"])
+    t0 = time.perf_counter()
+    out = api.legacy_propagationelhl(S, h, Psi_bra, Psi_ket, 0.0, dt, tau, copy_inputs=False)
+    t = time.perf_counter() - t0
+    api.gpu_finalize()
+    os.environ.pop("DYNEMOL_B200_MODE", None)
+    return {"s_per_call": round(t, 4), "h2d_bytes": int(16 * N * N + 2 * 2 * 16 * N), "d2h_bytes": int(8 * N * N + 3 * 2 * 16 * N),
+            "call": "propagationelhl2_gpucaller_ (host S, h -> H', packets, AO_bra), Chebyshev, dt=0.0005 ps",
+            "note": "H' output buffer is pageable host memory (the Fortran caller pins it with GPU_Pin)"}
 
 
 def cpu_baseline(Hp_np, Psi_bra, Psi_ket, tau, budget_s=15.0):

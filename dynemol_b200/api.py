@@ -298,11 +298,14 @@ def _ref(x, ctype):
     return C.byref(ctype(x))
 
 
-def legacy_propagationelhl(S, h, PSI_bra, PSI_ket, t_init, t_max, tau, batched: bool | None = None):
+def legacy_propagationelhl(S, h, PSI_bra, PSI_ket, t_init, t_max, tau, batched: bool | None = None, copy_inputs: bool = True):
     """call PropagationElHl_gpucaller(N, S, h0, H_prime, AO_bra(:,p), AO_ket(:,p), Psi_t_bra(:,p), Psi_t_ket(:,p),
     t_init, t_max, tau, save_tau)  -- ElHl_Chebyshev_GPU.f:269-272.  PSI_* of shape (N,) use the per-particle
     symbol, shape (N,2) the batched el+hole symbol.  Returns dict(H_prime, AO_bra, PSI_bra, PSI_ket, save_tau)."""
-    S = np.array(S, dtype=np.float64, order="F", copy=True); h = np.array(h, dtype=np.float64, order="F", copy=True)
+    if copy_inputs:
+        S = np.array(S, dtype=np.float64, order="F", copy=True); h = np.array(h, dtype=np.float64, order="F", copy=True)
+    else:                      # S and h are read-only for the callee (const double* in the ABI)
+        S = _fd(S); h = _fd(h)
     N = S.shape[0]
     PSI_bra = _fz(PSI_bra); PSI_ket = _fz(PSI_ket)
     two = PSI_bra.ndim == 2 and PSI_bra.shape[1] == 2
