@@ -50,6 +50,27 @@ def main():
             out["ok"] = bool(out["ok"] and same_trace and save_tau[p] == st and eb < 1e-10 and ek < 1e-10)
         out["worst_rel_err"] = float(worst)
         out["pairs"] = [int(t.n_matvec_pairs) for t in traces]
+    dist.barrier()
+
+    # Chebyshev mode through the same exchange (three-term recurrence reads x and x_prev on the owned slice)
+    e = np.linalg.eigvals(Hp).real
+    lo, hi = e.min() - 0.05 * (e.max() - e.min()), e.max() + 0.05 * (e.max() - e.min())
+    dt2 = 20 * dt; tau2 = dt2 / api.H_BAR
+    P.set_packets(w.Psi_bra, w.Psi_ket)
+    P.set_spectral_bounds(lo, hi)
+    save2, traces2 = P.propagate(0.0, dt2, tau2, mode=api.MODE_CHEBYSHEV)
+    bra2, ket2 = P.get_packets()
+    mark('chebyshev propagated')
+    if rank == 0:
+        worst2 = 0.0
+        for p in range(2):
+            b, k, _, st, tr = oracle.cheb_scaled_propagation(Hp, w.Psi_bra[:, p], w.Psi_ket[:, p], 0.0, dt2, tau2, 0.5 * (hi + lo), 0.5 * (hi - lo))
+            eb = np.abs(bra2[:, p] - b).max() / np.abs(b).max(); ek = np.abs(ket2[:, p] - k).max() / np.abs(k).max()
+            worst2 = max(worst2, eb, ek)
+            same = [(x[0], x[1], x[2]) for x in traces2[p].events()] == [(x[0], x[1], x[2]) for x in tr.events()]
+            out["ok"] = bool(out["ok"] and same and eb < 1e-10 and ek < 1e-10)
+        out["worst_rel_err_cheb"] = float(worst2)
+        out["pairs_cheb"] = [int(t.n_matvec_pairs) for t in traces2]
         print("SHARDED_RESULT " + json.dumps(out), flush=True)
     dist.barrier()
     P.close()
