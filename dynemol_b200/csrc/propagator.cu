@@ -171,7 +171,11 @@ static Plan make_plan(int N, int M, int sm_count) {
     p.TPP   = (N + TILE_COLS - 1) / TILE_COLS;
     p.Ncpad = p.TPP * TILE_COLS;
     p.T     = p.NP * p.TPP;
-    p.grid  = std::min(sm_count, p.T);
+    // small operators: fewer, longer-running CTAs (every CTA costs a 64 KiB ket slab, barrier set-up and a pipeline
+    // fill, and every segment is one more term in the epilogue's slab sums)
+    int min_tiles = (p.T < 8 * sm_count) ? 4 : 1;          // measured: N=1024 28 -> 21 us per term, N>=4096 unaffected
+    if (const char* e = getenv("DYNEMOL_B200_MIN_TILES")) min_tiles = std::max(1, atoi(e));
+    p.grid  = std::max(1, std::min(sm_count, p.T / min_tiles));
     p.seg_base.assign(p.grid, 0);
     std::vector<int> pcount(p.NP, 0);
     int seg = 0;
