@@ -1292,6 +1292,7 @@ int dyb_ehrenfest_kernel(dyb_ctx* c, const double* h_A, const double* h_X, doubl
 
 int dyb_populations(dyb_ctx* c, int n_part, int n_frag, const int32_t* fragment, double t, double* out) {
     if (!c || !fragment || !out || n_part < 1 || n_part > 2 || n_frag < 0 || n_frag > MAX_FRAG) return fail(DYB_EINVAL, "bad argument");
+    if (c->M != c->N) return fail(DYB_EINVAL, "full-matrix contexts only (row-sharded: gather the packets with dyb_get_packets)");
     CK(cudaSetDevice(c->device));
     if (!c->frag) CK(cudaMalloc(&c->frag, sizeof(int) * c->N));
     CK(cudaMemcpyAsync(c->frag, fragment, sizeof(int) * c->N, cudaMemcpyHostToDevice, c->stream));
