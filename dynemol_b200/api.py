@@ -75,7 +75,7 @@ lib = _load()
 DECLARED_SYMBOLS = [
     "propagationelhl_gpucaller_", "propagationelhl2_gpucaller_", "propagation_gpucaller_", "nakedbessel_", "ehrenfestkernel_gpu_",
     "gpu_init_", "gpu_finalize_", "gpu_pin_", "gpu_unpin_",
-    "dyb_last_error", "dyb_version", "dyb_device_count", "dyb_plan", "dyb_create", "dyb_destroy", "dyb_set_kernel",
+    "dyb_last_error", "dyb_version", "dyb_device_count", "dyb_plan", "dyb_create", "dyb_destroy", "dyb_set_kernel", "dyb_set_persistent",
     "dyb_get_info", "dyb_upload_hprime", "dyb_upload_hprime_device", "dyb_upload_hprime_rows_device", "dyb_hprime_device", "dyb_form_hprime", "dyb_form_hprime_device", "dyb_form_hprime_from_overlap",
     "dyb_download_hprime", "dyb_set_packets", "dyb_get_packets", "dyb_propagate", "dyb_ao_bra",
     "dyb_populations", "dyb_run_terms", "dyb_dual_matvec", "dyb_sync", "dyb_launch_count",
@@ -149,10 +149,13 @@ class Propagator:
     def set_kernel(self, kernel: int):
         _check(lib.dyb_set_kernel(self._h, C.c_int(kernel)))
 
+    def set_persistent(self, on: bool):
+        _check(lib.dyb_set_persistent(self._h, C.c_int(1 if on else 0)))
+
     def info(self) -> dict:
         buf = (C.c_int64 * 16)()
         _check(lib.dyb_get_info(self._h, buf))
-        keys = ["N", "ld", "n_rows", "grid", "tiles", "segments", "sm_count", "smem_bytes", "variant", "panels", "tiles_per_panel", "passes_last", "p2p"]
+        keys = ["N", "ld", "n_rows", "grid", "tiles", "segments", "sm_count", "smem_bytes", "variant", "panels", "tiles_per_panel", "passes_last", "p2p", "persistent"]
         return {k: int(buf[i]) for i, k in enumerate(keys)}
 
     # ---- operator

@@ -185,8 +185,11 @@ __device__ __forceinline__ void issue_tile_h(uint8_t* smem, uint64_t* bar_full, 
     mbar_arrive_expect_tx(&bar_full[stage], STAGE_TX_BYTES);
     tma_load_3d(smem + (size_t)stage * STAGE_BYTES, tmap, &bar_full[stage], 0, tc.panel * N_CWARPS, tc.ct * TILE_COLS, policy);
 }
+__device__ __forceinline__ void issue_tile_x(uint8_t* smem, uint64_t* bar_full, const double* Xk, int stage, const TileCursor& tc) {
+    bulk_load_1d(smem + (size_t)stage * STAGE_BYTES + STAGE_H_BYTES, Xk + (size_t)tc.ct * TILE_COLS * NQ, TILE_COLS * NQ * 8, &bar_full[stage]);
+}
 __device__ __forceinline__ void issue_tile_x(uint8_t* smem, uint64_t* bar_full, const MatvecParams& P, int stage, const TileCursor& tc) {
-    bulk_load_1d(smem + (size_t)stage * STAGE_BYTES + STAGE_H_BYTES, P.Xk + (size_t)tc.ct * TILE_COLS * NQ, TILE_COLS * NQ * 8, &bar_full[stage]);
+    issue_tile_x(smem, bar_full, P.Xk, stage, tc);
 }
 
 __global__ void __launch_bounds__(TMA_THREADS, 1)

@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "matvec.cuh"
 #include "epilogue.cuh"
+#include "series.cuh"
 
 using namespace dyb;
 typedef std::complex<double> cplx;
@@ -88,6 +89,9 @@ struct dyb_ctx {
     size_t Lq = 0;                       // quad vector length (indices)
     int variant = DYB_KERNEL_TMA;
     bool use_pdl = true;                 // programmatic dependent launch between the dual product and the epilogue
+    bool persistent = false;             // one cooperative launch per series (series.cuh) instead of two launches per term
+    PassParams* d_passes = nullptr;      // per-term parameters of the series in flight
+    unsigned long long* gbar = nullptr;  // grid barrier counter
     cudaStream_t stream = nullptr;
     CUtensorMap tmap;
     bool have_tmap = false;
@@ -328,6 +332,30 @@ static int run_term(dyb_ctx* c, const EpiParams& E, int cur, int nxt, bool use_c
     return DYB_OK;
 }
 
+// Whole series in one cooperative launch (series.cuh).  Usable when every CTA owns at least TMA_STAGES tiles.
+static bool persistent_ok(const dyb_ctx* c) {
+    return c->persistent && c->world == 1 && c->variant == DYB_KERNEL_TMA && c->T >= TMA_STAGES * c->grid;
+}
+constexpr int MAX_SERIES_TERMS = 32;
+
+static int run_series_persistent(dyb_ctx* c, const std::vector<PassParams>& passes) {
+    const int n = (int)passes.size();
+    if (n < 1 || n > MAX_SERIES_TERMS) return fail(DYB_EINVAL, "series length %d out of range", n);
+    CK(cudaMemcpyAsync(c->d_passes, passes.data(), sizeof(PassParams) * n, cudaMemcpyHostToDevice, c->stream));   // pageable source: staged before return
+    CK(cudaMemsetAsync(c->gbar, 0, sizeof(unsigned long long), c->stream));
+    SeriesParams S;
+    memset(&S, 0, sizeof S);
+    S.mv = matvec_params(c, nullptr, nullptr, false);
+    S.row0 = c->row0; S.n_bra_slabs = c->NP; S.pseg_start = c->pseg_start;
+    for (int i = 0; i < 3; ++i) { S.vb[i] = c->vb[i]; S.vk[i] = c->vk[i]; }
+    S.sum_b = c->sum_b; S.sum_k = c->sum_k; S.blockpart = c->blockpart; S.ctrl = c->ctrl;
+    S.passes = c->d_passes; S.n_steps = n; S.gbar = c->gbar;
+    void* args[] = {(void*)&c->tmap, (void*)&S};
+    CK(cudaLaunchCooperativeKernel((const void*)series_kernel, dim3(c->grid), dim3(TMA_THREADS), args, TmaSmem::total, c->stream));
+    c->launches++;
+    return DYB_OK;
+}
+
 static int launch_series_init(dyb_ctx* c, const int adopt[2], const int active[2], int cur, const cplx* sum_scale = nullptr) {
     InitParams I;
     I.M = c->M; I.row0 = c->row0; I.Nc = c->N;
@@ -485,6 +513,15 @@ static int propagate_series(dyb_ctx* c, int mode, double t_init, double t_max, c
         int prv = 2, cur = 0, nxt = 1;
         if ((rc = launch_series_init(c, adopt, active, cur, mode == DYB_MODE_TAYLOR ? nullptr : sum_scale))) return rc;
         adopt[0] = adopt[1] = 0;
+        if (persistent_ok(c) && L <= MAX_SERIES_TERMS) {
+            std::vector<PassParams> passes(L);
+            for (int s = 0; s < L; ++s) {
+                memset(&passes[s], 0, sizeof(PassParams));
+                for (int p = 0; p < 2; ++p)
+                    if (active[p] && s < P[p].n_terms) fill_pass(passes[s].part[p], P[p], mode, s, ebar, de);
+            }
+            if ((rc = run_series_persistent(c, passes))) return rc;
+        } else
         for (int s = 0; s < L; ++s) {
             EpiParams E = epi_params(c, cur, prv, nxt);
             for (int p = 0; p < 2; ++p) {
@@ -603,6 +640,8 @@ int dyb_destroy(dyb_ctx* c) {
     if (c->pseg_start) cudaFree(c->pseg_start);
     if (c->frag) cudaFree(c->frag);
     if (c->ctrl) cudaFree(c->ctrl);
+    if (c->d_passes) cudaFree(c->d_passes);
+    if (c->gbar) cudaFree(c->gbar);
     if (c->h_ctrl) cudaFreeHost(c->h_ctrl);
     if (c->h_scal) cudaFreeHost(c->h_scal);
     for (auto e : c->ev) cudaEventDestroy(e);
@@ -649,6 +688,10 @@ int dyb_create(dyb_ctx** out, int device, int N, int row0, int n_rows) {
     CKCU(cudaMallocHost(&c->h_scal, 64 * sizeof(double)));
     CKC(build_tensor_map(c));
     CKCU(cudaFuncSetAttribute(dual_matvec_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TmaSmem::total));
+    CKCU(cudaFuncSetAttribute(series_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TmaSmem::total));
+    CKCU(cudaMalloc(&c->d_passes, sizeof(PassParams) * MAX_SERIES_TERMS));
+    CKCU(cudaMalloc(&c->gbar, sizeof(unsigned long long)));
+    if (const char* e = getenv("DYNEMOL_B200_PERSISTENT")) c->persistent = (e[0] != '0');
     CKCU(cudaDeviceSynchronize());     // the zero fills above ran on the legacy stream; c->stream is non-blocking
 #undef CKC
 #undef CKCU
@@ -665,11 +708,18 @@ int dyb_set_kernel(dyb_ctx* c, int v) {
     return DYB_OK;
 }
 
+int dyb_set_persistent(dyb_ctx* c, int on) {
+    if (!c) return fail(DYB_EINVAL, "ctx is NULL");
+    c->persistent = on != 0;
+    return DYB_OK;
+}
+
 int dyb_get_info(dyb_ctx* c, int64_t* o) {
     if (!c || !o) return fail(DYB_EINVAL, "NULL argument");
     memset(o, 0, 16 * sizeof(int64_t));
     o[0] = c->N; o[1] = c->ld; o[2] = c->M; o[3] = c->grid; o[4] = c->T; o[5] = c->n_seg; o[6] = c->sm_count;
     o[7] = TmaSmem::total; o[8] = c->variant; o[9] = c->NP; o[10] = c->TPP; o[11] = c->passes_last; o[12] = c->p2p ? 1 : 0;
+    o[13] = persistent_ok(c) ? 1 : 0;
     return DYB_OK;
 }
 
@@ -1030,6 +1080,30 @@ int dyb_run_terms(dyb_ctx* c, double tau, int n_terms, float* elapsed_ms, float*
     while (c->ev.size() < need) { cudaEvent_t e; CK(cudaEventCreate(&e)); c->ev.push_back(e); }
     const int none[2] = {0, 0}, both[2] = {1, c->n_part > 1 ? 1 : 0};
     int rc, cur = 0, nxt = 1;
+    if (persistent_ok(c) && !per_kernel) {
+        // one series_init + one cooperative launch per 24-term series
+        CK(cudaEventRecord(c->ev[0], c->stream));
+        for (int s0 = 0; s0 < n_terms; s0 += ORDER - 1) {
+            const int len = std::min(ORDER - 1, n_terms - s0);
+            if ((rc = launch_series_init(c, none, both, 0))) return rc;
+            std::vector<PassParams> passes(len);
+            for (int s = 0; s < len; ++s) {
+                memset(&passes[s], 0, sizeof(PassParams));
+                const int k = 2 + s;
+                const cplx r = C[k - 1] / C[k - 2];
+                for (int p = 0; p < 2; ++p) {
+                    PartPass& a = passes[s].part[p];
+                    a.active = both[p]; a.k = k; a.alpha_re = r.real(); a.alpha_im = r.imag(); a.norm_ref = 1.0;
+                }
+            }
+            if ((rc = run_series_persistent(c, passes))) return rc;
+        }
+        CK(cudaEventRecord(c->ev[1], c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->passes_last = n_terms;
+        if (elapsed_ms) CK(cudaEventElapsedTime(elapsed_ms, c->ev[0], c->ev[1]));
+        return DYB_OK;
+    }
     CK(cudaEventRecord(c->ev[0], c->stream));
     for (int s = 0; s < n_terms; ++s) {
         const int k = 2 + (s % (ORDER - 1));                      // repeated 24-term series, like Convergence calls

@@ -132,6 +132,9 @@ int  dyb_plan(int N, int n_rows, int sm_count, int64_t* out8, int32_t* seg_base,
 int  dyb_create(dyb_ctx** out, int device, int N, int row0, int n_rows);
 int  dyb_destroy(dyb_ctx* ctx);
 int  dyb_set_kernel(dyb_ctx* ctx, int kernel_variant);
+/* one cooperative launch per series (all terms and their epilogues in one persistent kernel) instead of two launches
+ * per term; single GPU, TMA variant, operators with at least 3 tiles per CTA */
+int  dyb_set_persistent(dyb_ctx* ctx, int on);
 int  dyb_get_info(dyb_ctx* ctx, int64_t* info16);   /* [0]=N [1]=ld [2]=n_rows [3]=grid [4]=tiles [5]=segments [6]=sm_count [7]=smem_bytes [8]=variant */
 
 /* Operator: either upload H' (host, lda >= N; only rows row0..row0+n_rows-1 are kept),
