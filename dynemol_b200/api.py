@@ -75,7 +75,7 @@ lib = _load()
 DECLARED_SYMBOLS = [
     "propagationelhl_gpucaller_", "propagationelhl2_gpucaller_", "propagation_gpucaller_", "nakedbessel_", "ehrenfestkernel_gpu_",
     "gpu_init_", "gpu_finalize_", "gpu_pin_", "gpu_unpin_",
-    "dyb_last_error", "dyb_version", "dyb_device_count", "dyb_plan", "dyb_create", "dyb_destroy", "dyb_set_kernel", "dyb_set_persistent",
+    "dyb_last_error", "dyb_version", "dyb_device_count", "dyb_plan", "dyb_create", "dyb_destroy", "dyb_set_kernel", "dyb_set_series_kernel",
     "dyb_get_info", "dyb_upload_hprime", "dyb_upload_hprime_device", "dyb_upload_hprime_rows_device", "dyb_hprime_device", "dyb_form_hprime", "dyb_form_hprime_device", "dyb_form_hprime_from_overlap",
     "dyb_download_hprime", "dyb_set_packets", "dyb_get_packets", "dyb_propagate", "dyb_ao_bra",
     "dyb_populations", "dyb_run_terms", "dyb_dual_matvec", "dyb_sync", "dyb_launch_count",
@@ -149,13 +149,15 @@ class Propagator:
     def set_kernel(self, kernel: int):
         _check(lib.dyb_set_kernel(self._h, C.c_int(kernel)))
 
-    def set_persistent(self, on: bool):
-        _check(lib.dyb_set_persistent(self._h, C.c_int(1 if on else 0)))
+    def set_series_kernel(self, kind):
+        """kind: 'auto' | 'term' | 'stream' | 'resident' (include/dynemol_b200.h: DYB_SERIES_*)."""
+        code = {"auto": 0, "term": 1, "stream": 2, "resident": 3}[kind] if isinstance(kind, str) else int(kind)
+        _check(lib.dyb_set_series_kernel(self._h, C.c_int(code)))
 
     def info(self) -> dict:
         buf = (C.c_int64 * 16)()
         _check(lib.dyb_get_info(self._h, buf))
-        keys = ["N", "ld", "n_rows", "grid", "tiles", "segments", "sm_count", "smem_bytes", "variant", "panels", "tiles_per_panel", "passes_last", "p2p", "persistent"]
+        keys = ["N", "ld", "n_rows", "grid", "tiles", "segments", "sm_count", "smem_bytes", "variant", "panels", "tiles_per_panel", "passes_last", "p2p", "series_kernel", "resident_grid_side", "resident_block"]
         return {k: int(buf[i]) for i, k in enumerate(keys)}
 
     # ---- operator

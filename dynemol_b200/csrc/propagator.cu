@@ -26,6 +26,7 @@
 #include "matvec.cuh"
 #include "epilogue.cuh"
 #include "series.cuh"
+#include "resident.cuh"
 
 using namespace dyb;
 typedef std::complex<double> cplx;
@@ -89,7 +90,10 @@ struct dyb_ctx {
     size_t Lq = 0;                       // quad vector length (indices)
     int variant = DYB_KERNEL_TMA;
     bool use_pdl = true;                 // programmatic dependent launch between the dual product and the epilogue
-    bool persistent = false;             // one cooperative launch per series (series.cuh) instead of two launches per term
+    int series_kind = DYB_SERIES_AUTO;   // how a series is launched: per term, streaming cooperative kernel, smem-resident kernel
+    int res_Gd = 0, res_Bs = 0, res_ldS = 0;     // resident.cuh: grid side, block size, smem column stride (0: does not fit)
+    size_t res_smem = 0;
+    double *res_pk = nullptr, *res_pb = nullptr, *res_dscal = nullptr;
     PassParams* d_passes = nullptr;      // per-term parameters of the series in flight
     unsigned long long* gbar = nullptr;  // grid barrier counter
     cudaStream_t stream = nullptr;
@@ -334,7 +338,11 @@ static int run_term(dyb_ctx* c, const EpiParams& E, int cur, int nxt, bool use_c
 
 // Whole series in one cooperative launch (series.cuh).  Usable when every CTA owns at least TMA_STAGES tiles.
 static bool persistent_ok(const dyb_ctx* c) {
-    return c->persistent && c->world == 1 && c->variant == DYB_KERNEL_TMA && c->T >= TMA_STAGES * c->grid;
+    return c->series_kind == DYB_SERIES_STREAM && c->world == 1 && c->variant == DYB_KERNEL_TMA && c->T >= TMA_STAGES * c->grid;
+}
+// Operator resident in shared memory for the whole series (resident.cuh): small N only, single GPU.
+static bool resident_ok(const dyb_ctx* c) {
+    return (c->series_kind == DYB_SERIES_RESIDENT || c->series_kind == DYB_SERIES_AUTO) && c->world == 1 && c->res_Gd > 0;
 }
 constexpr int MAX_SERIES_TERMS = 32;
 
@@ -350,10 +358,62 @@ static int run_series_persistent(dyb_ctx* c, const std::vector<PassParams>& pass
     for (int i = 0; i < 3; ++i) { S.vb[i] = c->vb[i]; S.vk[i] = c->vk[i]; }
     S.sum_b = c->sum_b; S.sum_k = c->sum_k; S.blockpart = c->blockpart; S.ctrl = c->ctrl;
     S.passes = c->d_passes; S.n_steps = n; S.gbar = c->gbar;
+#ifdef DYB_SERIES_PROF
+    static long long* d_prof = nullptr;
+    const size_t n_prof = (size_t)MAX_SERIES_TERMS * c->grid * 6;
+    if (!d_prof) CK(cudaMalloc(&d_prof, n_prof * 8));
+    CK(cudaMemsetAsync(d_prof, 0, n_prof * 8, c->stream));
+    S.prof = d_prof;
+#endif
     void* args[] = {(void*)&c->tmap, (void*)&S};
     CK(cudaLaunchCooperativeKernel((const void*)series_kernel, dim3(c->grid), dim3(TMA_THREADS), args, TmaSmem::total, c->stream));
     c->launches++;
+#ifdef DYB_SERIES_PROF
+    {   // diagnostic build: mean / max cycles of each phase over CTAs and terms (first call of every 50 only)
+        static int calls = 0;
+        if (calls++ % 50 == 1) {
+            std::vector<long long> h(n_prof);
+            CK(cudaStreamSynchronize(c->stream));
+            CK(cudaMemcpy(h.data(), d_prof, n_prof * 8, cudaMemcpyDeviceToHost));
+            const char* name[6] = {"tiles", "barrierA", "epilogue", "barrierB", "decision", "next-term-x+gap"};
+            double mean[6] = {0}, mx[6] = {0};
+            for (int t = 0; t < n; ++t) for (int b = 0; b < c->grid; ++b) {
+                const long long* q = &h[((size_t)t * c->grid + b) * 6];
+                for (int i = 0; i < 6; ++i) {
+                    const long long nxt = (i < 5) ? q[i + 1] : ((t + 1 < n) ? h[((size_t)(t + 1) * c->grid + b) * 6] : q[5]);
+                    const double d = double(nxt - q[i]);
+                    mean[i] += d; mx[i] = std::max(mx[i], d);
+                }
+            }
+            fprintf(stderr, "series_prof N=%d grid=%d terms=%d:", c->N, c->grid, n);
+            for (int i = 0; i < 6; ++i) fprintf(stderr, "  %s mean %.0f max %.0f cyc;", name[i], mean[i] / ((double)n * c->grid), mx[i]);
+            fprintf(stderr, "\n");
+        }
+    }
+#endif
     return DYB_OK;
+}
+
+static int run_series_resident(dyb_ctx* c, const std::vector<PassParams>& passes) {
+    const int n = (int)passes.size();
+    if (n < 1 || n > MAX_SERIES_TERMS) return fail(DYB_EINVAL, "series length %d out of range", n);
+    CK(cudaMemcpyAsync(c->d_passes, passes.data(), sizeof(PassParams) * n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->gbar, 0, sizeof(unsigned long long), c->stream));
+    ResidentParams R;
+    memset(&R, 0, sizeof R);
+    R.H = c->H; R.ld = c->ld; R.N = c->N; R.Gd = c->res_Gd; R.Bs = c->res_Bs; R.ldS = c->res_ldS;
+    R.x0k = c->vk[0]; R.x0b = c->vb[0]; R.sum_b = c->sum_b; R.sum_k = c->sum_k;
+    R.pk = c->res_pk; R.pb = c->res_pb; R.dscal = c->res_dscal;
+    R.ctrl = c->ctrl; R.passes = c->d_passes; R.n_steps = n; R.gbar = c->gbar;
+    void* args[] = {(void*)&R};
+    CK(cudaLaunchCooperativeKernel((const void*)resident_series_kernel, dim3(c->res_Gd * c->res_Gd), dim3(RES_THREADS), args, c->res_smem, c->stream));
+    c->launches++;
+    return DYB_OK;
+}
+
+// One series through whichever single-launch kernel applies (the caller checked resident_ok / persistent_ok).
+static int run_series_single_launch(dyb_ctx* c, const std::vector<PassParams>& passes) {
+    return resident_ok(c) ? run_series_resident(c, passes) : run_series_persistent(c, passes);
 }
 
 static int launch_series_init(dyb_ctx* c, const int adopt[2], const int active[2], int cur, const cplx* sum_scale = nullptr) {
@@ -513,14 +573,14 @@ static int propagate_series(dyb_ctx* c, int mode, double t_init, double t_max, c
         int prv = 2, cur = 0, nxt = 1;
         if ((rc = launch_series_init(c, adopt, active, cur, mode == DYB_MODE_TAYLOR ? nullptr : sum_scale))) return rc;
         adopt[0] = adopt[1] = 0;
-        if (persistent_ok(c) && L <= MAX_SERIES_TERMS) {
+        if ((resident_ok(c) || persistent_ok(c)) && L <= MAX_SERIES_TERMS) {
             std::vector<PassParams> passes(L);
             for (int s = 0; s < L; ++s) {
                 memset(&passes[s], 0, sizeof(PassParams));
                 for (int p = 0; p < 2; ++p)
                     if (active[p] && s < P[p].n_terms) fill_pass(passes[s].part[p], P[p], mode, s, ebar, de);
             }
-            if ((rc = run_series_persistent(c, passes))) return rc;
+            if ((rc = run_series_single_launch(c, passes))) return rc;
         } else
         for (int s = 0; s < L; ++s) {
             EpiParams E = epi_params(c, cur, prv, nxt);
@@ -642,6 +702,9 @@ int dyb_destroy(dyb_ctx* c) {
     if (c->ctrl) cudaFree(c->ctrl);
     if (c->d_passes) cudaFree(c->d_passes);
     if (c->gbar) cudaFree(c->gbar);
+    if (c->res_pk) cudaFree(c->res_pk);
+    if (c->res_pb) cudaFree(c->res_pb);
+    if (c->res_dscal) cudaFree(c->res_dscal);
     if (c->h_ctrl) cudaFreeHost(c->h_ctrl);
     if (c->h_scal) cudaFreeHost(c->h_scal);
     for (auto e : c->ev) cudaEventDestroy(e);
@@ -691,7 +754,27 @@ int dyb_create(dyb_ctx** out, int device, int N, int row0, int n_rows) {
     CKCU(cudaFuncSetAttribute(series_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TmaSmem::total));
     CKCU(cudaMalloc(&c->d_passes, sizeof(PassParams) * MAX_SERIES_TERMS));
     CKCU(cudaMalloc(&c->gbar, sizeof(unsigned long long)));
-    if (const char* e = getenv("DYNEMOL_B200_PERSISTENT")) c->persistent = (e[0] != '0');
+    if (row0 == 0 && n_rows == N) {    // resident.cuh: does a Gd x Gd blocking of H' fit the shared memories?
+        int smem_optin = 0;
+        CKCU(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        cudaFuncAttributes fa;
+        CKCU(cudaFuncGetAttributes(&fa, resident_series_kernel));
+        int gd_max = 1;
+        while ((gd_max + 1) * (gd_max + 1) <= c->sm_count && gd_max + 1 <= RES_MAX_GD) ++gd_max;     // 12 on 148 SMs
+        const int Gd = std::min(gd_max, std::max(1, (N + 31) / 32));                                  // blocks of >= 32 rows
+        const int Bs = (N + Gd - 1) / Gd, ldS = Bs | 1;
+        const ResidentSmem L(Bs, ldS);
+        if (Bs <= RES_MAX_BS && L.bytes() + fa.sharedSizeBytes <= (size_t)smem_optin) {
+            c->res_Gd = Gd; c->res_Bs = Bs; c->res_ldS = ldS; c->res_smem = L.bytes();
+            CKCU(cudaFuncSetAttribute(resident_series_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RES_SMEM_MAX));
+            CKC(alloc_zero(&c->res_pk, (size_t)2 * Gd * Gd * Bs * NQ)); CKC(alloc_zero(&c->res_pb, (size_t)2 * Gd * Gd * Bs * NQ));
+            CKC(alloc_zero(&c->res_dscal, (size_t)2 * Gd * 8));
+        }
+    }
+    if (const char* e = getenv("DYNEMOL_B200_SERIES")) {
+        c->series_kind = !strcmp(e, "term") ? DYB_SERIES_PER_TERM : !strcmp(e, "stream") ? DYB_SERIES_STREAM
+                       : !strcmp(e, "resident") ? DYB_SERIES_RESIDENT : DYB_SERIES_AUTO;
+    }
     CKCU(cudaDeviceSynchronize());     // the zero fills above ran on the legacy stream; c->stream is non-blocking
 #undef CKC
 #undef CKCU
@@ -708,9 +791,10 @@ int dyb_set_kernel(dyb_ctx* c, int v) {
     return DYB_OK;
 }
 
-int dyb_set_persistent(dyb_ctx* c, int on) {
+int dyb_set_series_kernel(dyb_ctx* c, int kind) {
     if (!c) return fail(DYB_EINVAL, "ctx is NULL");
-    c->persistent = on != 0;
+    if (kind < DYB_SERIES_AUTO || kind > DYB_SERIES_RESIDENT) return fail(DYB_EINVAL, "unknown series kernel %d", kind);
+    c->series_kind = kind;
     return DYB_OK;
 }
 
@@ -719,7 +803,8 @@ int dyb_get_info(dyb_ctx* c, int64_t* o) {
     memset(o, 0, 16 * sizeof(int64_t));
     o[0] = c->N; o[1] = c->ld; o[2] = c->M; o[3] = c->grid; o[4] = c->T; o[5] = c->n_seg; o[6] = c->sm_count;
     o[7] = TmaSmem::total; o[8] = c->variant; o[9] = c->NP; o[10] = c->TPP; o[11] = c->passes_last; o[12] = c->p2p ? 1 : 0;
-    o[13] = persistent_ok(c) ? 1 : 0;
+    o[13] = resident_ok(c) ? DYB_SERIES_RESIDENT : persistent_ok(c) ? DYB_SERIES_STREAM : DYB_SERIES_PER_TERM;
+    o[14] = c->res_Gd; o[15] = c->res_Bs;
     return DYB_OK;
 }
 
@@ -1080,7 +1165,7 @@ int dyb_run_terms(dyb_ctx* c, double tau, int n_terms, float* elapsed_ms, float*
     while (c->ev.size() < need) { cudaEvent_t e; CK(cudaEventCreate(&e)); c->ev.push_back(e); }
     const int none[2] = {0, 0}, both[2] = {1, c->n_part > 1 ? 1 : 0};
     int rc, cur = 0, nxt = 1;
-    if (persistent_ok(c) && !per_kernel) {
+    if ((resident_ok(c) || persistent_ok(c)) && !per_kernel) {
         // one series_init + one cooperative launch per 24-term series
         CK(cudaEventRecord(c->ev[0], c->stream));
         for (int s0 = 0; s0 < n_terms; s0 += ORDER - 1) {
@@ -1096,7 +1181,7 @@ int dyb_run_terms(dyb_ctx* c, double tau, int n_terms, float* elapsed_ms, float*
                     a.active = both[p]; a.k = k; a.alpha_re = r.real(); a.alpha_im = r.imag(); a.norm_ref = 1.0;
                 }
             }
-            if ((rc = run_series_persistent(c, passes))) return rc;
+            if ((rc = run_series_single_launch(c, passes))) return rc;
         }
         CK(cudaEventRecord(c->ev[1], c->stream));
         CK(cudaStreamSynchronize(c->stream));

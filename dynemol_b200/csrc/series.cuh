@@ -19,6 +19,12 @@
 
 namespace dyb {
 
+#ifdef DYB_SERIES_PROF
+#define DYB_STAMP(i) do { if (threadIdx.x == 0) S.prof[((size_t)t * G + b) * 6 + (i)] = clock64(); } while (0)
+#else
+#define DYB_STAMP(i) do { } while (0)
+#endif
+
 struct SeriesParams {
     MatvecParams mv;                 // H', plan, slabs (Xk/Xb/ctrl members unused here)
     int row0, n_bra_slabs;           // epilogue: owned rows start at global index row0 (single GPU: 0)
@@ -30,6 +36,7 @@ struct SeriesParams {
     const PassParams* passes;        // [n_steps] per-term parameters (device memory)
     int n_steps;
     unsigned long long* gbar;        // grid barrier counter, zeroed by the host before the launch
+    long long* prof;                 // DYB_SERIES_PROF builds: [n_steps][grid][6] clock64 stamps of the phases (else null)
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
@@ -160,6 +167,7 @@ series_kernel(const __grid_constant__ CUtensorMap tmap, const SeriesParams S)
     __shared__ Ctrl   sctrl;                           // every CTA keeps (and updates identically) its own copy
     __shared__ double wpart[TMA_THREADS / 32][8];
     __shared__ double fin[8];
+    __shared__ PassParams spass;                       // this term's parameters (read by the epilogue and the decision)
 
     const MatvecParams& P = S.mv;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -191,6 +199,8 @@ series_kernel(const __grid_constant__ CUtensorMap tmap, const SeriesParams S)
     for (int t = 0; t < S.n_steps; ++t) {
         if (sctrl.all_latched) break;                  // uniform over the grid: every CTA holds the same sctrl
         const bool more = (t + 1 < S.n_steps);
+        if (threadIdx.x < sizeof(PassParams) / 8)        // visible to the CTA after the __syncthreads of barrier A
+            reinterpret_cast<double*>(&spass)[threadIdx.x] = reinterpret_cast<const double*>(S.passes + t)[threadIdx.x];
         const double* xk_cur = pick3(S.vk, cur);
         const double* xb_cur = pick3(S.vb, cur);
 
@@ -202,6 +212,7 @@ series_kernel(const __grid_constant__ CUtensorMap tmap, const SeriesParams S)
             for (int i = 0; i < TMA_STAGES; ++i) { issue_tile_x(smem, bar_full, xk_cur, slot, tc); tc.next(P.TPP); if (++slot == TMA_STAGES) slot = 0; }
         }
 
+        DYB_STAMP(0);
         // ---------------------------------------------------------------- dual product over this CTA's tiles
         ConsumerRegs r;
         zero_acc(r);
@@ -265,31 +276,53 @@ series_kernel(const __grid_constant__ CUtensorMap tmap, const SeriesParams S)
             }
         }
 
+        DYB_STAMP(1);
         bar_target += G;
         grid_barrier(S.gbar, bar_target);              // A: every slab of this term is complete
 
+        DYB_STAMP(2);
         // ---------------------------------------------------------------- epilogue on rows r0..r1-1 of this CTA
-        const PassParams pass = S.passes[t];
-        epilogue_phase(S, pass, sctrl, r0, r1, prv, cur, nxt, wpart);
+        epilogue_phase(S, spass, sctrl, r0, r1, prv, cur, nxt, wpart);
 
+        DYB_STAMP(3);
         bar_target += G;
         grid_barrier(S.gbar, bar_target);              // B: new vectors and every CTA's scalars are visible
 
+        DYB_STAMP(4);
         // ---------------------------------------------------------------- replicated decision (same inputs, same order)
-        if (threadIdx.x < 8) {
-            const int q = threadIdx.x;
-            double v = __ldcg(S.blockpart + q);
-            for (int bb = 1; bb < G; ++bb) { const double x = __ldcg(S.blockpart + (size_t)bb * 8 + q); v = ((q & 3) < 2) ? fmax(v, x) : v + x; }
-            fin[q] = v;
+        {   // 256 threads: q = tid & 7, CTAs tid>>3, +32, ... (independent loads), then a fixed tree: same result in every CTA
+            const int q = threadIdx.x & 7;
+            const bool is_max = (q & 3) < 2;
+            double v = 0.0;                              // maxima are of non-negative numbers: 0 is neutral for both
+            for (int b0 = threadIdx.x >> 3; b0 < G; b0 += 128) {
+                double x[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) x[u] = (b0 + 32 * u < G) ? __ldcg(S.blockpart + (size_t)(b0 + 32 * u) * 8 + q) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v = is_max ? fmax(v, x[u]) : v + x[u];
+            }
+#pragma unroll
+            for (int off = 8; off < 32; off <<= 1) {
+                const double o = __shfl_xor_sync(0xffffffffu, v, off);
+                v = is_max ? fmax(v, o) : v + o;
+            }
+            if (lane < 8) wpart[w][lane] = v;
+            __syncthreads();
+            if (threadIdx.x < 8) {
+                double f = wpart[0][q];
+                for (int w2 = 1; w2 < TMA_THREADS / 32; ++w2) f = is_max ? fmax(f, wpart[w2][q]) : f + wpart[w2][q];
+                fin[q] = f;
+            }
         }
         __syncthreads();
         if (threadIdx.x == 0) {
             unsigned dummy = sctrl.block_counter;
-            apply_decision(&sctrl, pass, fin);
+            apply_decision(&sctrl, spass, fin);
             sctrl.block_counter = dummy;
         }
         __syncthreads();
         const int old_prv = prv; prv = cur; cur = nxt; nxt = old_prv;
+        DYB_STAMP(5);
 
         if (more && sctrl.all_latched) {
             // the series is decided but the next term's H' tiles are in flight: complete them (their barriers expect

@@ -132,10 +132,18 @@ int  dyb_plan(int N, int n_rows, int sm_count, int64_t* out8, int32_t* seg_base,
 int  dyb_create(dyb_ctx** out, int device, int N, int row0, int n_rows);
 int  dyb_destroy(dyb_ctx* ctx);
 int  dyb_set_kernel(dyb_ctx* ctx, int kernel_variant);
-/* one cooperative launch per series (all terms and their epilogues in one persistent kernel) instead of two launches
- * per term; single GPU, TMA variant, operators with at least 3 tiles per CTA */
-int  dyb_set_persistent(dyb_ctx* ctx, int on);
-int  dyb_get_info(dyb_ctx* ctx, int64_t* info16);   /* [0]=N [1]=ld [2]=n_rows [3]=grid [4]=tiles [5]=segments [6]=sm_count [7]=smem_bytes [8]=variant */
+/* How the terms of one series (one Convergence() call / one steady sub-step of Taylor.f:81-126) are launched:
+ *   PER_TERM  two launches per term (dual product + fused epilogue, chained by programmatic dependent launch);
+ *   STREAM    one cooperative launch per series, H' streamed by TMA every term (single GPU, >= 3 tiles per CTA);
+ *   RESIDENT  one cooperative launch per series, H' blocked over the shared memories of the SMs for the whole
+ *             series (single GPU, N <= ~1800: the QM regions of the Ehrenfest / CSDM examples);
+ *   AUTO      RESIDENT when the operator fits, else PER_TERM (default; env DYNEMOL_B200_SERIES=term|stream|resident|auto). */
+#define DYB_SERIES_AUTO     0
+#define DYB_SERIES_PER_TERM 1
+#define DYB_SERIES_STREAM   2
+#define DYB_SERIES_RESIDENT 3
+int  dyb_set_series_kernel(dyb_ctx* ctx, int kind);
+int  dyb_get_info(dyb_ctx* ctx, int64_t* info16);   /* [0]=N [1]=ld [2]=n_rows [3]=grid [4]=tiles [5]=segments [6]=sm_count [7]=smem_bytes [8]=variant ... [13]=series kernel in effect [14]=resident grid side [15]=resident block size */
 
 /* Operator: either upload H' (host, lda >= N; only rows row0..row0+n_rows-1 are kept),
  * or write it directly into the device buffer (bench: synthetic H' generated on the

@@ -1,0 +1,13 @@
+#!/bin/bash
+# Shared-memory-resident series kernel (small N): parity under the default (auto) selection, then A/B against launch-per-term.
+mkdir -p gpurun_out
+timeout 400 python -m pytest tests/test_gpu_parity.py tests/test_gpu_chebyshev.py tests/test_gpu_poststep.py tests/test_gpu_driver.py -x -q -m gpu --durations=5 2>&1 | tail -15 | tee gpurun_out/resident_tests.log
+for kind in term auto; do
+  export DYNEMOL_B200_SERIES=$kind
+  for n in ${SIZES:-128 512 900 1792}; do
+    timeout 200 python bench.py --basis $n --steps 100 --warmup 5 --skip-cpu --skip-65k --skip-e2e 2>&1 | tail -1 | python -c "
+import json,sys,os
+d=json.loads(sys.stdin.read())
+print('series',os.environ['DYNEMOL_B200_SERIES'],'N',d['config']['basis'],'us/term',round(1e3*d['ms_per_step']/24,2),'value',round(d['value'],1),'launches',d['gpu_launches'])" 2>&1 | tee -a gpurun_out/resident_ab.log
+  done
+done
