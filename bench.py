@@ -218,6 +218,10 @@ def run_ours_single(args):
             host_Sh = None
     cpu = None if args.skip_cpu else cpu_baseline(np.asfortranarray(P.download_hprime()), Psi_bra, Psi_ket, tau, budget_s=args.cpu_budget)
 
+    small = None
+    if N == 16384 and not args.skip_small:
+        small = small_operator(args)
+
     n65536 = None
     if N == 16384 and not args.skip_65k:
         n65536 = single_gpu_65536(P, args)
@@ -229,8 +233,32 @@ def run_ours_single(args):
                        "terms_per_step": TERMS_PER_STEP, "l2": "inputs larger than L2 (H' = %.2f GB per pass)" % (alg_bytes / 1e9),
                        "kernel_variant": args.kernel, "grid": info["grid"], "tiles": info["tiles"], "build": build_info},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "n65536_single_gpu": n65536}
+            "n65536_single_gpu": n65536, "small_operator": small}
     print(json.dumps(line))
+
+
+def small_operator(args, N=900):
+    """Side measurement at the QM-region size of BASELINE config 2 (heptazine + water droplet, N ~ 900):
+    the same 24-term series through the launch-per-term path and through the shared-memory-resident series kernel
+    (csrc/resident.cuh), which is what the library selects by itself at this size."""
+    import torch
+    try:
+        P, bra, ket, _, _ = build_single_gpu(N)
+        P.set_packets(bra, ket)
+        tau = pick_tau(N)
+        out = {"basis": N, "unit": UNIT, "steps": 200}
+        for kind in ("term", "auto"):
+            P.set_series_kernel(kind)
+            for _ in range(5):
+                P.run_terms(tau, TERMS_PER_STEP)
+            ms, _ = P.run_terms(tau, TERMS_PER_STEP * 200)
+            key = "per_term" if kind == "term" else ("resident" if P.info()["series_kernel"] == 3 else "auto")
+            out[key] = {"value": round(TERMS_PER_STEP * 200 / (ms * 1e-3), 1), "us_per_term": round(ms * 1e3 / (TERMS_PER_STEP * 200), 2)}
+        P.close()
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:      # the headline line must survive a failure of the side measurement
+        return {"error": repr(e)[:200]}
 
 
 def single_gpu_65536(P_small, args):
@@ -389,6 +417,7 @@ def main():
     ap.add_argument("--ref-terms-per-step", type=int, default=2)
     ap.add_argument("--kernel", default="tma", choices=["tma", "ldg"])
     ap.add_argument("--no-ref1", action="store_true", help="multi-GPU: skip the 1-GPU same-workload reference on rank 0")
+    ap.add_argument("--skip-small", action="store_true", help="N=1: skip the N=900 small-operator side measurement")
     ap.add_argument("--skip-65k", action="store_true", help="N=1: skip the N=65536 single-GPU side measurement")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: no CPU baseline leg")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: no end-to-end leg")

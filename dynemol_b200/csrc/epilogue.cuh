@@ -63,24 +63,23 @@ __device__ __forceinline__ Cx reduce_bra(const EpiParams& E, int i, int pp) {
 
 // The per-term decision the reference takes on the host (Taylor.f:194-207 inside Convergence, :102-105 in
 // the steady loop), from the 8 reduced scalars v = {max_b, max_k, dot_re, dot_im} x {el, hl}.
-__device__ __forceinline__ void apply_decision(Ctrl* c, const PassParams& pass, const double* v) {
-    for (int p = 0; p < 2; ++p) {
-        const PartPass q = pass.part[p];
-        PartState& st = c->part[p];
-        if (!q.active || st.latched) continue;
-        st.n_terms += 1;
-        st.max_b = v[p * 4 + 0]; st.max_k = v[p * 4 + 1];
-        st.dot_re = v[p * 4 + 2]; st.dot_im = v[p * 4 + 3];
-        st.norm = hypot(st.dot_re, st.dot_im);
-        const bool norm_ok = fabs(st.norm - q.norm_ref) < TOL_NORM;                    // Taylor.f:104,199
-        if (q.check_conv) {
-            const bool conv = !(st.max_b > TOL_TERM) && !(st.max_k > TOL_TERM);        // Taylor.f:194-195
-            if (conv && norm_ok) { st.latched = 1; st.ok = 1; st.k_exit = q.k; }
-            else if (q.last)     { st.latched = 1; st.ok = 0; st.k_exit = 0; }
-        } else if (q.last) {
-            st.latched = 1; st.ok = (q.last_ok_by_norm ? (norm_ok ? 1 : 0) : 1); st.k_exit = q.k;
-        }
+__device__ __forceinline__ void decide_particle(PartState& st, const PartPass& q, const double* v4) {
+    if (!q.active || st.latched) return;
+    st.n_terms += 1;
+    st.max_b = v4[0]; st.max_k = v4[1];
+    st.dot_re = v4[2]; st.dot_im = v4[3];
+    st.norm = hypot(st.dot_re, st.dot_im);
+    const bool norm_ok = fabs(st.norm - q.norm_ref) < TOL_NORM;                        // Taylor.f:104,199
+    if (q.check_conv) {
+        const bool conv = !(st.max_b > TOL_TERM) && !(st.max_k > TOL_TERM);            // Taylor.f:194-195
+        if (conv && norm_ok) { st.latched = 1; st.ok = 1; st.k_exit = q.k; }
+        else if (q.last)     { st.latched = 1; st.ok = 0; st.k_exit = 0; }
+    } else if (q.last) {
+        st.latched = 1; st.ok = (q.last_ok_by_norm ? (norm_ok ? 1 : 0) : 1); st.k_exit = q.k;
     }
+}
+__device__ __forceinline__ void apply_decision(Ctrl* c, const PassParams& pass, const double* v) {
+    for (int p = 0; p < 2; ++p) decide_particle(c->part[p], pass.part[p], v + 4 * p);
     c->all_latched = (c->part[0].latched && c->part[1].latched) ? 1 : 0;
     c->block_counter = 0u;
     __threadfence();

@@ -405,9 +405,40 @@ static int run_series_resident(dyb_ctx* c, const std::vector<PassParams>& passes
     R.x0k = c->vk[0]; R.x0b = c->vb[0]; R.sum_b = c->sum_b; R.sum_k = c->sum_k;
     R.pk = c->res_pk; R.pb = c->res_pb; R.dscal = c->res_dscal;
     R.ctrl = c->ctrl; R.passes = c->d_passes; R.n_steps = n; R.gbar = c->gbar;
+#ifdef DYB_SERIES_PROF
+    static long long* d_rprof = nullptr;
+    const int rgrid = c->res_Gd * c->res_Gd;
+    const size_t n_rprof = (size_t)MAX_SERIES_TERMS * rgrid * 6;
+    if (!d_rprof) CK(cudaMalloc(&d_rprof, (size_t)MAX_SERIES_TERMS * 512 * 6 * 8));
+    CK(cudaMemsetAsync(d_rprof, 0, n_rprof * 8, c->stream));
+    R.prof = d_rprof;
+#endif
     void* args[] = {(void*)&R};
     CK(cudaLaunchCooperativeKernel((const void*)resident_series_kernel, dim3(c->res_Gd * c->res_Gd), dim3(RES_THREADS), args, c->res_smem, c->stream));
     c->launches++;
+#ifdef DYB_SERIES_PROF
+    {   // diagnostic build: mean / max cycles of each phase over CTAs and terms
+        static int calls = 0;
+        if (calls++ % 50 == 1) {
+            std::vector<long long> h(n_rprof);
+            CK(cudaStreamSynchronize(c->stream));
+            CK(cudaMemcpy(h.data(), d_rprof, n_rprof * 8, cudaMemcpyDeviceToHost));
+            const char* name[6] = {"product", "partial-store", "barrier", "gather+decide", "update+diag", "loop-gap"};
+            double mean[6] = {0}, mx[6] = {0};
+            for (int t = 0; t + 1 < n; ++t) for (int b = 0; b < rgrid; ++b) {
+                const long long* q = &h[((size_t)t * rgrid + b) * 6];
+                for (int i = 0; i < 6; ++i) {
+                    const long long nx = (i < 5) ? q[i + 1] : h[((size_t)(t + 1) * rgrid + b) * 6];
+                    const double d = double(nx - q[i]);
+                    mean[i] += d; mx[i] = std::max(mx[i], d);
+                }
+            }
+            fprintf(stderr, "resident_prof N=%d grid=%d Bs=%d terms=%d:", c->N, rgrid, c->res_Bs, n);
+            for (int i = 0; i < 6; ++i) fprintf(stderr, "  %s mean %.0f max %.0f cyc;", name[i], mean[i] / ((double)(n - 1) * rgrid), mx[i]);
+            fprintf(stderr, "\n");
+        }
+    }
+#endif
     return DYB_OK;
 }
 

@@ -27,10 +27,10 @@
 
 namespace dyb {
 
-constexpr int RES_THREADS = 512;          // threads 0..255: ket side, 256..511: bra side
-constexpr int RES_HALF    = 256;
+constexpr int RES_THREADS = 640;          // threads 0..319: ket side, 320..639: bra side
+constexpr int RES_HALF    = 320;
 constexpr int RES_MAX_BS  = 152;          // 152*153*8 B = 186 KB of H' per CTA
-constexpr int RES_MAX_GD  = 18;          // multiple of the gather batch (6)
+constexpr int RES_MAX_GD  = 12;          // grid side (12 x 12 = 144 CTAs on the 148 SMs of a B200)
 constexpr int RES_SMEM_MAX = 227 * 1024 - 2048;   // dynamic shared memory opt-in (the kernel's static part stays below 2 KB)
 
 struct ResidentParams {
@@ -43,7 +43,14 @@ struct ResidentParams {
     Ctrl* ctrl;
     const PassParams* passes; int n_steps;
     unsigned long long* gbar;             // grid barrier counter (zeroed before the launch)
+    long long* prof;                      // DYB_SERIES_PROF builds: [n_steps][grid][6] clock64 stamps (else null)
 };
+
+#ifdef DYB_SERIES_PROF
+#define DYB_RSTAMP(i) do { if (threadIdx.x == 0) R.prof[((size_t)t * G + blockIdx.x) * 6 + (i)] = clock64(); } while (0)
+#else
+#define DYB_RSTAMP(i) do { } while (0)
+#endif
 
 struct ResidentSmem {                     // dynamic shared memory carve-up (offsets in doubles)
     int hs, xk, xb, part, sq, total;
@@ -51,9 +58,11 @@ struct ResidentSmem {                     // dynamic shared memory carve-up (off
         hs = 0;
         xk = (Bs * ldS + 1) & ~1;         // 16 B alignment for the quads
         xb = xk + Bs * NQ;
-        part = xb + Bs * NQ;              // [2][RES_HALF][NQ] partials of the split inner range
-        sq = part + 2 * RES_HALF * NQ;    // diagonal CTAs: updated sums [2][Bs][NQ] + term magnitudes [2][Bs][2]
-        total = sq + 2 * Bs * NQ + 2 * Bs * 2;
+        part = xb + Bs * NQ;              // [2][NG][Bs][NQ] partials of the NG inner-range groups
+        sq = part;                        // diagonal CTAs: updated sums [2][Bs][NQ] + term magnitudes [2][Bs][2]; shares the
+                                          // space of `part` (dead between the partial store and the next product)
+        const int Bh = (Bs + 1) >> 1, NG = RES_HALF / ((Bh + 31) & ~31);
+        total = part + 2 * NG * Bs * NQ;
     }
     __host__ __device__ size_t bytes() const { return (size_t)total * 8; }
 };
@@ -67,11 +76,11 @@ __device__ __forceinline__ unsigned long long res_ld_acquire_gpu(const unsigned 
 __device__ __forceinline__ void res_grid_barrier(unsigned long long* ctr, unsigned long long target) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(ctr, 1ULL);
+        // release-add orders the CTA's writes (made visible to this thread by the __syncthreads above) before the
+        // arrival; the acquire poll orders the other CTAs' writes before everything after the second __syncthreads
+        asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(ctr) : "memory");
         for (long long it = 0; res_ld_acquire_gpu(ctr) < target; ++it)
             if (it > (1ll << 26)) __trap();
-        __threadfence();
     }
     __syncthreads();
 }
@@ -82,7 +91,6 @@ resident_series_kernel(const ResidentParams R)
     extern __shared__ __align__(16) double rsm[];
     const ResidentSmem L(R.Bs, R.ldS);
     double* Hs = rsm + L.hs;
-    double* xs[2] = {rsm + L.xk, rsm + L.xb};
     double* part = rsm + L.part;
     double* sq = rsm + L.sq;
     double* mq = sq + 2 * R.Bs * NQ;
@@ -96,227 +104,225 @@ resident_series_kernel(const ResidentParams R)
     const int bi = blockIdx.x / Gd, bj = blockIdx.x % Gd;       // block row, block column
     const int G = Gd * Gd;
     const bool diag = (bi == bj);
-    const int side = tid >> 8, tl = tid & (RES_HALF - 1);       // 0: ket (rows of block bi / entries of block bj), 1: bra
+    const int side = tid / RES_HALF, tl = tid - side * RES_HALF; // 0: ket (rows of block bi / entries of block bj), 1: bra
+    double* const xsd = rsm + (side ? L.xb : L.xk);             // this half's input vector block (quads) in shared memory
 
     // ---- H'(bi, bj) -> shared memory, column-major with an odd column stride (conflict-free from both sides)
     {
         const int r_base = bi * Bs, c_base = bj * Bs;
-        for (int idx = tid; idx < Bs * Bs; idx += RES_THREADS) {
-            const int cl = idx / Bs, rl = idx - cl * Bs;
-            const int r = r_base + rl, c = c_base + cl;
-            Hs[cl * ldS + rl] = (r < N && c < N) ? R.H[(size_t)c * R.ld + r] : 0.0;
+        // a warp per column, lanes along the rows (coalesced), up to 20 independent loads in flight per thread
+#pragma unroll 4
+        for (int cl = tid >> 5; cl < Bs; cl += RES_THREADS / 32) {
+            const int c = c_base + cl;
+            const double* src = R.H + (size_t)c * R.ld + r_base;
+#pragma unroll
+            for (int k = 0; k < (RES_MAX_BS + 31) / 32; ++k) {
+                const int rl = lane + 32 * k;
+                if (rl < Bs) Hs[cl * ldS + rl] = (r_base + rl < N && c < N) ? __ldg(src + rl) : 0.0;
+            }
         }
         if (tid == 0) sctrl = *R.ctrl;
     }
 
-    // ---- epilogue task of this thread: entry n of block (side == 0 ? bj : bi), both particles, state in registers
+    // ---- epilogue task of this thread: particle tp of entry te of block (side == 0 ? bj : bi); state in registers
     const int  tblock = side ? bi : bj;
-    const int  tn = tblock * Bs + tl;                            // global index
-    const bool task = (tl < Bs) && (tn < N);
-    double cur[NQ] = {0.0, 0.0, 0.0, 0.0}, prv[NQ] = {0.0, 0.0, 0.0, 0.0}, sum[NQ] = {0.0, 0.0, 0.0, 0.0};
+    const int  te = tl >> 1, tp = tl & 1;
+    const int  tn = tblock * Bs + te;                            // global index
+    const bool slot = (te < Bs);                                 // owns a (possibly padding) entry of the block
+    const bool task = slot && (tn < N);
+    double2 cur = make_double2(0.0, 0.0), prv = make_double2(0.0, 0.0), sum = make_double2(0.0, 0.0);
     if (task) {
-        const double2* x0 = reinterpret_cast<const double2*>((side ? R.x0b : R.x0k) + (size_t)tn * NQ);
-        const double2* s0 = reinterpret_cast<const double2*>((side ? R.sum_b : R.sum_k) + (size_t)tn * NQ);
-        const double2 a = x0[0], b = x0[1], c = s0[0], d = s0[1];
-        cur[0] = a.x; cur[1] = a.y; cur[2] = b.x; cur[3] = b.y;
-        sum[0] = c.x; sum[1] = c.y; sum[2] = d.x; sum[3] = d.y;
+        cur = *reinterpret_cast<const double2*>((side ? R.x0b : R.x0k) + (size_t)tn * NQ + 2 * tp);
+        sum = *reinterpret_cast<const double2*>((side ? R.sum_b : R.sum_k) + (size_t)tn * NQ + 2 * tp);
     }
-    if (tl < Bs) {
-        double2* xd = reinterpret_cast<double2*>(xs[side] + tl * NQ);
-        xd[0] = make_double2(cur[0], cur[1]); xd[1] = make_double2(cur[2], cur[3]);
-    }
+    if (slot) *reinterpret_cast<double2*>(xsd + te * NQ + 2 * tp) = cur;
 
-    // ---- product mapping: owner o (row for the ket side, column for the bra side), inner range split in NG groups
-    const int Bo = (Bs + 31) & ~31;
-    const int NG = RES_HALF / Bo;                               // >= 1 because Bs <= 152
+    // ---- product mapping: a thread owns TWO owners oA = o and oB = o + Bh (rows for the ket side, columns for the bra
+    // side) so that every broadcast x quad read from shared memory feeds 8 FMAs; the inner range is split in NG groups
+    const int Bh = (Bs + 1) >> 1;
+    const int Bo = (Bh + 31) & ~31;
+    const int NG = RES_HALF / Bo;                               // >= 3 because Bs <= 152
     const int o = tl % Bo, g = tl / Bo;
-    const bool worker = (g < NG) && (o < Bs);
+    const bool worker = (g < NG) && (o < Bh);
+    const bool validB = (o + Bh < Bs);
     const int i0 = (Bs * g) / NG, i1 = (Bs * (g + 1)) / NG;
     const int so = side ? ldS : 1, si = side ? 1 : ldS;
 
     unsigned long long bar_target = 0;
     bool decided_all = false;
+    double pass_word = 0.0;
+    if (tid < sizeof(PassParams) / 8 && R.n_steps > 0) pass_word = reinterpret_cast<const double*>(R.passes)[tid];
     __syncthreads();
 
     int t = 0;
     for (; t < R.n_steps; ++t) {
-        if (sctrl.all_latched) { decided_all = true; break; }
-        if (tid < sizeof(PassParams) / 8)
-            reinterpret_cast<double*>(&spass[t & 1])[tid] = reinterpret_cast<const double*>(R.passes + t)[tid];
+        if (sctrl.part[0].latched && sctrl.part[1].latched) { decided_all = true; break; }
+        if (tid < sizeof(PassParams) / 8) {                      // this term's parameters were fetched one term ahead
+            reinterpret_cast<double*>(&spass[t & 1])[tid] = pass_word;
+            if (t + 1 < R.n_steps) pass_word = reinterpret_cast<const double*>(R.passes + t + 1)[tid];
+        }
 
+        DYB_RSTAMP(0);
         // ---------------------------------------------------------------- 1. both products of the resident block
-        {
-            double a0[NQ] = {0.0, 0.0, 0.0, 0.0}, a1[NQ] = {0.0, 0.0, 0.0, 0.0};
-            if (worker) {
-                const double* hp = Hs + o * so;
-                const double* xin = xs[side];
-                int i = i0;
-                for (; i + 1 < i1; i += 2) {                     // two independent chains per component
-                    const double h0 = hp[i * si], h1 = hp[(i + 1) * si];
-                    const double2 x0 = *reinterpret_cast<const double2*>(xin + i * NQ), x1 = *reinterpret_cast<const double2*>(xin + i * NQ + 2);
-                    const double2 y0 = *reinterpret_cast<const double2*>(xin + (i + 1) * NQ), y1 = *reinterpret_cast<const double2*>(xin + (i + 1) * NQ + 2);
-                    a0[0] = fma(h0, x0.x, a0[0]); a0[1] = fma(h0, x0.y, a0[1]); a0[2] = fma(h0, x1.x, a0[2]); a0[3] = fma(h0, x1.y, a0[3]);
-                    a1[0] = fma(h1, y0.x, a1[0]); a1[1] = fma(h1, y0.y, a1[1]); a1[2] = fma(h1, y1.x, a1[2]); a1[3] = fma(h1, y1.y, a1[3]);
-                }
-                if (i < i1) {
-                    const double h0 = hp[i * si];
-                    const double2 x0 = *reinterpret_cast<const double2*>(xin + i * NQ), x1 = *reinterpret_cast<const double2*>(xin + i * NQ + 2);
-                    a0[0] = fma(h0, x0.x, a0[0]); a0[1] = fma(h0, x0.y, a0[1]); a0[2] = fma(h0, x1.x, a0[2]); a0[3] = fma(h0, x1.y, a0[3]);
-                }
+        if (worker) {
+            double aA[NQ] = {0.0, 0.0, 0.0, 0.0}, aB[NQ] = {0.0, 0.0, 0.0, 0.0};
+            const double* hA = Hs + o * so;
+            const double* hB = Hs + (validB ? o + Bh : o) * so;
+#pragma unroll 2
+            for (int i = i0; i < i1; ++i) {
+                const double h0 = hA[i * si], h1 = hB[i * si];
+                const double2 x0 = *reinterpret_cast<const double2*>(xsd + i * NQ), x1 = *reinterpret_cast<const double2*>(xsd + i * NQ + 2);
+                aA[0] = fma(h0, x0.x, aA[0]); aA[1] = fma(h0, x0.y, aA[1]); aA[2] = fma(h0, x1.x, aA[2]); aA[3] = fma(h0, x1.y, aA[3]);
+                aB[0] = fma(h1, x0.x, aB[0]); aB[1] = fma(h1, x0.y, aB[1]); aB[2] = fma(h1, x1.x, aB[2]); aB[3] = fma(h1, x1.y, aB[3]);
             }
-            double2* pd = reinterpret_cast<double2*>(part + (size_t)(side * RES_HALF + tl) * NQ);
-            pd[0] = make_double2(a0[0] + a1[0], a0[1] + a1[1]); pd[1] = make_double2(a0[2] + a1[2], a0[3] + a1[3]);
+            double2* pA = reinterpret_cast<double2*>(part + ((size_t)(side * NG + g) * Bs + o) * NQ);
+            pA[0] = make_double2(aA[0], aA[1]); pA[1] = make_double2(aA[2], aA[3]);
+            if (validB) {
+                double2* pB = reinterpret_cast<double2*>(part + ((size_t)(side * NG + g) * Bs + o + Bh) * NQ);
+                pB[0] = make_double2(aB[0], aB[1]); pB[1] = make_double2(aB[2], aB[3]);
+            }
         }
         __syncthreads();
-        if (tl < Bs) {                                           // fixed order over the NG groups
-            double v[NQ] = {0.0, 0.0, 0.0, 0.0};
+        DYB_RSTAMP(1);
+        if (slot) {                                              // fixed order over the NG groups; this thread: one particle
+            double2 v = make_double2(0.0, 0.0);
             for (int gg = 0; gg < NG; ++gg) {
-                const double2* ps = reinterpret_cast<const double2*>(part + (size_t)(side * RES_HALF + gg * Bo + tl) * NQ);
-                const double2 p0 = ps[0], p1 = ps[1];
-                v[0] += p0.x; v[1] += p0.y; v[2] += p1.x; v[3] += p1.y;
+                const double2 p0 = *reinterpret_cast<const double2*>(part + ((size_t)(side * NG + gg) * Bs + te) * NQ + 2 * tp);
+                v.x += p0.x; v.y += p0.y;
             }
-            // ket partial of block row bi from block column bj -> pk[t&1][bj][bi][tl];  bra partial of block column bj
-            // from block row bi -> pb[t&1][bi][bj][tl]
-            double* dst = side ? R.pb + ((((size_t)(t & 1) * Gd + bi) * Gd + bj) * Bs + tl) * NQ
-                               : R.pk + ((((size_t)(t & 1) * Gd + bj) * Gd + bi) * Bs + tl) * NQ;
-            __stcg(reinterpret_cast<double2*>(dst), make_double2(v[0], v[1]));
-            __stcg(reinterpret_cast<double2*>(dst) + 1, make_double2(v[2], v[3]));
+            // ket partial of block row bi from block column bj -> pk[t&1][bj][bi][te];  bra partial of block column bj
+            // from block row bi -> pb[t&1][bi][bj][te]
+            double* dst = side ? R.pb + ((((size_t)(t & 1) * Gd + bi) * Gd + bj) * Bs + te) * NQ
+                               : R.pk + ((((size_t)(t & 1) * Gd + bj) * Gd + bi) * Bs + te) * NQ;
+            __stcg(reinterpret_cast<double2*>(dst + 2 * tp), v);
         }
 
+        DYB_RSTAMP(2);
         // ---------------------------------------------------------------- 2. the one grid barrier of the term
         bar_target += G;
         res_grid_barrier(R.gbar, bar_target);
 
+        DYB_RSTAMP(3);
         // ---------------------------------------------------------------- 3. gather: partial sums for this thread's entry,
-        //                                                                     and (one warp) the scalars of term t-1
-        double hx[NQ] = {0.0, 0.0, 0.0, 0.0};
-        if (task) {
-            // ket entry n of block bj: sum over jj of pk[.][jj][bj][tl];  bra entry n of block bi: sum over ii of pb[.][ii][bi][tl]
-            const double* src = (side ? R.pb : R.pk) + ((((size_t)(t & 1) * Gd) * Gd + tblock) * Bs + tl) * NQ;
-            const size_t stride = (size_t)Gd * Bs * NQ;
+        //                                                                     and (eight threads) the scalars of term t-1
+        double2 hx = make_double2(0.0, 0.0);
+        {
+            // Task threads: ket entry of block bj = sum over jj of pk[.][jj][bj][te]; bra entry of block bi = sum over ii
+            // of pb[.][ii][bi][te].  The last four threads (never a task: Bs <= 152) fetch, the same way, the scalars the
+            // diagonal CTAs left for term t-1: thread j takes components 2j, 2j+1 = a pair of maxima or a pair of sums.
+            const bool scal = (t > 0) && (tid >= RES_THREADS - 4);
+            const int  j2 = 2 * (tid - (RES_THREADS - 4));
+            const double* src = scal ? R.dscal + (size_t)((t + 1) & 1) * Gd * 8 + j2
+                                     : (side ? R.pb : R.pk) + ((((size_t)(t & 1) * Gd) * Gd + tblock) * Bs + te) * NQ + 2 * tp;
+            const size_t stride = scal ? (size_t)8 : (size_t)Gd * Bs * NQ;
+            if (task || scal) {
+                double2 v[RES_MAX_GD];                           // all Gd values in flight at once: one L2 round trip
 #pragma unroll
-            for (int u0 = 0; u0 < RES_MAX_GD; u0 += 6) {          // batches of 6 independent loads (register budget: 128)
-                if (u0 >= Gd) break;
-                double2 v0[6], v1[6];
+                for (int u = 0; u < RES_MAX_GD; ++u) if (u < Gd) v[u] = __ldcg(reinterpret_cast<const double2*>(src + u * stride));
+                if (scal && (j2 & 2) == 0) {                     // maxima (of non-negative numbers)
 #pragma unroll
-                for (int u = 0; u < 6; ++u)
-                    if (u0 + u < Gd) { v0[u] = __ldcg(reinterpret_cast<const double2*>(src + (u0 + u) * stride)); v1[u] = __ldcg(reinterpret_cast<const double2*>(src + (u0 + u) * stride) + 1); }
+                    for (int u = 0; u < RES_MAX_GD; ++u) if (u < Gd) { hx.x = fmax(hx.x, v[u].x); hx.y = fmax(hx.y, v[u].y); }
+                } else {
 #pragma unroll
-                for (int u = 0; u < 6; ++u)
-                    if (u0 + u < Gd) { hx[0] += v0[u].x; hx[1] += v0[u].y; hx[2] += v1[u].x; hx[3] += v1[u].y; }
+                    for (int u = 0; u < RES_MAX_GD; ++u) if (u < Gd) { hx.x += v[u].x; hx.y += v[u].y; }
+                }
+                if (scal) { fin[j2] = hx.x; fin[j2 + 1] = hx.y; }
             }
         }
-        if (t > 0 && tid >= RES_THREADS - 32 && lane < 8) {       // last warp never holds a task (Bs <= 152 < 224)
-            const double* ds = R.dscal + (size_t)((t - 1) & 1) * Gd * 8 + lane;
-            const bool is_max = (lane & 3) < 2;
-            double x[RES_MAX_GD];
-#pragma unroll
-            for (int u = 0; u < RES_MAX_GD; ++u) x[u] = (u < Gd) ? __ldcg(ds + u * 8) : 0.0;
-            double v = 0.0;
-#pragma unroll
-            for (int u = 0; u < RES_MAX_GD; ++u) v = is_max ? fmax(v, x[u]) : v + x[u];
-            fin[lane] = v;
-        }
         __syncthreads();
-        if (t > 0) {
-            if (tid == 0) apply_decision(&sctrl, spass[(t - 1) & 1], fin);
+        if (t > 0) {                                             // one thread per particle, in different warps
+            if (tid == 0 || tid == 32) { const int p = tid >> 5; decide_particle(sctrl.part[p], spass[(t - 1) & 1].part[p], fin + 4 * p); }
             __syncthreads();
-            if (sctrl.all_latched) { decided_all = true; break; }
+            if (sctrl.part[0].latched && sctrl.part[1].latched) { decided_all = true; break; }
         }
 
+        DYB_RSTAMP(4);
         // ---------------------------------------------------------------- 4. recurrence + series sum (registers)
-        double mag[2] = {0.0, 0.0};
+        double mag = 0.0;
         if (task) {
-#pragma unroll
-            for (int p = 0; p < 2; ++p) {
-                const PartPass& pa = spass[t & 1].part[p];
-                if (!pa.active || sctrl.part[p].latched) continue;
-                Cx y = cmul({pa.alpha_re, pa.alpha_im}, {hx[2 * p], hx[2 * p + 1]});
+            const PartPass& pa = spass[t & 1].part[tp];
+            if (pa.active && !sctrl.part[tp].latched) {
+                Cx y = cmul({pa.alpha_re, pa.alpha_im}, {hx.x, hx.y});
                 if (pa.three_term) {
-                    const Cx bc = cmul({pa.beta_re, pa.beta_im}, {cur[2 * p], cur[2 * p + 1]});
+                    const Cx bc = cmul({pa.beta_re, pa.beta_im}, {cur.x, cur.y});
                     y.re += bc.re; y.im += bc.im;
-                    if (pa.gamma != 0.0) { y.re += pa.gamma * prv[2 * p]; y.im += pa.gamma * prv[2 * p + 1]; }
+                    if (pa.gamma != 0.0) { y.re += pa.gamma * prv.x; y.im += pa.gamma * prv.y; }
                 }
                 Cx tt = y;
                 if (pa.scale_term) tt = cmul({pa.c_re, pa.c_im}, y);
-                const double so_re = sum[2 * p], so_im = sum[2 * p + 1];
-                const double nw_re = so_re + tt.re, nw_im = so_im + tt.im;
-                mag[p] = hypot(nw_re - so_re, nw_im - so_im);             // |new - old| like isConverged (Taylor.f:290-303)
-                prv[2 * p] = cur[2 * p]; prv[2 * p + 1] = cur[2 * p + 1];
-                cur[2 * p] = y.re; cur[2 * p + 1] = y.im;
-                sum[2 * p] = nw_re; sum[2 * p + 1] = nw_im;
+                const double nw_re = sum.x + tt.re, nw_im = sum.y + tt.im;
+                const double dx = nw_re - sum.x, dy = nw_im - sum.y;
+                mag = dx * dx + dy * dy;                         // |new - old|^2 (isConverged, Taylor.f:290-303); root after the max
+                prv = cur;
+                cur = make_double2(y.re, y.im);
+                sum = make_double2(nw_re, nw_im);
             }
         }
-        if (tl < Bs) {
-            double2* xd = reinterpret_cast<double2*>(xs[side] + tl * NQ);
-            xd[0] = make_double2(cur[0], cur[1]); xd[1] = make_double2(cur[2], cur[3]);
+        if (slot) {
+            *reinterpret_cast<double2*>(xsd + te * NQ + 2 * tp) = cur;
             if (diag) {
-                double2* sd = reinterpret_cast<double2*>(sq + (size_t)(side * Bs + tl) * NQ);
-                sd[0] = make_double2(sum[0], sum[1]); sd[1] = make_double2(sum[2], sum[3]);
-                *reinterpret_cast<double2*>(mq + (size_t)(side * Bs + tl) * 2) = make_double2(mag[0], mag[1]);
+                *reinterpret_cast<double2*>(sq + (size_t)(side * Bs + te) * NQ + 2 * tp) = sum;
+                mq[(size_t)(side * Bs + te) * 2 + tp] = mag;
             }
         }
         __syncthreads();
 
         // ---------------------------------------------------------------- 5. diagonal CTAs: scalars of their block
         if (diag) {
-            if (side == 0) {                                     // 8 warps, entry tl of block bi == bj
-                double v[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};     // {max_b, max_k, dot_re, dot_im} x particle
-                if (tl < Bs) {
-                    const double2* sk2 = reinterpret_cast<const double2*>(sq + (size_t)tl * NQ);
-                    const double2* sb2 = reinterpret_cast<const double2*>(sq + (size_t)(Bs + tl) * NQ);
-                    const double2 mk = *reinterpret_cast<const double2*>(mq + (size_t)tl * 2);
-                    const double2 mb = *reinterpret_cast<const double2*>(mq + (size_t)(Bs + tl) * 2);
-#pragma unroll
-                    for (int p = 0; p < 2; ++p) {
-                        const double2 k = sk2[p], b = sb2[p];
-                        v[p * 4 + 0] = p ? mb.y : mb.x; v[p * 4 + 1] = p ? mk.y : mk.x;
-                        v[p * 4 + 2] = b.x * k.x + b.y * k.y;    // conj(bra) * ket
-                        v[p * 4 + 3] = b.x * k.y - b.y * k.x;
-                    }
+            if (side == 0) {                                     // 10 warps; thread = (entry te, particle tp) of block bi == bj
+                double v[4] = {0.0, 0.0, 0.0, 0.0};              // max_b, max_k, dot_re, dot_im of this particle
+                if (slot) {
+                    const double2 k = *reinterpret_cast<const double2*>(sq + (size_t)te * NQ + 2 * tp);
+                    const double2 b = *reinterpret_cast<const double2*>(sq + (size_t)(Bs + te) * NQ + 2 * tp);
+                    v[0] = mq[(size_t)(Bs + te) * 2 + tp]; v[1] = mq[(size_t)te * 2 + tp];
+                    v[2] = b.x * k.x + b.y * k.y;                // conj(bra) * ket
+                    v[3] = b.x * k.y - b.y * k.x;
                 }
 #pragma unroll
-                for (int off = 1; off < 32; off <<= 1)
+                for (int off = 2; off < 32; off <<= 1) {         // lanes of equal particle (lane bit 0)
+                    v[0] = fmax(v[0], __shfl_xor_sync(0xffffffffu, v[0], off)); v[1] = fmax(v[1], __shfl_xor_sync(0xffffffffu, v[1], off));
+                    v[2] += __shfl_xor_sync(0xffffffffu, v[2], off);            v[3] += __shfl_xor_sync(0xffffffffu, v[3], off);
+                }
+                if (lane < 2)
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const double ov = __shfl_xor_sync(0xffffffffu, v[q], off);
-                        v[q] = ((q & 3) < 2) ? fmax(v[q], ov) : v[q] + ov;
-                    }
-                if (lane == 0)
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) wred[tl >> 5][q] = v[q];
+                    for (int q = 0; q < 4; ++q) wred[tl >> 5][lane * 4 + q] = v[q];
             }
             __syncthreads();
             if (tid < 8) {
                 double f = wred[0][tid];
                 for (int w2 = 1; w2 < RES_HALF / 32; ++w2) f = ((tid & 3) < 2) ? fmax(f, wred[w2][tid]) : f + wred[w2][tid];
+                if ((tid & 3) < 2) f = sqrt(f);
                 __stcg(R.dscal + ((size_t)(t & 1) * Gd + bi) * 8 + tid, f);
             }
         }
+        DYB_RSTAMP(5);
     }
 
     // ---- decision on the last term (one more barrier), unless the series was decided on the way
     if (!decided_all && t > 0) {
         bar_target += G;
         res_grid_barrier(R.gbar, bar_target);
-        if (tid >= RES_THREADS - 32 && lane < 8) {
-            const double* ds = R.dscal + (size_t)((t - 1) & 1) * Gd * 8 + lane;
-            const bool is_max = (lane & 3) < 2;
+        if (tid >= RES_THREADS - 8) {
+            const int q = tid & 7;
+            const double* ds = R.dscal + (size_t)((t - 1) & 1) * Gd * 8 + q;
+            const bool is_max = (q & 3) < 2;
             double v = 0.0;
             for (int u = 0; u < Gd; ++u) { const double x = __ldcg(ds + u * 8); v = is_max ? fmax(v, x) : v + x; }
-            fin[lane] = v;
+            fin[q] = v;
         }
         __syncthreads();
-        if (tid == 0) apply_decision(&sctrl, spass[(t - 1) & 1], fin);
+        if (tid == 0 || tid == 32) { const int p = tid >> 5; decide_particle(sctrl.part[p], spass[(t - 1) & 1].part[p], fin + 4 * p); }
         __syncthreads();
     }
 
     // ---- results: the diagonal CTAs hold the bra and ket sums of their block
-    if (diag && task) {
-        double2* d = reinterpret_cast<double2*>((side ? R.sum_b : R.sum_k) + (size_t)tn * NQ);
-        d[0] = make_double2(sum[0], sum[1]); d[1] = make_double2(sum[2], sum[3]);
+    if (diag && task)
+        *reinterpret_cast<double2*>((side ? R.sum_b : R.sum_k) + (size_t)tn * NQ + 2 * tp) = sum;
+    if (blockIdx.x == 0 && tid == 0) {
+        sctrl.all_latched = (sctrl.part[0].latched && sctrl.part[1].latched) ? 1 : 0;
+        sctrl.block_counter = 0u;
+        *R.ctrl = sctrl;
     }
-    if (blockIdx.x == 0 && tid == 0) { const unsigned keep = R.ctrl->block_counter; *R.ctrl = sctrl; R.ctrl->block_counter = keep; }
 }
 
 }  // namespace dyb
