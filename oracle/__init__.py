@@ -25,6 +25,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "_build", "liboracle.so")
 _REF_CHEB = os.path.join(_HERE, "_ref", "libref_chebyshev_cpu.so")
 _REF_XPU = os.path.join(_HERE, "_ref", "libref_xpu_cpu.so")
+_REF_TAYLOR_GPU = os.path.join(_HERE, "_ref", "libref_taylor_gpu.so")
 
 ORDER = 25
 H_BAR = 6.58264e-4  # eV*ps, constants_m.f:23
@@ -323,3 +324,68 @@ def ref_dsymm_LU(A, B) -> np.ndarray:
     _xpu().xpu_dsymm_(C.c_char_p(b"L"), C.c_char_p(b"U"), C.byref(n), C.byref(n), C.byref(one), _cp(A), C.byref(n),
                       _cp(B), C.byref(n), C.byref(zero), _cp(out), C.byref(n))
     return out
+
+
+# --------------------------------------------------------------------------- the reference's own GPU propagator (GPU box only)
+_ref_tgpu = None
+_ref_tgpu_elhl_n = None
+
+
+def ref_gpu_available() -> bool:
+    """_ref/libref_taylor_gpu.so present (compiled from /root/reference/Taylor_gpu.cpp + dzgemv_kernels.cu by
+    oracle/Makefile) and a CUDA device to run it on."""
+    if not os.path.exists(_REF_TAYLOR_GPU):
+        return False
+    try:
+        return _tgpu() is not None
+    except OSError:
+        return False
+
+
+def _tgpu():
+    global _ref_tgpu
+    if _ref_tgpu is None:
+        lib_ = C.CDLL(_REF_TAYLOR_GPU)            # RTLD_LOCAL: its symbol names are the product's legacy names too
+        lib_.ref_gpu_init_.restype = C.c_int
+        if lib_.ref_gpu_init_() != 0:
+            raise OSError("ref_gpu_init_ failed (no CUDA device?)")
+        _ref_tgpu = lib_
+    return _ref_tgpu
+
+
+def ref_gpu_propagation(H, bra, ket, t_init, t_max, tau):
+    """propagation_gpucaller_ of /root/reference/Taylor_gpu.cpp:295-330 (one particle, H' given, host buffers).
+    Returns (bra, ket, save_tau)."""
+    Hf = _fd(H); n = C.c_int(Hf.shape[0])
+    b = _fz(bra).copy(order="F"); k = _fz(ket).copy(order="F")
+    tau_ = C.c_double(tau); save = C.c_double(0.0)
+    _tgpu().propagation_gpucaller_(C.byref(n), C.byref(tau_), C.byref(save), C.byref(C.c_double(t_init)), C.byref(C.c_double(t_max)),
+                                   _cp(b), _cp(k), _cp(Hf))
+    return b, k, save.value
+
+
+def ref_gpu_propagationelhl(S, h, bra, ket, t_init, t_max, tau):
+    """propagationelhl_gpucaller_ of /root/reference/Taylor_gpu.cpp:634-736 (one particle per call, like one MPI rank of
+    ElHl_Chebyshev_GPU.f:269-272).  The reference sizes its static device buffers by the first N it sees: one N per process.
+    Returns (H_prime, AO_bra, Psi_bra, Psi_ket, save_tau)."""
+    global _ref_tgpu_elhl_n
+    Sf = _fd(S); hf = _fd(h); N = Sf.shape[0]
+    if _ref_tgpu_elhl_n not in (None, N):
+        raise ValueError(f"reference propagationelhl_gpucaller_ was first called with N={_ref_tgpu_elhl_n} (static buffers)")
+    _ref_tgpu_elhl_n = N
+    n = C.c_int(N)
+    Hp = np.zeros((N, N), dtype=np.float64, order="F")
+    b = _fz(bra).copy(order="F"); k = _fz(ket).copy(order="F")
+    ao_b = np.zeros(N, dtype=np.complex128); ao_k = np.zeros(N, dtype=np.complex128)
+    tau_ = C.c_double(tau); save = C.c_double(0.0)
+    _tgpu().propagationelhl_gpucaller_(C.byref(n), _cp(Sf), _cp(hf), _cp(Hp), _cp(ao_b), _cp(ao_k), _cp(b), _cp(k),
+                                       C.byref(C.c_double(t_init)), C.byref(C.c_double(t_max)), C.byref(tau_), C.byref(save))
+    return Hp, ao_b, b, k, save.value
+
+
+def ref_gpu_ehrenfestkernel(H, A, X):
+    """ehrenfestkernel_gpu_ of /root/reference/Taylor_gpu.cpp:743-795: K = X o A - H' A (static buffers: one N per process)."""
+    Hf = _fd(H); Af = _fd(A); Xf = _fd(X); N = Hf.shape[0]
+    K = np.zeros((N, N), dtype=np.float64, order="F")
+    _tgpu().ehrenfestkernel_gpu_(C.byref(C.c_int(N)), _cp(Hf), _cp(Af), _cp(Xf), _cp(K))
+    return K
