@@ -75,7 +75,7 @@ lib = _load()
 DECLARED_SYMBOLS = [
     "propagationelhl_gpucaller_", "propagationelhl2_gpucaller_", "propagation_gpucaller_", "nakedbessel_", "ehrenfestkernel_gpu_",
     "gpu_init_", "gpu_finalize_", "gpu_pin_", "gpu_unpin_",
-    "dyb_last_error", "dyb_version", "dyb_device_count", "dyb_plan", "dyb_create", "dyb_destroy", "dyb_set_kernel", "dyb_set_series_kernel",
+    "dyb_last_error", "dyb_version", "dyb_device_count", "dyb_plan", "dyb_resident_plan", "dyb_create", "dyb_destroy", "dyb_set_kernel", "dyb_set_series_kernel",
     "dyb_get_info", "dyb_upload_hprime", "dyb_upload_hprime_device", "dyb_upload_hprime_rows_device", "dyb_hprime_device", "dyb_form_hprime", "dyb_form_hprime_device", "dyb_form_hprime_from_overlap",
     "dyb_download_hprime", "dyb_set_packets", "dyb_get_packets", "dyb_propagate", "dyb_ao_bra",
     "dyb_populations", "dyb_run_terms", "dyb_dual_matvec", "dyb_sync", "dyb_launch_count",
@@ -117,6 +117,13 @@ def plan(N: int, n_rows: int | None = None, sm_count: int = 148) -> dict:
     _check(lib.dyb_plan(C.c_int(N), C.c_int(n_rows), C.c_int(sm_count), out, seg_base, pseg))
     d["seg_base"] = list(seg_base); d["pseg_start"] = list(pseg)
     return d
+
+
+def resident_plan(N: int, sm_count: int = 148, smem_optin: int = 232448) -> dict:
+    """Blocking of the shared-memory-resident series kernel (host arithmetic only, works without a GPU)."""
+    out = (C.c_int64 * 6)()
+    _check(lib.dyb_resident_plan(C.c_int(N), C.c_int(sm_count), C.c_int64(smem_optin), out))
+    return dict(zip(["grid_side", "block", "smem_stride", "smem_bytes", "threads", "fits"], [int(v) for v in out]))
 
 
 def device_count() -> int:

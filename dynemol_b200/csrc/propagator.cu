@@ -708,6 +708,29 @@ int dyb_plan(int N, int n_rows, int sm_count, int64_t* out8, int32_t* seg_base, 
     return DYB_OK;
 }
 
+// Host-only: the blocking of the shared-memory-resident series kernel (resident.cuh) for an N x N operator on a GPU
+// with sm_count SMs and smem_optin bytes of opt-in shared memory per block.  out6 = {grid side Gd, block size Bs,
+// smem column stride, dynamic smem bytes, threads per CTA, fits (0/1)}.
+struct ResidentPlan { int Gd, Bs, ldS; size_t smem; bool fits; };
+static ResidentPlan make_resident_plan(int N, int sm_count, size_t smem_optin, size_t static_smem) {
+    ResidentPlan r;
+    int gd_max = 1;
+    while ((gd_max + 1) * (gd_max + 1) <= sm_count && gd_max + 1 <= RES_MAX_GD) ++gd_max;          // 12 on 148 SMs
+    r.Gd = std::min(gd_max, std::max(1, N / 32));                                                  // blocks of >= 32 rows
+    r.Bs = (N + r.Gd - 1) / r.Gd;
+    r.ldS = r.Bs | 1;
+    const ResidentSmem L(r.Bs, r.ldS);
+    r.smem = L.bytes();
+    r.fits = r.Bs <= RES_MAX_BS && r.smem <= (size_t)RES_SMEM_MAX && r.smem + static_smem <= smem_optin;
+    return r;
+}
+int dyb_resident_plan(int N, int sm_count, int64_t smem_optin, int64_t* out6) {
+    if (N <= 0 || sm_count <= 0 || smem_optin <= 0 || !out6) return fail(DYB_EINVAL, "bad argument");
+    const ResidentPlan r = make_resident_plan(N, sm_count, (size_t)smem_optin, 2048);
+    out6[0] = r.Gd; out6[1] = r.Bs; out6[2] = r.ldS; out6[3] = (int64_t)r.smem; out6[4] = RES_THREADS; out6[5] = r.fits ? 1 : 0;
+    return DYB_OK;
+}
+
 int dyb_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -790,13 +813,10 @@ int dyb_create(dyb_ctx** out, int device, int N, int row0, int n_rows) {
         CKCU(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         cudaFuncAttributes fa;
         CKCU(cudaFuncGetAttributes(&fa, resident_series_kernel));
-        int gd_max = 1;
-        while ((gd_max + 1) * (gd_max + 1) <= c->sm_count && gd_max + 1 <= RES_MAX_GD) ++gd_max;     // 12 on 148 SMs
-        const int Gd = std::min(gd_max, std::max(1, (N + 31) / 32));                                  // blocks of >= 32 rows
-        const int Bs = (N + Gd - 1) / Gd, ldS = Bs | 1;
-        const ResidentSmem L(Bs, ldS);
-        if (Bs <= RES_MAX_BS && L.bytes() + fa.sharedSizeBytes <= (size_t)smem_optin) {
-            c->res_Gd = Gd; c->res_Bs = Bs; c->res_ldS = ldS; c->res_smem = L.bytes();
+        const ResidentPlan rp = make_resident_plan(N, c->sm_count, (size_t)smem_optin, fa.sharedSizeBytes);
+        const int Gd = rp.Gd, Bs = rp.Bs;
+        if (rp.fits) {
+            c->res_Gd = Gd; c->res_Bs = Bs; c->res_ldS = rp.ldS; c->res_smem = rp.smem;
             CKCU(cudaFuncSetAttribute(resident_series_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RES_SMEM_MAX));
             CKC(alloc_zero(&c->res_pk, (size_t)2 * Gd * Gd * Bs * NQ)); CKC(alloc_zero(&c->res_pb, (size_t)2 * Gd * Gd * Bs * NQ));
             CKC(alloc_zero(&c->res_dscal, (size_t)2 * Gd * 8));

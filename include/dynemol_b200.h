@@ -127,6 +127,10 @@ int  dyb_device_count(void);
  * segments, tile_cols, panel_rows, padded_cols}; seg_base[grid] / pseg_start[panels+1] filled when non-NULL. */
 int  dyb_plan(int N, int n_rows, int sm_count, int64_t* out8, int32_t* seg_base, int32_t* pseg_start);
 
+/* Host-only: blocking of the shared-memory-resident series kernel (DYB_SERIES_RESIDENT) for an N x N operator.
+ * out6 = {grid side, block size, smem column stride, dynamic smem bytes, threads per CTA, fits (0/1)}. */
+int  dyb_resident_plan(int N, int sm_count, int64_t smem_optin_bytes, int64_t* out6);
+
 /* One context = one GPU, one basis size.  n_rows/row0 select a row shard of H'
  * (single GPU: row0 = 0, n_rows = N).  The context owns all device buffers. */
 int  dyb_create(dyb_ctx** out, int device, int N, int row0, int n_rows);

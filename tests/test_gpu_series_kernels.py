@@ -45,7 +45,7 @@ def run(api, kind, Hp, bra, ket, dt, tau0, mode=None, bounds=None):
     return in_effect, save_tau, traces, b, k, n_launch
 
 
-# N = 36: blocks smaller than a warp; 892: about the heptazine-in-water QM region,
+# N = 36: a single CTA; 256: 8 x 8 CTAs of 32-row blocks; 892: about the heptazine-in-water QM region,
 # not a multiple of the grid side; 1824: the largest operator that fits (152-row blocks on a 12 x 12 grid)
 @pytest.mark.parametrize("N,dt", [(36, 2e-5), (256, 5e-6), (892, 2e-6), (1824, 5e-7)])
 def test_resident_taylor_matches_per_term_and_oracle(api, oracle_mod, N, dt):

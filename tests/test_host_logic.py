@@ -66,3 +66,26 @@ def test_torch_generators_match_numpy():
     assert np.abs(shard.numpy().T - w.h[32:96, :]).max() < 1e-13
     dense = syn.make_h_shard_colmajor_torch(N, 32, 64, "cpu")
     assert (dense == 0).sum() == 0 and np.abs(dense.numpy().T - w.h[32:96, :]).max() <= 1e-3
+
+
+def test_resident_plan_blocking():
+    """Host arithmetic of the shared-memory-resident series kernel (csrc/resident.cuh): the Gd x Gd blocking covers the
+    operator, fits one CTA per SM and the opt-in shared memory, and keeps the column stride odd (bank-conflict-free
+    from both sides).  Largest operator that fits on a B200: N = 1824 (152-row blocks on 12 x 12 CTAs)."""
+    from dynemol_b200 import api
+    for N in list(range(1, 70)) + [127, 128, 129, 383, 384, 385, 512, 892, 900, 1000, 1727, 1728, 1792, 1823, 1824]:
+        p = api.resident_plan(N)
+        assert p["fits"] == 1, N
+        assert p["grid_side"] ** 2 <= 148 and p["grid_side"] * p["block"] >= N
+        assert (p["grid_side"] - 1) * p["block"] < N, "no empty block row"
+        assert p["smem_stride"] % 2 == 1 and p["smem_stride"] >= p["block"]
+        assert p["block"] <= 152 and p["smem_bytes"] <= 227 * 1024 - 2048
+        assert p["block"] >= min(N, 32) or p["grid_side"] == 12
+        assert p["block"] * p["smem_stride"] * 8 < p["smem_bytes"]
+    for N in (1825, 2048, 4096, 16384):
+        assert api.resident_plan(N)["fits"] == 0
+    assert api.resident_plan(1824)["grid_side"] == 12 and api.resident_plan(1824)["block"] == 152
+    # a smaller GPU (fewer SMs) gets a smaller grid and therefore a smaller limit
+    p = api.resident_plan(900, sm_count=64)
+    assert p["grid_side"] == 8 and p["block"] == 113 and p["fits"] == 1
+    assert api.resident_plan(1824, sm_count=64)["fits"] == 0
