@@ -27,6 +27,7 @@
 #include "epilogue.cuh"
 #include "series.cuh"
 #include "resident.cuh"
+#include "blocked.cuh"
 
 using namespace dyb;
 typedef std::complex<double> cplx;
@@ -94,6 +95,9 @@ struct dyb_ctx {
     int res_Gd = 0, res_Bs = 0, res_ldS = 0;     // resident.cuh: grid side, block size, smem column stride (0: does not fit)
     size_t res_smem = 0;
     double *res_pk = nullptr, *res_pb = nullptr, *res_dscal = nullptr;
+    int blk_Gd = 0, blk_Bs = 0, blk_ldS = 0, blk_Cc = 0;    // blocked.cuh: streamed 2-D blocks for mid-size operators (0: not applicable)
+    size_t blk_smem = 0;
+    double *blk_pk = nullptr, *blk_pb = nullptr, *blk_dscal = nullptr, *blk_prv = nullptr, *blk_sum = nullptr, *blk_mag = nullptr;
     PassParams* d_passes = nullptr;      // per-term parameters of the series in flight
     unsigned long long* gbar = nullptr;  // grid barrier counter
     cudaStream_t stream = nullptr;
@@ -394,6 +398,30 @@ static int run_series_persistent(dyb_ctx* c, const std::vector<PassParams>& pass
     return DYB_OK;
 }
 
+// Mid-size operators streamed as 2-D blocks (blocked.cuh): explicit request only until AUTO's crossover is settled.
+static bool blocked_ok(const dyb_ctx* c) {
+    return c->series_kind == DYB_SERIES_BLOCKED && c->world == 1 && c->blk_Gd > 0;
+}
+
+static int run_series_blocked(dyb_ctx* c, const std::vector<PassParams>& passes) {
+    const int n = (int)passes.size();
+    if (n < 1 || n > MAX_SERIES_TERMS) return fail(DYB_EINVAL, "series length %d out of range", n);
+    CK(cudaMemcpyAsync(c->d_passes, passes.data(), sizeof(PassParams) * n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->gbar, 0, sizeof(unsigned long long), c->stream));
+    BlockedParams R;
+    memset(&R, 0, sizeof R);
+    R.H = c->H; R.ld = c->ld; R.N = c->N; R.Gd = c->blk_Gd; R.Bs = c->blk_Bs; R.ldS = c->blk_ldS; R.Cc = c->blk_Cc;
+    R.n_chunks = (c->blk_Bs + c->blk_Cc - 1) / c->blk_Cc;
+    R.x0k = c->vk[0]; R.x0b = c->vb[0]; R.sum_b = c->sum_b; R.sum_k = c->sum_k;
+    R.pk = c->blk_pk; R.pb = c->blk_pb; R.dscal = c->blk_dscal;
+    R.st_prv = c->blk_prv; R.st_sum = c->blk_sum; R.st_mag = c->blk_mag;
+    R.ctrl = c->ctrl; R.passes = c->d_passes; R.n_steps = n; R.gbar = c->gbar;
+    void* args[] = {(void*)&R};
+    CK(cudaLaunchCooperativeKernel((const void*)blocked_series_kernel, dim3(c->blk_Gd * c->blk_Gd), dim3(BLK_THREADS), args, c->blk_smem, c->stream));
+    c->launches++;
+    return DYB_OK;
+}
+
 static int run_series_resident(dyb_ctx* c, const std::vector<PassParams>& passes) {
     const int n = (int)passes.size();
     if (n < 1 || n > MAX_SERIES_TERMS) return fail(DYB_EINVAL, "series length %d out of range", n);
@@ -443,8 +471,9 @@ static int run_series_resident(dyb_ctx* c, const std::vector<PassParams>& passes
 }
 
 // One series through whichever single-launch kernel applies (the caller checked resident_ok / persistent_ok).
+static bool single_launch_ok(const dyb_ctx* c) { return resident_ok(c) || blocked_ok(c) || persistent_ok(c); }
 static int run_series_single_launch(dyb_ctx* c, const std::vector<PassParams>& passes) {
-    return resident_ok(c) ? run_series_resident(c, passes) : run_series_persistent(c, passes);
+    return resident_ok(c) ? run_series_resident(c, passes) : blocked_ok(c) ? run_series_blocked(c, passes) : run_series_persistent(c, passes);
 }
 
 static int launch_series_init(dyb_ctx* c, const int adopt[2], const int active[2], int cur, const cplx* sum_scale = nullptr) {
@@ -604,7 +633,7 @@ static int propagate_series(dyb_ctx* c, int mode, double t_init, double t_max, c
         int prv = 2, cur = 0, nxt = 1;
         if ((rc = launch_series_init(c, adopt, active, cur, mode == DYB_MODE_TAYLOR ? nullptr : sum_scale))) return rc;
         adopt[0] = adopt[1] = 0;
-        if ((resident_ok(c) || persistent_ok(c)) && L <= MAX_SERIES_TERMS) {
+        if (single_launch_ok(c) && L <= MAX_SERIES_TERMS) {
             std::vector<PassParams> passes(L);
             for (int s = 0; s < L; ++s) {
                 memset(&passes[s], 0, sizeof(PassParams));
@@ -724,6 +753,31 @@ static ResidentPlan make_resident_plan(int N, int sm_count, size_t smem_optin, s
     r.fits = r.Bs <= RES_MAX_BS && r.smem <= (size_t)RES_SMEM_MAX && r.smem + static_smem <= smem_optin;
     return r;
 }
+// Blocking of the streamed 2-D block kernel (blocked.cuh): always the full grid side; the chunk width Cc is the
+// largest that lets BLK_STAGES chunks, the two vector blocks and the partial buffers share the opt-in shared memory.
+struct BlockedPlan { int Gd, Bs, ldS, Cc; size_t smem; bool fits; };
+static BlockedPlan make_blocked_plan(int N, int sm_count, size_t smem_optin, size_t static_smem) {
+    BlockedPlan r;
+    int gd_max = 1;
+    while ((gd_max + 1) * (gd_max + 1) <= sm_count && gd_max + 1 <= RES_MAX_GD) ++gd_max;
+    r.Gd = gd_max;
+    r.Bs = (N + r.Gd - 1) / r.Gd;
+    r.ldS = r.Bs | 1;
+    r.Cc = 0; r.smem = 0; r.fits = false;
+    if (r.Bs > BLK_MAX_BS || r.Bs < 64) return r;
+    for (int Cc = std::min(r.Bs, 64); Cc >= 8; --Cc) {
+        const BlockedSmem L(r.Bs, r.ldS, Cc);
+        if (L.bytes() <= (size_t)BLK_SMEM_MAX && L.bytes() + static_smem <= smem_optin) { r.Cc = Cc; r.smem = L.bytes(); r.fits = true; break; }
+    }
+    return r;
+}
+int dyb_blocked_plan(int N, int sm_count, int64_t smem_optin, int64_t* out6) {
+    if (N <= 0 || sm_count <= 0 || smem_optin <= 0 || !out6) return fail(DYB_EINVAL, "bad argument");
+    const BlockedPlan r = make_blocked_plan(N, sm_count, (size_t)smem_optin, 2048);
+    out6[0] = r.Gd; out6[1] = r.Bs; out6[2] = r.ldS; out6[3] = (int64_t)r.smem; out6[4] = r.Cc; out6[5] = r.fits ? 1 : 0;
+    return DYB_OK;
+}
+
 int dyb_resident_plan(int N, int sm_count, int64_t smem_optin, int64_t* out6) {
     if (N <= 0 || sm_count <= 0 || smem_optin <= 0 || !out6) return fail(DYB_EINVAL, "bad argument");
     const ResidentPlan r = make_resident_plan(N, sm_count, (size_t)smem_optin, 2048);
@@ -756,6 +810,7 @@ int dyb_destroy(dyb_ctx* c) {
     if (c->ctrl) cudaFree(c->ctrl);
     if (c->d_passes) cudaFree(c->d_passes);
     if (c->gbar) cudaFree(c->gbar);
+    for (double* b : {c->blk_pk, c->blk_pb, c->blk_dscal, c->blk_prv, c->blk_sum, c->blk_mag}) if (b) cudaFree(b);
     if (c->res_pk) cudaFree(c->res_pk);
     if (c->res_pb) cudaFree(c->res_pb);
     if (c->res_dscal) cudaFree(c->res_dscal);
@@ -822,9 +877,25 @@ int dyb_create(dyb_ctx** out, int device, int N, int row0, int n_rows) {
             CKC(alloc_zero(&c->res_dscal, (size_t)2 * Gd * 8));
         }
     }
+    if (row0 == 0 && n_rows == N && c->res_Gd == 0) {     // blocked.cuh: mid-size operators
+        int smem_optin = 0;
+        CKCU(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        cudaFuncAttributes fa;
+        CKCU(cudaFuncGetAttributes(&fa, blocked_series_kernel));
+        const BlockedPlan bp = make_blocked_plan(N, c->sm_count, (size_t)smem_optin, fa.sharedSizeBytes);
+        if (bp.fits) {
+            c->blk_Gd = bp.Gd; c->blk_Bs = bp.Bs; c->blk_ldS = bp.ldS; c->blk_Cc = bp.Cc; c->blk_smem = bp.smem;
+            CKCU(cudaFuncSetAttribute(blocked_series_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BLK_SMEM_MAX));
+            const size_t G = (size_t)bp.Gd * bp.Gd;
+            CKC(alloc_zero(&c->blk_pk, 2 * G * bp.Bs * NQ)); CKC(alloc_zero(&c->blk_pb, 2 * G * bp.Bs * NQ));
+            CKC(alloc_zero(&c->blk_dscal, (size_t)2 * bp.Gd * 8));
+            CKC(alloc_zero(&c->blk_prv, G * 2 * bp.Bs * NQ)); CKC(alloc_zero(&c->blk_sum, G * 2 * bp.Bs * NQ));
+            CKC(alloc_zero(&c->blk_mag, G * 2 * bp.Bs * 2));
+        }
+    }
     if (const char* e = getenv("DYNEMOL_B200_SERIES")) {
         c->series_kind = !strcmp(e, "term") ? DYB_SERIES_PER_TERM : !strcmp(e, "stream") ? DYB_SERIES_STREAM
-                       : !strcmp(e, "resident") ? DYB_SERIES_RESIDENT : DYB_SERIES_AUTO;
+                       : !strcmp(e, "resident") ? DYB_SERIES_RESIDENT : !strcmp(e, "blocked") ? DYB_SERIES_BLOCKED : DYB_SERIES_AUTO;
     }
     CKCU(cudaDeviceSynchronize());     // the zero fills above ran on the legacy stream; c->stream is non-blocking
 #undef CKC
@@ -844,7 +915,7 @@ int dyb_set_kernel(dyb_ctx* c, int v) {
 
 int dyb_set_series_kernel(dyb_ctx* c, int kind) {
     if (!c) return fail(DYB_EINVAL, "ctx is NULL");
-    if (kind < DYB_SERIES_AUTO || kind > DYB_SERIES_RESIDENT) return fail(DYB_EINVAL, "unknown series kernel %d", kind);
+    if (kind < DYB_SERIES_AUTO || kind > DYB_SERIES_BLOCKED) return fail(DYB_EINVAL, "unknown series kernel %d", kind);
     c->series_kind = kind;
     return DYB_OK;
 }
@@ -854,7 +925,7 @@ int dyb_get_info(dyb_ctx* c, int64_t* o) {
     memset(o, 0, 16 * sizeof(int64_t));
     o[0] = c->N; o[1] = c->ld; o[2] = c->M; o[3] = c->grid; o[4] = c->T; o[5] = c->n_seg; o[6] = c->sm_count;
     o[7] = TmaSmem::total; o[8] = c->variant; o[9] = c->NP; o[10] = c->TPP; o[11] = c->passes_last; o[12] = c->p2p ? 1 : 0;
-    o[13] = resident_ok(c) ? DYB_SERIES_RESIDENT : persistent_ok(c) ? DYB_SERIES_STREAM : DYB_SERIES_PER_TERM;
+    o[13] = resident_ok(c) ? DYB_SERIES_RESIDENT : blocked_ok(c) ? DYB_SERIES_BLOCKED : persistent_ok(c) ? DYB_SERIES_STREAM : DYB_SERIES_PER_TERM;
     o[14] = c->res_Gd; o[15] = c->res_Bs;
     return DYB_OK;
 }
@@ -1216,7 +1287,7 @@ int dyb_run_terms(dyb_ctx* c, double tau, int n_terms, float* elapsed_ms, float*
     while (c->ev.size() < need) { cudaEvent_t e; CK(cudaEventCreate(&e)); c->ev.push_back(e); }
     const int none[2] = {0, 0}, both[2] = {1, c->n_part > 1 ? 1 : 0};
     int rc, cur = 0, nxt = 1;
-    if ((resident_ok(c) || persistent_ok(c)) && !per_kernel) {
+    if (single_launch_ok(c) && !per_kernel) {
         // one series_init + one cooperative launch per 24-term series
         CK(cudaEventRecord(c->ev[0], c->stream));
         for (int s0 = 0; s0 < n_terms; s0 += ORDER - 1) {

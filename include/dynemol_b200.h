@@ -130,6 +130,9 @@ int  dyb_plan(int N, int n_rows, int sm_count, int64_t* out8, int32_t* seg_base,
 /* Host-only: blocking of the shared-memory-resident series kernel (DYB_SERIES_RESIDENT) for an N x N operator.
  * out6 = {grid side, block size, smem column stride, dynamic smem bytes, threads per CTA, fits (0/1)}. */
 int  dyb_resident_plan(int N, int sm_count, int64_t smem_optin_bytes, int64_t* out6);
+/* Same for the streamed 2-D block kernel (DYB_SERIES_BLOCKED): out6 = {grid side, block size, smem column stride,
+ * dynamic smem bytes, chunk columns, fits (0/1)}. */
+int  dyb_blocked_plan(int N, int sm_count, int64_t smem_optin_bytes, int64_t* out6);
 
 /* One context = one GPU, one basis size.  n_rows/row0 select a row shard of H'
  * (single GPU: row0 = 0, n_rows = N).  The context owns all device buffers. */
@@ -146,6 +149,7 @@ int  dyb_set_kernel(dyb_ctx* ctx, int kernel_variant);
 #define DYB_SERIES_PER_TERM 1
 #define DYB_SERIES_STREAM   2
 #define DYB_SERIES_RESIDENT 3
+#define DYB_SERIES_BLOCKED  4   /* one cooperative launch per series, H' streamed as 12 x 12 blocks (single GPU, 768 <= N <= 6144) */
 int  dyb_set_series_kernel(dyb_ctx* ctx, int kind);
 int  dyb_get_info(dyb_ctx* ctx, int64_t* info16);   /* [0]=N [1]=ld [2]=n_rows [3]=grid [4]=tiles [5]=segments [6]=sm_count [7]=smem_bytes [8]=variant ... [13]=series kernel in effect [14]=resident grid side [15]=resident block size */
 
