@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""tools/ref_gpu_bench.py -- side measurement, NOT part of bench.py's contract: the reference's OWN GPU kernels
+"""tests/ref_gpu_bench.py -- side measurement (lives under tests/ because it executes oracle/_ref: checker code, never the product), NOT part of bench.py's contract: the reference's OWN GPU kernels
 (oracle/_ref/libref_taylor_gpu.so = Taylor_gpu.cpp + dzgemv_kernels.cu compiled in place for sm_100a) timed on the
 same B200 next to the product.
 

@@ -75,3 +75,9 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f
+                assert "libref_" not in txt and "oracle/_ref" not in txt, f
+    # helper scripts outside tests/ do not execute the checker either (tests/ref_gpu_bench.py is the one that may)
+    tools = os.path.join(ROOT, "tools")
+    for f in os.listdir(tools):
+        txt = open(os.path.join(tools, f), errors="ignore").read()
+        assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt and "libref_" not in txt, f
