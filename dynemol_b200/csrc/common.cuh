@@ -47,7 +47,12 @@ struct PartPass {
     int    check_conv;   // Convergence(): early exit when both term maxima <= tol and the norm holds
     int    last;         // last term of this series for this particle: latch with ok = norm test (or 0)
     int    last_ok_by_norm; // steady sub-step: ok decided by the norm test alone at the last term
+    int    begin;        // chained steady sub-steps (resident kernel): this term starts a new sub-step from the sum of the
+                         // previous one (psi <- sum ; sum <- s * psi), Taylor.f:81-126 without the host in the loop
+    int    chain;        // this is the last term of a sub-step and another sub-step of the same particle follows in the
+                         // same launch: a passed norm test counts the sub-step and does not latch
     int    pad_;
+    double s_re, s_im;   // scale of the series sum at `begin` (c_0 of the Chebyshev series; 1 for Taylor)
     double alpha_re, alpha_im;
     double beta_re, beta_im;
     double gamma;
@@ -63,6 +68,8 @@ struct PartState {
     int    ok;
     int    k_exit;
     int    n_terms;      // terms actually applied in this series
+    int    n_sub_ok;     // steady sub-steps (last term without check_conv) that passed the norm test in this launch
+    int    pad_;
     double max_b, max_k; // last term maxima
     double dot_re, dot_im;
     double norm;         // | <sum_b | sum_k> | of the last applied term

@@ -75,7 +75,9 @@ __device__ __forceinline__ void decide_particle(PartState& st, const PartPass& q
         if (conv && norm_ok) { st.latched = 1; st.ok = 1; st.k_exit = q.k; }
         else if (q.last)     { st.latched = 1; st.ok = 0; st.k_exit = 0; }
     } else if (q.last) {
-        st.latched = 1; st.ok = (q.last_ok_by_norm ? (norm_ok ? 1 : 0) : 1); st.k_exit = q.k;
+        const int ok = q.last_ok_by_norm ? (norm_ok ? 1 : 0) : 1;
+        st.n_sub_ok += ok;
+        if (!(ok && q.chain)) { st.latched = 1; st.ok = ok; st.k_exit = q.k; }      // a chained success just goes on
     }
 }
 __device__ __forceinline__ void apply_decision(Ctrl* c, const PassParams& pass, const double* v) {
@@ -357,8 +359,8 @@ __global__ void series_init_kernel(const InitParams I)
     if (idx == 0) {
         for (int p = 0; p < 2; ++p) {
             PartState& st = I.ctrl->part[p];
-            if (I.active[p]) { st.latched = 0; st.ok = 0; st.k_exit = 0; st.n_terms = 0; }
-            else             { st.latched = 1; }
+            if (I.active[p]) { st.latched = 0; st.ok = 0; st.k_exit = 0; st.n_terms = 0; st.n_sub_ok = 0; }
+            else             { st.latched = 1; st.ok = 1; }      // sits this launch out (ok = 1: "did not fail")
         }
         I.ctrl->all_latched = (I.active[0] || I.active[1]) ? 0 : 1;
         I.ctrl->block_counter = 0u;

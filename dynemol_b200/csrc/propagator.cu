@@ -91,6 +91,7 @@ struct dyb_ctx {
     size_t Lq = 0;                       // quad vector length (indices)
     int variant = DYB_KERNEL_TMA;
     bool use_pdl = true;                 // programmatic dependent launch between the dual product and the epilogue
+    bool chain_steady = true;            // resident kernel: run the whole steady loop of a step in one launch (env DYNEMOL_B200_CHAIN=0 disables)
     int series_kind = DYB_SERIES_AUTO;   // how a series is launched: per term, streaming cooperative kernel, smem-resident kernel
     int res_Gd = 0, res_Bs = 0, res_ldS = 0;     // resident.cuh: grid side, block size, smem column stride (0: does not fit)
     size_t res_smem = 0;
@@ -349,6 +350,7 @@ static bool resident_ok(const dyb_ctx* c) {
     return (c->series_kind == DYB_SERIES_RESIDENT || c->series_kind == DYB_SERIES_AUTO) && c->world == 1 && c->res_Gd > 0;
 }
 constexpr int MAX_SERIES_TERMS = 32;
+constexpr int MAX_CHAIN_PASSES = 4096;      // chained steady sub-steps of one launch (resident kernel)
 
 static int run_series_persistent(dyb_ctx* c, const std::vector<PassParams>& passes) {
     const int n = (int)passes.size();
@@ -424,7 +426,7 @@ static int run_series_blocked(dyb_ctx* c, const std::vector<PassParams>& passes)
 
 static int run_series_resident(dyb_ctx* c, const std::vector<PassParams>& passes) {
     const int n = (int)passes.size();
-    if (n < 1 || n > MAX_SERIES_TERMS) return fail(DYB_EINVAL, "series length %d out of range", n);
+    if (n < 1 || n > MAX_CHAIN_PASSES) return fail(DYB_EINVAL, "series length %d out of range", n);
     CK(cudaMemcpyAsync(c->d_passes, passes.data(), sizeof(PassParams) * n, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemsetAsync(c->gbar, 0, sizeof(unsigned long long), c->stream));
     ResidentParams R;
@@ -453,7 +455,7 @@ static int run_series_resident(dyb_ctx* c, const std::vector<PassParams>& passes
             CK(cudaMemcpy(h.data(), d_rprof, n_rprof * 8, cudaMemcpyDeviceToHost));
             const char* name[6] = {"product", "partial-store", "barrier", "gather+decide", "update+diag", "loop-gap"};
             double mean[6] = {0}, mx[6] = {0};
-            for (int t = 0; t + 1 < n; ++t) for (int b = 0; b < rgrid; ++b) {
+            for (int t = 0; t + 1 < std::min(n, MAX_SERIES_TERMS); ++t) for (int b = 0; b < rgrid; ++b) {
                 const long long* q = &h[((size_t)t * rgrid + b) * 6];
                 for (int i = 0; i < 6; ++i) {
                     const long long nx = (i < 5) ? q[i + 1] : h[((size_t)(t + 1) * rgrid + b) * 6];
@@ -629,6 +631,78 @@ static int propagate_series(dyb_ctx* c, int mode, double t_init, double t_max, c
         }
         if (!active[0] && !active[1]) break;
         if (++guard > 2000000) return fail(DYB_EINVAL, "propagation does not terminate (tau -> 0?)");
+
+        // Small operators (resident kernel) with every active particle in the steady loop: the whole remaining loop of
+        // Taylor.f:81-126 goes into ONE launch.  The sub-step schedule (tau, the shortened last sub-step and its
+        // coefficients, Taylor.f:116-121) is predicted with the very operations the state machine below performs;
+        // the device chains the sub-steps (PartPass::begin / chain) and stops a particle at the first failed norm test.
+        bool all_steady = resident_ok(c) && c->chain_steady;
+        for (int p = 0; p < 2; ++p) if (active[p] && P[p].phase != 1) all_steady = false;
+        if (all_steady) {
+            std::vector<PassParams> passes;
+            for (int p = 0; p < 2; ++p) {
+                if (!active[p]) continue;
+                Particle sim = P[p];
+                size_t pos = 0;
+                int n_sub = 0;
+                while (sim.t < t_max) {
+                    const int nt = sim.k_ref - 1;
+                    if (nt < 1 || pos + nt > (size_t)MAX_CHAIN_PASSES) break;
+                    if (passes.size() < pos + nt) {
+                        const size_t old_n = passes.size();
+                        passes.resize(pos + nt);
+                        memset(&passes[old_n], 0, sizeof(PassParams) * (pos + nt - old_n));
+                    }
+                    sim.check = false; sim.n_terms = nt;
+                    for (int j = 0; j < nt; ++j) fill_pass(passes[pos + j].part[p], sim, mode, j, ebar, de);
+                    if (n_sub > 0) {
+                        PartPass& first = passes[pos].part[p];
+                        const cplx s0 = (mode == DYB_MODE_TAYLOR) ? cplx(1.0, 0.0) : sim.C[0];
+                        first.begin = 1; first.s_re = s0.real(); first.s_im = s0.imag();
+                        passes[pos - 1].part[p].chain = 1;
+                    }
+                    pos += nt; ++n_sub;
+                    sim.t += sim.tau * H_BAR;                     // Taylor.f:116
+                    if (t_max - sim.t < sim.tau * H_BAR) {        // Taylor.f:118-121
+                        sim.tau = (t_max - sim.t) / H_BAR;
+                        coefficient(sim);
+                    }
+                }
+                if (n_sub == 0) return fail(DYB_EINVAL, "steady sub-step of %d terms does not fit a launch", sim.k_ref - 1);
+            }
+            if ((rc = launch_series_init(c, adopt, active, 0, mode == DYB_MODE_TAYLOR ? nullptr : sum_scale))) return rc;
+            adopt[0] = adopt[1] = 0;
+            if ((rc = run_series_resident(c, passes))) return rc;
+            if ((rc = read_ctrl(c))) return rc;
+            c->passes_last += std::max(active[0] ? c->h_ctrl->part[0].n_terms : 0, active[1] ? c->h_ctrl->part[1].n_terms : 0);
+            for (int p = 0; p < 2; ++p) {
+                Particle& q = P[p];
+                if (!active[p]) continue;
+                const PartState& st = c->h_ctrl->part[p];
+                const bool failed = st.latched && !st.ok;
+                if (q.tr) { q.tr->n_matvec_pairs += st.n_terms; q.tr->last_k_ref = q.k_ref; }
+                for (int i = 0; i < st.n_sub_ok; ++i) {           // Taylor.f:102-105, :116-121 for every accepted sub-step
+                    if (q.tr) q.tr->n_substeps++;
+                    trace_event(q.tr, 2, q.k_ref, 1, q.tau);
+                    q.t += q.tau * H_BAR;
+                    if (t_max - q.t < q.tau * H_BAR) {
+                        q.tau = (t_max - q.t) / H_BAR;
+                        coefficient(q);
+                    }
+                    if (!(q.t < t_max)) q.done = true;
+                }
+                if (st.n_sub_ok > 0) adopt[p] = 1;                // sum holds the last accepted vector (resident.cuh hands back
+                                                                  // the start of a failed sub-step)
+                if (failed) {                                     // Taylor.f:108-110
+                    if (q.tr) q.tr->n_substeps++;
+                    trace_event(q.tr, 2, q.k_ref, 0, q.tau);
+                    q.tau *= 0.975;
+                    if (q.tr) q.tr->n_rescale++;
+                    q.phase = 2;
+                }
+            }
+            continue;
+        }
 
         int prv = 2, cur = 0, nxt = 1;
         if ((rc = launch_series_init(c, adopt, active, cur, mode == DYB_MODE_TAYLOR ? nullptr : sum_scale))) return rc;
@@ -861,7 +935,7 @@ int dyb_create(dyb_ctx** out, int device, int N, int row0, int n_rows) {
     CKC(build_tensor_map(c));
     CKCU(cudaFuncSetAttribute(dual_matvec_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TmaSmem::total));
     CKCU(cudaFuncSetAttribute(series_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TmaSmem::total));
-    CKCU(cudaMalloc(&c->d_passes, sizeof(PassParams) * MAX_SERIES_TERMS));
+    CKCU(cudaMalloc(&c->d_passes, sizeof(PassParams) * MAX_CHAIN_PASSES));
     CKCU(cudaMalloc(&c->gbar, sizeof(unsigned long long)));
     if (row0 == 0 && n_rows == N) {    // resident.cuh: does a Gd x Gd blocking of H' fit the shared memories?
         int smem_optin = 0;
@@ -893,6 +967,7 @@ int dyb_create(dyb_ctx** out, int device, int N, int row0, int n_rows) {
             CKC(alloc_zero(&c->blk_mag, G * 2 * bp.Bs * 2));
         }
     }
+    if (const char* e = getenv("DYNEMOL_B200_CHAIN")) c->chain_steady = (e[0] != '0');
     if (const char* e = getenv("DYNEMOL_B200_SERIES")) {
         c->series_kind = !strcmp(e, "term") ? DYB_SERIES_PER_TERM : !strcmp(e, "stream") ? DYB_SERIES_STREAM
                        : !strcmp(e, "resident") ? DYB_SERIES_RESIDENT : !strcmp(e, "blocked") ? DYB_SERIES_BLOCKED : DYB_SERIES_AUTO;

@@ -47,7 +47,7 @@ struct ResidentParams {
 };
 
 #ifdef DYB_SERIES_PROF
-#define DYB_RSTAMP(i) do { if (threadIdx.x == 0) R.prof[((size_t)t * G + blockIdx.x) * 6 + (i)] = clock64(); } while (0)
+#define DYB_RSTAMP(i) do { if (threadIdx.x == 0 && t < 32) R.prof[((size_t)t * G + blockIdx.x) * 6 + (i)] = clock64(); } while (0)
 #else
 #define DYB_RSTAMP(i) do { } while (0)
 #endif
@@ -98,6 +98,8 @@ resident_series_kernel(const ResidentParams R)
     __shared__ PassParams spass[2];
     __shared__ double     fin[8];
     __shared__ double     wred[RES_HALF / 32][8];
+    __shared__ int        stop_chain;                            // a particle failed a chained sub-step: the other one stops at
+                                                                 // its next sub-step boundary so that both resume together
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int Gd = R.Gd, Bs = R.Bs, ldS = R.ldS, N = R.N;
@@ -121,7 +123,7 @@ resident_series_kernel(const ResidentParams R)
                 if (rl < Bs) Hs[cl * ldS + rl] = (r_base + rl < N && c < N) ? __ldg(src + rl) : 0.0;
             }
         }
-        if (tid == 0) sctrl = *R.ctrl;
+        if (tid == 0) { sctrl = *R.ctrl; stop_chain = 0; }
     }
 
     // ---- epilogue task of this thread: particle tp of entry te of block (side == 0 ? bj : bi); state in registers
@@ -131,10 +133,14 @@ resident_series_kernel(const ResidentParams R)
     const bool slot = (te < Bs);                                 // owns a (possibly padding) entry of the block
     const bool task = slot && (tn < N);
     double2 cur = make_double2(0.0, 0.0), prv = make_double2(0.0, 0.0), sum = make_double2(0.0, 0.0);
+    double2 psi = make_double2(0.0, 0.0);                        // start vector of the sub-step in progress (chained sub-steps)
     if (task) {
         cur = *reinterpret_cast<const double2*>((side ? R.x0b : R.x0k) + (size_t)tn * NQ + 2 * tp);
         sum = *reinterpret_cast<const double2*>((side ? R.sum_b : R.sum_k) + (size_t)tn * NQ + 2 * tp);
+        psi = cur;
     }
+    bool was_active = false;                                     // set below from the control block: only particles that take
+                                                                 // part in this launch hand a vector back
     if (slot) *reinterpret_cast<double2*>(xsd + te * NQ + 2 * tp) = cur;
 
     // ---- product mapping: a thread owns TWO owners oA = o and oB = o + Bh (rows for the ket side, columns for the bra
@@ -153,6 +159,7 @@ resident_series_kernel(const ResidentParams R)
     double pass_word = 0.0;
     if (tid < sizeof(PassParams) / 8 && R.n_steps > 0) pass_word = reinterpret_cast<const double*>(R.passes)[tid];
     __syncthreads();
+    was_active = !sctrl.part[tp].latched;                        // series_init_kernel latches the particles that sit out
 
     int t = 0;
     for (; t < R.n_steps; ++t) {
@@ -231,17 +238,29 @@ resident_series_kernel(const ResidentParams R)
         }
         __syncthreads();
         if (t > 0) {                                             // one thread per particle, in different warps
-            if (tid == 0 || tid == 32) { const int p = tid >> 5; decide_particle(sctrl.part[p], spass[(t - 1) & 1].part[p], fin + 4 * p); }
+            if (tid == 0 || tid == 32) {
+                const int p = tid >> 5;
+                PartPass q = spass[(t - 1) & 1].part[p];
+                if (stop_chain) q.chain = 0;                     // flag as of the previous term: the same in every CTA
+                decide_particle(sctrl.part[p], q, fin + 4 * p);
+            }
             __syncthreads();
             if (sctrl.part[0].latched && sctrl.part[1].latched) { decided_all = true; break; }
+            if (tid == 0 && ((sctrl.part[0].latched && !sctrl.part[0].ok) || (sctrl.part[1].latched && !sctrl.part[1].ok))) stop_chain = 1;
         }
 
         DYB_RSTAMP(4);
         // ---------------------------------------------------------------- 4. recurrence + series sum (registers)
         double mag = 0.0;
+        double2 xout = cur;                                      // what the next product multiplies
         if (task) {
             const PartPass& pa = spass[t & 1].part[tp];
             if (pa.active && !sctrl.part[tp].latched) {
+                if (pa.begin) {                                  // next steady sub-step: adopt the previous sum (Taylor.f:105,
+                    psi = sum; cur = sum;                        // :83-86); hx was computed from it (xout of the last term)
+                    const Cx s0 = cmul({pa.s_re, pa.s_im}, {sum.x, sum.y});
+                    sum = make_double2(s0.re, s0.im);
+                }
                 Cx y = cmul({pa.alpha_re, pa.alpha_im}, {hx.x, hx.y});
                 if (pa.three_term) {
                     const Cx bc = cmul({pa.beta_re, pa.beta_im}, {cur.x, cur.y});
@@ -256,10 +275,11 @@ resident_series_kernel(const ResidentParams R)
                 prv = cur;
                 cur = make_double2(y.re, y.im);
                 sum = make_double2(nw_re, nw_im);
+                xout = pa.chain ? sum : cur;                     // speculative: the next sub-step starts from this sum
             }
         }
         if (slot) {
-            *reinterpret_cast<double2*>(xsd + te * NQ + 2 * tp) = cur;
+            *reinterpret_cast<double2*>(xsd + te * NQ + 2 * tp) = xout;
             if (diag) {
                 *reinterpret_cast<double2*>(sq + (size_t)(side * Bs + te) * NQ + 2 * tp) = sum;
                 mq[(size_t)(side * Bs + te) * 2 + tp] = mag;
@@ -316,8 +336,10 @@ resident_series_kernel(const ResidentParams R)
     }
 
     // ---- results: the diagonal CTAs hold the bra and ket sums of their block
-    if (diag && task)
-        *reinterpret_cast<double2*>((side ? R.sum_b : R.sum_k) + (size_t)tn * NQ + 2 * tp) = sum;
+    // a particle that failed a steady sub-step hands back the start vector of that sub-step (= the last accepted sum)
+    if (diag && task && was_active)
+        *reinterpret_cast<double2*>((side ? R.sum_b : R.sum_k) + (size_t)tn * NQ + 2 * tp) =
+            (sctrl.part[tp].latched && !sctrl.part[tp].ok) ? psi : sum;
     if (blockIdx.x == 0 && tid == 0) {
         sctrl.all_latched = (sctrl.part[0].latched && sctrl.part[1].latched) ? 1 : 0;
         sctrl.block_counter = 0u;

@@ -186,3 +186,52 @@ def test_blocked_chebyshev_and_single_particle(api, oracle_mod):
     # electron alone: same bits as in the batched run
     k1, st1, tr1, b1, kk1, _ = run(api, "blocked", Hp, w.Psi_bra[:, 0], w.Psi_ket[:, 0], dt, tau0, mode=api.MODE_CHEBYSHEV, bounds=bounds)
     assert np.array_equal(b1[:, 0], b_b[:, 0]) and np.array_equal(kk1[:, 0], k_b[:, 0])
+
+
+def test_chained_steady_loop_is_bit_identical(api):
+    """Small operators run the whole steady loop of a nuclear step (Taylor.f:81-126) in ONE launch: the host predicts the
+    sub-step schedule, the device chains the sub-steps (PartPass::begin / chain) and stops at a failed norm test.  Against
+    the same kernel driven one sub-step per launch (DYNEMOL_B200_CHAIN=0): identical tau schedule, events, pass counts
+    and wavepackets, bit for bit, over several nuclear steps with the carried-over tau of ElHl_Chebyshev.f:182-184 (which
+    provokes failed norm tests and rescaling), in both modes; and far fewer launches."""
+    import os
+    N = 600
+    w = syn.make_workload(N)
+    res = {}
+    bounds = None          # estimated once: the Lanczos estimate (host OpenMP reductions) is not bit-reproducible run to run
+    for chain in ("0", "1"):
+        os.environ["DYNEMOL_B200_CHAIN"] = chain
+        try:
+            P = api.Propagator(N)
+        finally:
+            os.environ.pop("DYNEMOL_B200_CHAIN", None)
+        assert P.info()["series_kernel"] == SERIES_RESIDENT
+        P.form_hprime(w.S, w.h, want_hprime=False)
+        out = []
+        for mode, dt in ((api.MODE_TAYLOR, 2e-5), (api.MODE_CHEBYSHEV, 5e-4)):
+            P.set_packets(w.Psi_bra, w.Psi_ket)
+            if mode == api.MODE_CHEBYSHEV:
+                if bounds is None:
+                    bounds = P.estimate_spectral_bounds(24, 0.05)
+                P.set_spectral_bounds(*bounds)
+            tau = dt / H_BAR
+            save = np.array([tau, tau])
+            for _ in range(3):
+                l0 = P.launch_count()
+                save, tr = P.propagate(0.0, dt, np.minimum(tau, 1.15 * save), mode=mode)
+                b, k = P.get_packets()
+                out.append(dict(save=save.copy(), events=[[tuple(e) for e in t.events()] for t in tr], pairs=[t.n_matvec_pairs for t in tr],
+                                sub=[t.n_substeps for t in tr], resc=[t.n_rescale for t in tr], bra=b.copy(), ket=k.copy(), launches=P.launch_count() - l0))
+        res[chain] = out
+        P.close()
+    n_fail = 0
+    for i, (a, b) in enumerate(zip(res["0"], res["1"])):
+        assert np.array_equal(a["save"], b["save"])
+        assert a["events"] == b["events"] and a["pairs"] == b["pairs"] and a["sub"] == b["sub"] and a["resc"] == b["resc"]
+        assert np.array_equal(a["bra"], b["bra"]) and np.array_equal(a["ket"], b["ket"])
+        assert b["launches"] < a["launches"]
+        if i < 3:                                                # Taylor steps: hundreds of short sub-steps, a handful of launches
+            assert b["launches"] < a["launches"] / 3
+        n_fail += sum(a["resc"])
+        assert max(a["sub"]) >= 10, "the case must actually have a steady loop worth chaining"
+    assert n_fail > 0, "the case must exercise a failed sub-step inside a chained launch"
