@@ -1484,26 +1484,31 @@ int dyb_estimate_spectral_bounds(dyb_ctx* c, int n_iter, double margin, double* 
     std::vector<dyb_complex> w(n * np), v(n * np), wp(n * np, dyb_complex{0, 0}), vp(n * np, dyb_complex{0, 0}), hw(n * np), hv(n * np);
     int rc = dyb_get_packets(c, np, w.data(), v.data());
     if (rc) return rc;
-    // host loops are O(n_iter^2 N): threaded with OpenMP (static schedule + fixed thread count => reproducible sums)
+    // host loops are O(n_iter^2 N): threaded with OpenMP.  Sums run over fixed blocks of 4096 elements (one thread per
+    // block) and the block partials are added in order: the result depends neither on the thread count nor on the schedule
+    // (an OpenMP reduction clause does not promise that), so the estimated interval is bit-reproducible run to run.
     const long nn = (long)n;
-    auto dotc_re = [&](const dyb_complex* x, const dyb_complex* y) {
-        double s = 0;
-        #pragma omp parallel for reduction(+ : s) schedule(static)
-        for (long i = 0; i < nn; ++i) s += x[i].re * y[i].re + x[i].im * y[i].im;
-        return s;
+    auto blocked_dot = [&](const dyb_complex* x, const dyb_complex* y, double& re, double& im) {
+        const long BL = 4096, nb = (nn + BL - 1) / BL;
+        std::vector<double> pr(nb), pi(nb);
+        #pragma omp parallel for schedule(static)
+        for (long b = 0; b < nb; ++b) {
+            double sr = 0, si = 0;
+            const long i1 = std::min(nn, (b + 1) * BL);
+            for (long i = b * BL; i < i1; ++i) { sr += x[i].re * y[i].re + x[i].im * y[i].im; si += x[i].re * y[i].im - x[i].im * y[i].re; }
+            pr[b] = sr; pi[b] = si;
+        }
+        re = 0; im = 0;
+        for (long b = 0; b < nb; ++b) { re += pr[b]; im += pi[b]; }
     };
+    auto dotc_re = [&](const dyb_complex* x, const dyb_complex* y) { double re, im; blocked_dot(x, y, re, im); return re; };
     std::vector<std::vector<double>> al(np), be(np);
     std::vector<double> beta(np, 0.0);
     std::vector<bool> alive(np, true);
     // all Lanczos vectors are kept: without re-biorthogonalisation the two-sided recurrence loses the duality
     // w_j = S v_j after ~35 steps and produces Ritz values far outside the spectrum
     std::vector<std::vector<dyb_complex>> Wall(np), Vall(np);
-    auto dotc_c = [&](const dyb_complex* x, const dyb_complex* y, double& re, double& im) {
-        double sr = 0, si = 0;
-        #pragma omp parallel for reduction(+ : sr, si) schedule(static)
-        for (long i = 0; i < nn; ++i) { sr += x[i].re * y[i].re + x[i].im * y[i].im; si += x[i].re * y[i].im - x[i].im * y[i].re; }
-        re = sr; im = si;
-    };
+    auto dotc_c = [&](const dyb_complex* x, const dyb_complex* y, double& re, double& im) { blocked_dot(x, y, re, im); };
     for (int p = 0; p < np; ++p) {
         const double n0 = dotc_re(&w[p * n], &v[p * n]);
         if (!(n0 > 0.0)) return fail(DYB_EINVAL, "<bra|ket> of particle %d is not positive: packets are not an S-dual pair", p);

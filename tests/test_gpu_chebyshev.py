@@ -55,6 +55,7 @@ def test_lanczos_bounds_and_half_femtosecond_step(api, oracle_mod):
     P.upload_hprime(Hp)
     P.set_packets(w.Psi_bra, w.Psi_ket)
     lo, hi = P.estimate_spectral_bounds(n_iter=60, margin=0.02)
+    assert (lo, hi) == P.estimate_spectral_bounds(n_iter=60, margin=0.02), "the estimate must be bit-reproducible"
     width = e.max() - e.min()
     assert lo <= e.min() + 1e-6 * width and hi >= e.max() - 1e-6 * width, (lo, hi, e.min(), e.max())
     assert hi - lo < 1.10 * width, "bounds should be tight, not Gershgorin-loose"
