@@ -254,6 +254,16 @@ def small_operator(args, N=900):
             ms, _ = P.run_terms(tau, TERMS_PER_STEP * 200)
             key = "per_term" if kind == "term" else ("resident" if P.info()["series_kernel"] == 3 else "auto")
             out[key] = {"value": round(TERMS_PER_STEP * 200 / (ms * 1e-3), 1), "us_per_term": round(ms * 1e3 / (TERMS_PER_STEP * 200), 2)}
+            # whole nuclear steps through dyb_propagate (Taylor mode, dt = 0.02 fs, carried-over tau): host logic included
+            dt = 2e-5; tau0 = dt / H_BAR
+            P.set_packets(bra, ket)
+            save, _ = P.propagate(0.0, dt, tau0)
+            P.sync(); l0 = P.launch_count(); t0 = time.perf_counter()
+            for _ in range(5):
+                save, _ = P.propagate(0.0, dt, np.minimum(tau0, 1.15 * save))
+            P.sync()
+            out[key]["taylor_step_ms"] = round((time.perf_counter() - t0) / 5 * 1e3, 3)
+            out[key]["passes_per_step"] = P.info()["passes_last"]; out[key]["launches_per_step"] = (P.launch_count() - l0) // 5
         P.close()
         torch.cuda.empty_cache()
         return out
