@@ -944,7 +944,15 @@ int dyb_create(dyb_ctx** out, int device, int N, int row0, int n_rows) {
         CKCU(cudaFuncGetAttributes(&fa, resident_series_kernel));
         const ResidentPlan rp = make_resident_plan(N, c->sm_count, (size_t)smem_optin, fa.sharedSizeBytes);
         const int Gd = rp.Gd, Bs = rp.Bs;
-        if (rp.fits) {
+        bool launchable = rp.fits;
+        if (launchable) {   // a cooperative grid must be co-resident: one CTA per SM, and the device must support it
+            CKCU(cudaFuncSetAttribute(resident_series_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RES_SMEM_MAX));
+            int coop = 0, per_sm = 0;
+            CKCU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+            CKCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resident_series_kernel, RES_THREADS, rp.smem));
+            launchable = coop && (long)per_sm * c->sm_count >= (long)Gd * Gd;
+        }
+        if (launchable) {
             c->res_Gd = Gd; c->res_Bs = Bs; c->res_ldS = rp.ldS; c->res_smem = rp.smem;
             CKCU(cudaFuncSetAttribute(resident_series_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RES_SMEM_MAX));
             CKC(alloc_zero(&c->res_pk, (size_t)2 * Gd * Gd * Bs * NQ)); CKC(alloc_zero(&c->res_pb, (size_t)2 * Gd * Gd * Bs * NQ));
