@@ -63,7 +63,7 @@ __device__ __forceinline__ Cx reduce_bra(const EpiParams& E, int i, int pp) {
 
 // The per-term decision the reference takes on the host (Taylor.f:194-207 inside Convergence, :102-105 in
 // the steady loop), from the 8 reduced scalars v = {max_b, max_k, dot_re, dot_im} x {el, hl}.
-__device__ __forceinline__ void decide_particle(PartState& st, const PartPass& q, const double* v4) {
+__device__ __forceinline__ void decide_particle(PartState& st, const PartPass& q, const double* v4, bool allow_chain = true) {
     if (!q.active || st.latched) return;
     st.n_terms += 1;
     st.max_b = v4[0]; st.max_k = v4[1];
@@ -77,7 +77,7 @@ __device__ __forceinline__ void decide_particle(PartState& st, const PartPass& q
     } else if (q.last) {
         const int ok = q.last_ok_by_norm ? (norm_ok ? 1 : 0) : 1;
         st.n_sub_ok += ok;
-        if (!(ok && q.chain)) { st.latched = 1; st.ok = ok; st.k_exit = q.k; }      // a chained success just goes on
+        if (!(ok && q.chain && allow_chain)) { st.latched = 1; st.ok = ok; st.k_exit = q.k; }   // a chained success just goes on
     }
 }
 __device__ __forceinline__ void apply_decision(Ctrl* c, const PassParams& pass, const double* v) {

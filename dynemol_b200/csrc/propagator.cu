@@ -95,7 +95,7 @@ struct dyb_ctx {
     int series_kind = DYB_SERIES_AUTO;   // how a series is launched: per term, streaming cooperative kernel, smem-resident kernel
     int res_Gd = 0, res_Bs = 0, res_ldS = 0;     // resident.cuh: grid side, block size, smem column stride (0: does not fit)
     size_t res_smem = 0;
-    double *res_pk = nullptr, *res_pb = nullptr, *res_dscal = nullptr;
+    double *res_pk = nullptr, *res_pb = nullptr, *res_dscal = nullptr, *res_psi = nullptr;
     int blk_Gd = 0, blk_Bs = 0, blk_ldS = 0, blk_Cc = 0;    // blocked.cuh: streamed 2-D blocks for mid-size operators (0: not applicable)
     size_t blk_smem = 0;
     double *blk_pk = nullptr, *blk_pb = nullptr, *blk_dscal = nullptr, *blk_prv = nullptr, *blk_sum = nullptr, *blk_mag = nullptr;
@@ -433,7 +433,7 @@ static int run_series_resident(dyb_ctx* c, const std::vector<PassParams>& passes
     memset(&R, 0, sizeof R);
     R.H = c->H; R.ld = c->ld; R.N = c->N; R.Gd = c->res_Gd; R.Bs = c->res_Bs; R.ldS = c->res_ldS;
     R.x0k = c->vk[0]; R.x0b = c->vb[0]; R.sum_b = c->sum_b; R.sum_k = c->sum_k;
-    R.pk = c->res_pk; R.pb = c->res_pb; R.dscal = c->res_dscal;
+    R.pk = c->res_pk; R.pb = c->res_pb; R.dscal = c->res_dscal; R.psi_store = reinterpret_cast<double2*>(c->res_psi);
     R.ctrl = c->ctrl; R.passes = c->d_passes; R.n_steps = n; R.gbar = c->gbar;
 #ifdef DYB_SERIES_PROF
     static long long* d_rprof = nullptr;
@@ -888,6 +888,7 @@ int dyb_destroy(dyb_ctx* c) {
     if (c->res_pk) cudaFree(c->res_pk);
     if (c->res_pb) cudaFree(c->res_pb);
     if (c->res_dscal) cudaFree(c->res_dscal);
+    if (c->res_psi) cudaFree(c->res_psi);
     if (c->h_ctrl) cudaFreeHost(c->h_ctrl);
     if (c->h_scal) cudaFreeHost(c->h_scal);
     for (auto e : c->ev) cudaEventDestroy(e);
@@ -957,6 +958,7 @@ int dyb_create(dyb_ctx** out, int device, int N, int row0, int n_rows) {
             CKCU(cudaFuncSetAttribute(resident_series_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RES_SMEM_MAX));
             CKC(alloc_zero(&c->res_pk, (size_t)2 * Gd * Gd * Bs * NQ)); CKC(alloc_zero(&c->res_pb, (size_t)2 * Gd * Gd * Bs * NQ));
             CKC(alloc_zero(&c->res_dscal, (size_t)2 * Gd * 8));
+            CKC(alloc_zero(&c->res_psi, (size_t)Gd * Gd * RES_THREADS * 2));
         }
     }
     if (row0 == 0 && n_rows == N && c->res_Gd == 0) {     // blocked.cuh: mid-size operators

@@ -40,6 +40,7 @@ struct ResidentParams {
     double* sum_b; double* sum_k;         // in: series sums at the start; out: at the latch / end of the series
     double* pk; double* pb;               // [2][Gd][Gd][Bs][NQ] partial products (parity of the term first)
     double* dscal;                        // [2][Gd][8] scalars of the diagonal CTAs
+    double2* psi_store;                   // [grid][RES_THREADS] start vector of the sub-step in progress (needed only after a failure)
     Ctrl* ctrl;
     const PassParams* passes; int n_steps;
     unsigned long long* gbar;             // grid barrier counter (zeroed before the launch)
@@ -133,11 +134,13 @@ resident_series_kernel(const ResidentParams R)
     const bool slot = (te < Bs);                                 // owns a (possibly padding) entry of the block
     const bool task = slot && (tn < N);
     double2 cur = make_double2(0.0, 0.0), prv = make_double2(0.0, 0.0), sum = make_double2(0.0, 0.0);
-    double2 psi = make_double2(0.0, 0.0);                        // start vector of the sub-step in progress (chained sub-steps)
+    // start vector of the sub-step in progress (chained sub-steps): only a failed norm test needs it back, so it is
+    // parked in global memory (one fire-and-forget store per sub-step) instead of occupying registers
+    double2* const psi_slot = R.psi_store + (size_t)blockIdx.x * RES_THREADS + tid;
     if (task) {
         cur = *reinterpret_cast<const double2*>((side ? R.x0b : R.x0k) + (size_t)tn * NQ + 2 * tp);
         sum = *reinterpret_cast<const double2*>((side ? R.sum_b : R.sum_k) + (size_t)tn * NQ + 2 * tp);
-        psi = cur;
+        __stcg(psi_slot, cur);
     }
     bool was_active = false;                                     // set below from the control block: only particles that take
                                                                  // part in this launch hand a vector back
@@ -193,6 +196,7 @@ resident_series_kernel(const ResidentParams R)
         DYB_RSTAMP(1);
         if (slot) {                                              // fixed order over the NG groups; this thread: one particle
             double2 v = make_double2(0.0, 0.0);
+#pragma unroll 5
             for (int gg = 0; gg < NG; ++gg) {
                 const double2 p0 = *reinterpret_cast<const double2*>(part + ((size_t)(side * NG + gg) * Bs + te) * NQ + 2 * tp);
                 v.x += p0.x; v.y += p0.y;
@@ -239,10 +243,8 @@ resident_series_kernel(const ResidentParams R)
         __syncthreads();
         if (t > 0) {                                             // one thread per particle, in different warps
             if (tid == 0 || tid == 32) {
-                const int p = tid >> 5;
-                PartPass q = spass[(t - 1) & 1].part[p];
-                if (stop_chain) q.chain = 0;                     // flag as of the previous term: the same in every CTA
-                decide_particle(sctrl.part[p], q, fin + 4 * p);
+                const int p = tid >> 5;                          // stop_chain as of the previous term: the same in every CTA
+                decide_particle(sctrl.part[p], spass[(t - 1) & 1].part[p], fin + 4 * p, !stop_chain);
             }
             __syncthreads();
             if (sctrl.part[0].latched && sctrl.part[1].latched) { decided_all = true; break; }
@@ -257,7 +259,7 @@ resident_series_kernel(const ResidentParams R)
             const PartPass& pa = spass[t & 1].part[tp];
             if (pa.active && !sctrl.part[tp].latched) {
                 if (pa.begin) {                                  // next steady sub-step: adopt the previous sum (Taylor.f:105,
-                    psi = sum; cur = sum;                        // :83-86); hx was computed from it (xout of the last term)
+                    __stcg(psi_slot, sum); cur = sum;            // :83-86); hx was computed from it (xout of the last term)
                     const Cx s0 = cmul({pa.s_re, pa.s_im}, {sum.x, sum.y});
                     sum = make_double2(s0.re, s0.im);
                 }
@@ -309,8 +311,12 @@ resident_series_kernel(const ResidentParams R)
             }
             __syncthreads();
             if (tid < 8) {
-                double f = wred[0][tid];
-                for (int w2 = 1; w2 < RES_HALF / 32; ++w2) f = ((tid & 3) < 2) ? fmax(f, wred[w2][tid]) : f + wred[w2][tid];
+                double wv[RES_HALF / 32];                        // all loads first: one shared-memory latency, not ten
+#pragma unroll
+                for (int w2 = 0; w2 < RES_HALF / 32; ++w2) wv[w2] = wred[w2][tid];
+                double f = wv[0];
+#pragma unroll
+                for (int w2 = 1; w2 < RES_HALF / 32; ++w2) f = ((tid & 3) < 2) ? fmax(f, wv[w2]) : f + wv[w2];
                 if ((tid & 3) < 2) f = sqrt(f);
                 __stcg(R.dscal + ((size_t)(t & 1) * Gd + bi) * 8 + tid, f);
             }
@@ -339,7 +345,7 @@ resident_series_kernel(const ResidentParams R)
     // a particle that failed a steady sub-step hands back the start vector of that sub-step (= the last accepted sum)
     if (diag && task && was_active)
         *reinterpret_cast<double2*>((side ? R.sum_b : R.sum_k) + (size_t)tn * NQ + 2 * tp) =
-            (sctrl.part[tp].latched && !sctrl.part[tp].ok) ? psi : sum;
+            (sctrl.part[tp].latched && !sctrl.part[tp].ok) ? __ldcg(psi_slot) : sum;
     if (blockIdx.x == 0 && tid == 0) {
         sctrl.all_latched = (sctrl.part[0].latched && sctrl.part[1].latched) ? 1 : 0;
         sctrl.block_counter = 0u;
