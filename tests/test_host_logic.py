@@ -89,3 +89,18 @@ def test_resident_plan_blocking():
     p = api.resident_plan(900, sm_count=64)
     assert p["grid_side"] == 8 and p["block"] == 113 and p["fits"] == 1
     assert api.resident_plan(1824, sm_count=64)["fits"] == 0
+
+
+def test_blocked_plan_blocking():
+    """Host arithmetic of the streamed 2-D block series kernel (csrc/blocked.cuh, opt-in): full 12 x 12 grid, blocks of
+    64..512 rows, three chunk stages + vector blocks + partial buffers within the opt-in shared memory."""
+    from dynemol_b200 import api
+    for N in (768, 1000, 1825, 2048, 3000, 4096, 5000, 6144):
+        p = api.blocked_plan(N)
+        assert p["fits"] == 1, N
+        assert p["grid_side"] == 12 and p["grid_side"] * p["block"] >= N and (p["grid_side"] - 1) * p["block"] < N
+        assert 64 <= p["block"] <= 512 and p["smem_stride"] % 2 == 1
+        assert 8 <= p["chunk_cols"] <= 64 and p["smem_bytes"] <= 227 * 1024 - 2048
+        assert 3 * p["chunk_cols"] * p["smem_stride"] * 8 < p["smem_bytes"]
+    for N in (100, 700, 6145, 16384):
+        assert api.blocked_plan(N)["fits"] == 0
