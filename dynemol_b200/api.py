@@ -75,7 +75,7 @@ lib = _load()
 DECLARED_SYMBOLS = [
     "propagationelhl_gpucaller_", "propagationelhl2_gpucaller_", "propagation_gpucaller_", "nakedbessel_", "ehrenfestkernel_gpu_",
     "gpu_init_", "gpu_finalize_", "gpu_pin_", "gpu_unpin_",
-    "dyb_last_error", "dyb_version", "dyb_device_count", "dyb_plan", "dyb_resident_plan", "dyb_blocked_plan", "dyb_create", "dyb_destroy", "dyb_set_kernel", "dyb_set_series_kernel",
+    "dyb_last_error", "dyb_version", "dyb_device_count", "dyb_plan", "dyb_resident_plan", "dyb_blocked_plan", "dyb_steady_schedule", "dyb_create", "dyb_destroy", "dyb_set_kernel", "dyb_set_series_kernel",
     "dyb_get_info", "dyb_upload_hprime", "dyb_upload_hprime_device", "dyb_upload_hprime_rows_device", "dyb_hprime_device", "dyb_form_hprime", "dyb_form_hprime_device", "dyb_form_hprime_from_overlap",
     "dyb_download_hprime", "dyb_set_packets", "dyb_get_packets", "dyb_propagate", "dyb_ao_bra",
     "dyb_populations", "dyb_run_terms", "dyb_dual_matvec", "dyb_sync", "dyb_launch_count",
@@ -131,6 +131,16 @@ def blocked_plan(N: int, sm_count: int = 148, smem_optin: int = 232448) -> dict:
     out = (C.c_int64 * 6)()
     _check(lib.dyb_blocked_plan(C.c_int(N), C.c_int(sm_count), C.c_int64(smem_optin), out))
     return dict(zip(["grid_side", "block", "smem_stride", "smem_bytes", "chunk_cols", "fits"], [int(v) for v in out]))
+
+
+def steady_schedule(t: float, t_max: float, tau: float, max_sub: int = 4096) -> np.ndarray:
+    """tau of every remaining steady sub-step (Taylor.f:81-126) if all norm tests pass; host arithmetic only."""
+    out = np.zeros(max_sub)
+    lib.dyb_steady_schedule.restype = C.c_int
+    n = lib.dyb_steady_schedule(C.c_double(t), C.c_double(t_max), C.c_double(tau), C.c_int(max_sub), _p(out))
+    if n < 0:
+        raise ValueError("dyb_steady_schedule: bad argument")
+    return out[:n].copy()
 
 
 def device_count() -> int:

@@ -588,6 +588,19 @@ static void fill_pass(PartPass& a, const Particle& q, int mode, int s, double eb
     }
 }
 
+// The steady loop of Taylor.f:81-126 when every norm test passes: the tau of each remaining sub-step, computed with the
+// very operations the state machine performs (t += tau*h_bar ; a last, shorter sub-step when less than one tau is
+// left, :116-121).  Host arithmetic only (exported as dyb_steady_schedule for the CPU tests).
+static std::vector<double> steady_schedule(double t, double t_max, double tau, int max_sub) {
+    std::vector<double> taus;
+    while (t < t_max && (int)taus.size() < max_sub) {
+        taus.push_back(tau);
+        t += tau * H_BAR;                                         // Taylor.f:116
+        if (t_max - t < tau * H_BAR) tau = (t_max - t) / H_BAR;   // Taylor.f:118-121
+    }
+    return taus;
+}
+
 // Propagation(): Taylor.f:35-127 (identical control flow in Chebyshev_gpu.cpp:347-485), one state machine per
 // particle, all particles served by the same passes over H'.  Host decisions are taken once per series from
 // the device-side control block; per-term decisions (early exit of Convergence) are taken on the device.
@@ -645,9 +658,10 @@ static int propagate_series(dyb_ctx* c, int mode, double t_init, double t_max, c
                 Particle sim = P[p];
                 size_t pos = 0;
                 int n_sub = 0;
-                while (sim.t < t_max) {
-                    const int nt = sim.k_ref - 1;
-                    if (nt < 1 || pos + nt > (size_t)MAX_CHAIN_PASSES) break;
+                const int nt = sim.k_ref - 1;                     // k_ref stays (Taylor.f:118-121 only recomputes the coefficients)
+                const int cap = nt >= 1 ? MAX_CHAIN_PASSES / nt : 0;
+                for (const double tau_s : steady_schedule(sim.t, t_max, sim.tau, cap)) {
+                    if (tau_s != sim.tau) { sim.tau = tau_s; coefficient(sim); }
                     if (passes.size() < pos + nt) {
                         const size_t old_n = passes.size();
                         passes.resize(pos + nt);
@@ -662,11 +676,6 @@ static int propagate_series(dyb_ctx* c, int mode, double t_init, double t_max, c
                         passes[pos - 1].part[p].chain = 1;
                     }
                     pos += nt; ++n_sub;
-                    sim.t += sim.tau * H_BAR;                     // Taylor.f:116
-                    if (t_max - sim.t < sim.tau * H_BAR) {        // Taylor.f:118-121
-                        sim.tau = (t_max - sim.t) / H_BAR;
-                        coefficient(sim);
-                    }
                 }
                 if (n_sub == 0) return fail(DYB_EINVAL, "steady sub-step of %d terms does not fit a launch", sim.k_ref - 1);
             }
@@ -857,6 +866,14 @@ int dyb_resident_plan(int N, int sm_count, int64_t smem_optin, int64_t* out6) {
     const ResidentPlan r = make_resident_plan(N, sm_count, (size_t)smem_optin, 2048);
     out6[0] = r.Gd; out6[1] = r.Bs; out6[2] = r.ldS; out6[3] = (int64_t)r.smem; out6[4] = RES_THREADS; out6[5] = r.fits ? 1 : 0;
     return DYB_OK;
+}
+
+// Host-only: tau of every remaining steady sub-step of one particle (see steady_schedule above).  Returns the count.
+int dyb_steady_schedule(double t, double t_max, double tau, int max_sub, double* out_tau) {
+    if (max_sub < 0 || (max_sub > 0 && !out_tau)) return -1;
+    const std::vector<double> v = steady_schedule(t, t_max, tau, max_sub);
+    for (size_t i = 0; i < v.size(); ++i) out_tau[i] = v[i];
+    return (int)v.size();
 }
 
 int dyb_device_count(void) {

@@ -134,6 +134,11 @@ int  dyb_resident_plan(int N, int sm_count, int64_t smem_optin_bytes, int64_t* o
  * dynamic smem bytes, chunk columns, fits (0/1)}. */
 int  dyb_blocked_plan(int N, int sm_count, int64_t smem_optin_bytes, int64_t* out6);
 
+/* Host-only: the tau of every remaining sub-step of the steady loop (Taylor.f:81-126: t += tau*h_bar, a last shorter
+ * sub-step when less than one tau is left) assuming every norm test passes -- the schedule the library predicts when it
+ * chains the sub-steps of a small operator into one launch.  Returns the number of sub-steps written (<= max_sub). */
+int  dyb_steady_schedule(double t, double t_max, double tau, int max_sub, double* out_tau);
+
 /* One context = one GPU, one basis size.  n_rows/row0 select a row shard of H'
  * (single GPU: row0 = 0, n_rows = N).  The context owns all device buffers. */
 int  dyb_create(dyb_ctx** out, int device, int N, int row0, int n_rows);

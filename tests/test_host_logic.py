@@ -104,3 +104,45 @@ def test_blocked_plan_blocking():
         assert 3 * p["chunk_cols"] * p["smem_stride"] * 8 < p["smem_bytes"]
     for N in (100, 700, 6145, 16384):
         assert api.blocked_plan(N)["fits"] == 0
+
+
+@pytest.mark.parametrize("name", ["prop_N64_dt5e-6", "prop_N128_dt2e-5", "cheb_N64_dt5e-4", "cheb_N128_dt5e-5"])
+def test_steady_schedule_matches_oracle_traces(golden_dir, name):
+    """dyb_steady_schedule (the sub-step schedule the library predicts when it chains the steady loop of Taylor.f:81-126
+    into one launch) against the tau the oracle recorded for every steady sub-step of the golden runs: after the first
+    successful Convergence() (Taylor.f:65-78), as long as no norm test fails, the sequences must be identical."""
+    import os
+    from dynemol_b200 import api
+    H_BAR = 6.58264e-4
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    t_init, t_max = float(g["t_init"]), float(g["t_max"])
+    checked = 0
+    for tag in ("el", "hl"):
+        ev = g[f"{tag}_events"]; etau = g[f"{tag}_event_tau"]
+        i0 = next(i for i in range(len(ev)) if ev[i, 0] == 1 and ev[i, 2] == 1)        # first Convergence that succeeded
+        tau = float(etau[i0])
+        t = t_init + tau * H_BAR                                                      # Taylor.f:73
+        if t_max - t < tau * H_BAR:                                                   # Taylor.f:75-78
+            tau = (t_max - t) / H_BAR
+        steady = []
+        for i in range(i0 + 1, len(ev)):
+            if ev[i, 0] != 2 or ev[i, 2] != 1:
+                break
+            steady.append(float(etau[i]))
+        complete = (i0 + 1 + len(steady) == len(ev))                                  # no failure until the end of the step
+        pred = api.steady_schedule(t, t_max, tau)
+        assert len(pred) >= len(steady)
+        assert np.array_equal(pred[: len(steady)], np.array(steady)), (tag, pred[:4], steady[:4])
+        if complete and len(ev) < 256:                                                # (the trace keeps 256 events)
+            assert len(pred) == len(steady)
+        checked += len(steady)
+    assert checked > 0
+
+
+def test_steady_schedule_edges():
+    from dynemol_b200 import api
+    H_BAR = 6.58264e-4
+    assert len(api.steady_schedule(1.0, 1.0, 0.1)) == 0                               # t == t_max: nothing left (Taylor.f:81)
+    s = api.steady_schedule(0.0, 10 * 0.01 * H_BAR, 0.01)
+    assert 10 <= len(s) <= 11 and np.all(s[:9] == 0.01) and s.sum() * H_BAR == pytest.approx(10 * 0.01 * H_BAR, rel=1e-12)
+    assert len(api.steady_schedule(0.0, 1.0, 1e-3, max_sub=7)) == 7                    # capped
