@@ -75,7 +75,7 @@ lib = _load()
 DECLARED_SYMBOLS = [
     "propagationelhl_gpucaller_", "propagationelhl2_gpucaller_", "propagation_gpucaller_", "nakedbessel_", "ehrenfestkernel_gpu_",
     "gpu_init_", "gpu_finalize_", "gpu_pin_", "gpu_unpin_",
-    "dyb_last_error", "dyb_version", "dyb_device_count", "dyb_plan", "dyb_resident_plan", "dyb_blocked_plan", "dyb_steady_schedule", "dyb_create", "dyb_destroy", "dyb_set_kernel", "dyb_set_series_kernel",
+    "dyb_last_error", "dyb_version", "dyb_device_count", "dyb_plan", "dyb_resident_plan", "dyb_blocked_plan", "dyb_steady_schedule", "dyb_series_coefficients", "dyb_create", "dyb_destroy", "dyb_set_kernel", "dyb_set_series_kernel",
     "dyb_get_info", "dyb_upload_hprime", "dyb_upload_hprime_device", "dyb_upload_hprime_rows_device", "dyb_hprime_device", "dyb_form_hprime", "dyb_form_hprime_device", "dyb_form_hprime_from_overlap",
     "dyb_download_hprime", "dyb_set_packets", "dyb_get_packets", "dyb_propagate", "dyb_ao_bra",
     "dyb_populations", "dyb_run_terms", "dyb_dual_matvec", "dyb_sync", "dyb_launch_count",
@@ -141,6 +141,13 @@ def steady_schedule(t: float, t_max: float, tau: float, max_sub: int = 4096) -> 
     if n < 0:
         raise ValueError("dyb_steady_schedule: bad argument")
     return out[:n].copy()
+
+
+def series_coefficients(mode: int, tau: float, ebar: float = 0.0, de: float = 1.0):
+    """(C[25], k_max) the library uses for this tau (host arithmetic only)."""
+    out = np.zeros(25, dtype=np.complex128); km = C.c_int(0)
+    _check(lib.dyb_series_coefficients(C.c_int(mode), C.c_double(tau), C.c_double(ebar), C.c_double(de), _p(out), C.byref(km)))
+    return out, km.value
 
 
 def device_count() -> int:

@@ -868,6 +868,22 @@ int dyb_resident_plan(int N, int sm_count, int64_t smem_optin, int64_t* out6) {
     return DYB_OK;
 }
 
+// Host-only: the 25 series coefficients the library uses for a given tau and the number of terms k_max it would sum
+// (Taylor.f:224-239 + :165-171 ; Chebyshev_gpu.cpp:636-643 + :565-574 on the interval ebar +- de).  For the CPU tests.
+int dyb_series_coefficients(int mode, double tau, double ebar, double de, dyb_complex* out25, int* k_max) {
+    if (!out25 || (mode != DYB_MODE_TAYLOR && mode != DYB_MODE_CHEBYSHEV)) return fail(DYB_EINVAL, "bad argument");
+    cplx C[ORDER];
+    int km;
+    if (mode == DYB_MODE_TAYLOR) { taylor_coefficient(tau, C); km = taylor_kmax(C); }
+    else {
+        if (!(de > 0.0)) return fail(DYB_EINVAL, "Chebyshev mode needs a spectral half width de > 0");
+        cheb_coefficient(tau, ebar, de, C); km = cheb_kmax(C, de * tau);
+    }
+    for (int k = 0; k < ORDER; ++k) { out25[k].re = C[k].real(); out25[k].im = C[k].imag(); }
+    if (k_max) *k_max = km;
+    return DYB_OK;
+}
+
 // Host-only: tau of every remaining steady sub-step of one particle (see steady_schedule above).  Returns the count.
 int dyb_steady_schedule(double t, double t_max, double tau, int max_sub, double* out_tau) {
     if (max_sub < 0 || (max_sub > 0 && !out_tau)) return -1;

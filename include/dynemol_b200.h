@@ -138,6 +138,10 @@ int  dyb_blocked_plan(int N, int sm_count, int64_t smem_optin_bytes, int64_t* ou
  * sub-step when less than one tau is left) assuming every norm test passes -- the schedule the library predicts when it
  * chains the sub-steps of a small operator into one launch.  Returns the number of sub-steps written (<= max_sub). */
 int  dyb_steady_schedule(double t, double t_max, double tau, int max_sub, double* out_tau);
+/* Host-only: the 25 series coefficients for a given tau and the number of terms the series would use.
+ * DYB_MODE_TAYLOR: coefficient() of Taylor.f:224-239, k_max rule of :165-171.  DYB_MODE_CHEBYSHEV: Chebyshev_gpu.cpp:636-643
+ * with R = de*tau and the phase of the spectral shift, k_max rule of :565-574. */
+int  dyb_series_coefficients(int mode, double tau, double ebar, double de, dyb_complex* out25, int* k_max);
 
 /* One context = one GPU, one basis size.  n_rows/row0 select a row shard of H'
  * (single GPU: row0 = 0, n_rows = N).  The context owns all device buffers. */

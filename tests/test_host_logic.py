@@ -146,3 +146,31 @@ def test_steady_schedule_edges():
     s = api.steady_schedule(0.0, 10 * 0.01 * H_BAR, 0.01)
     assert 10 <= len(s) <= 11 and np.all(s[:9] == 0.01) and s.sum() * H_BAR == pytest.approx(10 * 0.01 * H_BAR, rel=1e-12)
     assert len(api.steady_schedule(0.0, 1.0, 1e-3, max_sub=7)) == 7                    # capped
+
+
+def test_series_coefficients_match_oracle(oracle_mod):
+    """The coefficient tables and k_max rules of the library's host logic (dyb_series_coefficients) against the oracle
+    (Taylor.f:224-239, :165-171; Chebyshev_gpu.cpp:636-643, :565-574 with the spectral rescaling) and the independent
+    numpy transcription."""
+    from dynemol_b200 import api
+    from oracle import taylor_numpy as tn
+    for tau in (1e-6, 7.6e-5, 3.0e-3, 0.03, 0.76):
+        C, km = api.series_coefficients(api.MODE_TAYLOR, tau)
+        ref = oracle_mod.coefficient(tau)
+        assert np.array_equal(C, ref) or np.abs(C - ref).max() <= 1e-16 * np.abs(ref).max()
+        assert np.abs(C - tn.coefficient(tau)).max() <= 1e-16
+        small = np.nonzero(np.abs(ref[1:]) < 1.0e-16)[0]
+        assert km == (int(small[0]) + 2 if small.size else 25)                         # Taylor.f:165-171
+    for tau, ebar, de in ((0.076, 480.0, 560.0), (0.76, 500.0, 520.0), (7.6e-3, 10.0, 30.0)):
+        C, km = api.series_coefficients(api.MODE_CHEBYSHEV, tau, ebar, de)
+        ref = oracle_mod.cheb_scaled_coefficient(tau, ebar, de)
+        assert np.abs(C - ref).max() <= 4e-16 and np.abs(C - tn.cheb_coefficient(tau, ebar, de)).max() <= 4e-16
+        R = de * tau
+        want = 25
+        for k in range(6, 25):                                                         # Chebyshev_gpu.cpp:565-574
+            if abs(ref[k] * oracle_mod.naked_bessel(k, R)) < 1.0e-20:
+                want = k
+                break
+        assert km == want
+    with pytest.raises(Exception):
+        api.series_coefficients(api.MODE_CHEBYSHEV, 0.1, 0.0, 0.0)
