@@ -367,6 +367,7 @@ def run_e2e_legacy(args, N, Psi_bra, Psi_ket, host_Sh):
 def cpu_baseline(Hp_np, Psi_bra, Psi_ket, tau, budget_s=15.0):
     import oracle                                                    # the checker, timed as the CPU baseline only
     oracle.build()
+    oracle.use_all_host_threads()
     N = Hp_np.shape[0]
     t0 = time.perf_counter(); oracle.terms(Hp_np, Psi_bra, Psi_ket, tau, 2); t2 = time.perf_counter() - t0
     n = int(max(2, min(200, budget_s / max(t2 / 2, 1e-6))))
@@ -384,6 +385,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    oracle.use_all_host_threads()            # torchrun exports OMP_NUM_THREADS=1 to its workers; the other ranks are idle here
     N = args.basis or (16384 if args.gpus == 1 else 65536)
     N_run = min(N, 16384)                    # host RAM / time bound: the CPU rate per byte does not depend on N
     rng = np.random.default_rng(1)

@@ -273,6 +273,17 @@ def num_threads() -> int:
     return lib().orc_num_threads()
 
 
+def use_all_host_threads() -> int:
+    """Make the OpenMP loops of the oracle use every core this process may run on, whatever OMP_NUM_THREADS says
+    (torchrun exports OMP_NUM_THREADS=1 to its workers).  Returns the thread count now in effect."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().orc_set_num_threads(C.c_int(n))
+    return num_threads()
+
+
 # --------------------------------------------------------------------------- the real reference, where it compiles
 def _openblas_path():
     import scipy
