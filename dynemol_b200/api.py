@@ -73,14 +73,14 @@ lib = _load()
 
 # every symbol include/dynemol_b200.h declares (checked by the CPU test-suite)
 DECLARED_SYMBOLS = [
-    "propagationelhl_gpucaller_", "propagationelhl2_gpucaller_", "propagation_gpucaller_", "nakedbessel_", "ehrenfestkernel_gpu_",
+    "propagationelhl_gpucaller_", "propagationelhl2_gpucaller_", "propagation_gpucaller_", "nakedbessel_", "ehrenfestkernel_gpu_", "ehrenfestkernel2_gpu_",
     "gpu_init_", "gpu_finalize_", "gpu_pin_", "gpu_unpin_",
     "dyb_last_error", "dyb_version", "dyb_device_count", "dyb_plan", "dyb_resident_plan", "dyb_blocked_plan", "dyb_steady_schedule", "dyb_series_coefficients", "dyb_create", "dyb_destroy", "dyb_set_kernel", "dyb_set_series_kernel",
     "dyb_get_info", "dyb_upload_hprime", "dyb_upload_hprime_device", "dyb_upload_hprime_rows_device", "dyb_hprime_device", "dyb_form_hprime", "dyb_form_hprime_device", "dyb_form_hprime_from_overlap",
     "dyb_download_hprime", "dyb_set_packets", "dyb_get_packets", "dyb_propagate", "dyb_ao_bra",
     "dyb_populations", "dyb_run_terms", "dyb_dual_matvec", "dyb_sync", "dyb_launch_count",
     "dyb_comm_unique_id", "dyb_comm_init", "dyb_comm_p2p_handle", "dyb_comm_p2p_open", "dyb_comm_p2p_enable", "dyb_set_spectral_bounds", "dyb_get_spectral_bounds", "dyb_estimate_spectral_bounds",
-    "dyb_quasiparticle_energies", "dyb_ehrenfest_kernel",
+    "dyb_quasiparticle_energies", "dyb_ehrenfest_kernel", "dyb_ehrenfest_kernel2",
 ]
 
 
@@ -377,6 +377,15 @@ def legacy_ehrenfestkernel(H, A, X):
     H = _fd(H); A = _fd(A); X = _fd(X); N = H.shape[0]
     K = np.empty((N, N), dtype=np.float64, order="F")
     lib.ehrenfestkernel_gpu_(C.byref(C.c_int(N)), _p(H), _p(A), _p(X), _p(K))
+    return K
+
+
+def legacy_ehrenfestkernel2(bra, ket, H, X):
+    """ehrenfestkernel2_gpu_(N, bra, ket, H_prime, X_ij, Kernel) -- Taylor_gpu.cpp:801-873; bra, ket: (N, 2) complex AO packets."""
+    H = _fd(H); X = _fd(X); bra = _fz(bra); ket = _fz(ket); N = H.shape[0]
+    assert bra.shape == (N, 2) and ket.shape == (N, 2)
+    K = np.empty((N, N), dtype=np.float64, order="F")
+    lib.ehrenfestkernel2_gpu_(C.byref(C.c_int(N)), _p(bra), _p(ket), _p(H), _p(X), _p(K))
     return K
 
 

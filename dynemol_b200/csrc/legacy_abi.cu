@@ -102,6 +102,15 @@ void ehrenfestkernel_gpu_(const int* N, const double* h_H, const double* h_A, co
     LCK(dyb_ehrenfest_kernel(c, h_A, h_X, h_K), "dyb_ehrenfest_kernel");
 }
 
+// Taylor_gpu.cpp:801-873 (no caller in the reference tree): the same kernel from the AO packets, the density matrix
+// rho / A being formed on the device
+void ehrenfestkernel2_gpu_(const int* N, const dyb_complex* h_bra, const dyb_complex* h_ket, const double* h_H, const double* h_X, double* h_K)
+{
+    dyb_ctx* c = ctx_for(*N);
+    LCK(dyb_upload_hprime(c, h_H, *N), "dyb_upload_hprime");
+    LCK(dyb_ehrenfest_kernel2(c, h_bra, h_ket, h_X, h_K), "dyb_ehrenfest_kernel2");
+}
+
 // Chebyshev_gpu.cpp:517:  2^(n-2) * (x^2 + 4) / x^n
 double nakedbessel_(const int* n, const double* x)
 {

@@ -1694,6 +1694,48 @@ int dyb_ehrenfest_kernel(dyb_ctx* c, const double* h_A, const double* h_X, doubl
     return rc;
 }
 
+// The same kernel with the electron-hole density built on the device (Taylor_gpu.cpp:801-873 ehrenfestkernel2_gpu_,
+// Chebyshev_gpu_kernels.cu:395-455 calculate_A; on the host: calculate_rho + A_ad_nd of diabatic-Ehren.f:107-109):
+//   rho(i,j) = Re{ ket(j,1) bra(i,1) } - Re{ ket(j,2) bra(i,2) } ,  A = (rho + rho^T)/2 ,  K = X o A - H' A.
+// bra/ket are the N x 2 complex AO packets (column 1 electron, column 2 hole); only 64 N bytes cross PCIe instead of 8 N^2.
+__global__ void ehrenfest_density_kernel(int n, const double2* __restrict__ bra, const double2* __restrict__ ket, double* __restrict__ A) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * n) return;
+    const int i = (int)(idx % n), j = (int)(idx / n);
+    const double2 bi0 = bra[i], bi1 = bra[n + i], bj0 = bra[j], bj1 = bra[n + j];
+    const double2 ki0 = ket[i], ki1 = ket[n + i], kj0 = ket[j], kj1 = ket[n + j];
+    const double rho_ij = (kj0.x * bi0.x - kj0.y * bi0.y) - (kj1.x * bi1.x - kj1.y * bi1.y);
+    const double rho_ji = (ki0.x * bj0.x - ki0.y * bj0.y) - (ki1.x * bj1.x - ki1.y * bj1.y);
+    A[idx] = 0.5 * (rho_ij + rho_ji);
+}
+
+int dyb_ehrenfest_kernel2(dyb_ctx* c, const dyb_complex* h_bra, const dyb_complex* h_ket, const double* h_X, double* h_K) {
+    if (!c || !h_bra || !h_ket || !h_X || !h_K) return fail(DYB_EINVAL, "NULL argument");
+    if (c->M != c->N) return fail(DYB_EINVAL, "full-matrix contexts only");
+    CK(cudaSetDevice(c->device));
+    const size_t n = c->N, bytes = n * n * 8, vbytes = n * 2 * sizeof(dyb_complex);
+    DevScratch bA, bX, bK, bB, bKt;
+    CK(cudaMalloc(&bA.p, bytes)); CK(cudaMalloc(&bX.p, bytes)); CK(cudaMalloc(&bK.p, bytes));
+    CK(cudaMalloc(&bB.p, vbytes)); CK(cudaMalloc(&bKt.p, vbytes));
+    double *A = static_cast<double*>(bA.p), *X = static_cast<double*>(bX.p), *K = static_cast<double*>(bK.p);
+    int rc = DYB_OK;
+    do {
+        if (!c->blas) { if (cublasCreate(&c->blas) != CUBLAS_STATUS_SUCCESS || cublasSetStream(c->blas, c->stream) != CUBLAS_STATUS_SUCCESS) { rc = fail(DYB_ECUDA, "cublasCreate failed"); break; } }
+        if (cudaMemcpyAsync(bB.p, h_bra, vbytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+            cudaMemcpyAsync(bKt.p, h_ket, vbytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+            cudaMemcpyAsync(X, h_X, bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { rc = fail(DYB_ECUDA, "H2D of packets/X failed"); break; }
+        ehrenfest_density_kernel<<<(unsigned)((n * n + 255) / 256), 256, 0, c->stream>>>((int)n, static_cast<const double2*>(bB.p), static_cast<const double2*>(bKt.p), A);
+        c->launches++;
+        const double one = 1.0, zero = 0.0;
+        if (cublasDgemm(c->blas, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, (int)n, (int)n, &one, c->H, (int)c->ld, A, (int)n, &zero, K, (int)n) != CUBLAS_STATUS_SUCCESS) { rc = fail(DYB_ECUDA, "cublasDgemm failed"); break; }
+        hadamard_minus_kernel<<<(unsigned)((n * n + 255) / 256), 256, 0, c->stream>>>(n * n, X, A, K);
+        c->launches++;
+        if (cudaGetLastError() != cudaSuccess || cudaMemcpyAsync(h_K, K, bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = fail(DYB_ECUDA, "Ehrenfest kernel failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+    } while (0);
+    return rc;
+}
+
 int dyb_populations(dyb_ctx* c, int n_part, int n_frag, const int32_t* fragment, double t, double* out) {
     if (!c || !fragment || !out || n_part < 1 || n_part > 2 || n_frag < 0 || n_frag > MAX_FRAG) return fail(DYB_EINVAL, "bad argument");
     if (c->M != c->N) return fail(DYB_EINVAL, "full-matrix contexts only (row-sharded: gather the packets with dyb_get_packets)");

@@ -72,6 +72,11 @@ void propagation_gpucaller_(const int* n, double* tau, double* save_tau,
 /* Replaces Taylor_gpu.cpp:743-797 (called from diabatic-Ehren.f:115): K = X o A - H' A, all host N x N col-major. */
 void ehrenfestkernel_gpu_(const int* N, const double* h_H, const double* h_A, const double* h_X, double* h_K);
 
+/* Replaces Taylor_gpu.cpp:801-873 (exported by the reference, no Fortran caller): the same kernel from the AO packets
+ * bra, ket (N x 2 complex, column 1 electron, column 2 hole); rho(i,j) = Re{ket(j,1) bra(i,1)} - Re{ket(j,2) bra(i,2)},
+ * A = (rho + rho^T)/2 are formed on the device (calculate_rho / A_ad_nd of diabatic-Ehren.f:107-109). */
+void ehrenfestkernel2_gpu_(const int* N, const dyb_complex* h_bra, const dyb_complex* h_ket, const double* h_H, const double* h_X, double* h_K);
+
 /* Replaces Chebyshev_gpu.cpp:517-519. */
 double nakedbessel_(const int* n, const double* x);
 
@@ -207,6 +212,8 @@ int  dyb_quasiparticle_energies(dyb_ctx* ctx, int n_part, double* out_reim);
 /* Diabatic-Ehrenfest kernel K = X o A - H' A (diabatic-Ehren.f:115-119) with the H' resident in the context;
  * A, X, K host N x N col-major. */
 int  dyb_ehrenfest_kernel(dyb_ctx* ctx, const double* h_A, const double* h_X, double* h_K);
+/* same, with A built on the device from the AO packets (N x 2 complex each): ehrenfestkernel2_gpu_ with H' resident */
+int  dyb_ehrenfest_kernel2(dyb_ctx* ctx, const dyb_complex* h_bra, const dyb_complex* h_ket, const double* h_X, double* h_K);
 
 /* Raw recursion for benchmarks and kernel-level parity: run n_terms el+hole series
  * terms (one pass over H' each, fused epilogue, no host decisions) starting from the

@@ -55,6 +55,25 @@ def test_ehrenfest_kernel_matches_reference_formula(api):
     api.gpu_finalize()
 
 
+def test_ehrenfest_kernel2_builds_the_density_on_the_device(api):
+    """ehrenfestkernel2_gpu_ (Taylor_gpu.cpp:801-873): rho(i,j) = Re{ket(j,1) bra(i,1)} - Re{ket(j,2) bra(i,2)}
+    (calculate_rho, diabatic-Ehren.f:107), A = (rho + rho^T)/2, K = X o A - H' A -- from the AO packets alone."""
+    N = 320
+    w = syn.make_workload(N)
+    rng = np.random.default_rng(9)
+    bra = np.asfortranarray(rng.normal(size=(N, 2)) + 1j * rng.normal(size=(N, 2)))
+    ket = np.asfortranarray(rng.normal(size=(N, 2)) + 1j * rng.normal(size=(N, 2)))
+    X = np.asfortranarray(syn.x_matrix(w.IP, w.k_WH, w.V_shift))
+    Hp = np.asfortranarray(np.linalg.solve(w.S, w.h))
+    rho = np.real(np.outer(bra[:, 0], ket[:, 0])) - np.real(np.outer(bra[:, 1], ket[:, 1]))      # rho[i, j]
+    A = 0.5 * (rho + rho.T)
+    ref = X * A - Hp @ A
+    K2 = api.legacy_ehrenfestkernel2(bra, ket, Hp, X)
+    assert relerr(K2, ref) < 1e-12
+    assert relerr(K2, api.legacy_ehrenfestkernel(Hp, np.asfortranarray(A), X)) < 1e-13
+    api.gpu_finalize()
+
+
 def test_formation_lu_fallback_for_indefinite_overlap(api):
     """The reference factorises S with Bunch-Kaufman (CPU) or LU (GPU): an S that is symmetric but not positive
     definite must still give H' = S^-1 h (here: Cholesky fails -> LU with partial pivoting)."""
