@@ -232,3 +232,70 @@ def cheb_propagation(Hp, bra, ket, t_init, t_max, tau, ebar, de, log=None):
             tau = (t_max - t) / H_BAR
             C = cheb_coefficient(tau, ebar, de)
     return bra, ket, tau, save_tau
+
+
+# ----------------------------------------------------------------------------- the reference's GPU variant
+def gpu_variant_convergence(Hp, bra, ket, tau, norm_ref):
+    """Taylor_gpu.cpp:511-622 (convergence_gpu), transcribed: raw powers H^k psi, c_k applied in the update, one term
+    fewer than Taylor.f (k = 1..k_max-1 with k_max the first 0-based k whose |c_k| < 1e-16), term test = modulus of the
+    complex element that holds the largest |re| or |im| (cublasIdamax over 2n reals) < tol.
+    Returns (ok, bra, ket, C, k_ref)."""
+    C = coefficient(tau)
+    k_max = ORDER
+    for k in range(1, ORDER):
+        if abs(C[k]) < 1.0e-16:
+            k_max = k
+            break
+    pb, pk = bra, ket
+    old_b, old_k = bra, ket
+
+    def max_elem(d):
+        flat = np.abs(d.view(np.float64))
+        return abs(d[int(np.argmax(flat)) // 2])
+
+    for k in range(1, k_max):
+        pb = Hp.T @ pb
+        pk = Hp @ pk
+        new_b = old_b + C[k] * pb
+        new_k = old_k + C[k] * pk
+        if max_elem(new_b - old_b) < ERROR and max_elem(new_k - old_k) < ERROR:
+            if abs(abs(np.vdot(new_b, new_k)) - norm_ref) < NORM_ERROR:
+                return True, new_b, new_k, C, k_max
+        old_b, old_k = new_b, new_k
+    return False, bra, ket, C, k_max
+
+
+def gpu_variant_propagation(Hp, bra, ket, t_init, t_max, tau):
+    """Taylor_gpu.cpp:334-480 (chebyshev_gpu of the Taylor file).  Returns (bra, ket, tau, save_tau, n_rescale)."""
+    norm_ref = abs(np.vdot(bra, ket))
+    while True:
+        ok, bra, ket, C, k_ref = gpu_variant_convergence(Hp, bra, ket, tau, norm_ref)
+        if ok:
+            break
+        tau *= 0.9
+    save_tau = tau
+    t = t_init + tau * H_BAR
+    if t_max - t < tau * H_BAR:
+        tau = (t_max - t) / H_BAR
+        C = coefficient(tau)
+    n_rescale = 0
+    while t < t_max:
+        pb, pk = bra, ket
+        sb = C[0] * pb; sk = C[0] * pk
+        for k in range(1, k_ref):
+            pb = Hp.T @ pb
+            pk = Hp @ pk
+            sb = sb + C[k] * pb; sk = sk + C[k] * pk
+        if abs(abs(np.vdot(sb, sk)) - norm_ref) < NORM_ERROR:
+            bra, ket = sb, sk
+        else:
+            ok = False
+            while not ok:
+                tau *= 0.975
+                n_rescale += 1
+                ok, bra, ket, C, k_ref = gpu_variant_convergence(Hp, bra, ket, tau, norm_ref)
+        t += tau * H_BAR
+        if t_max - t < tau * H_BAR:
+            tau = (t_max - t) / H_BAR
+            C = coefficient(tau)
+    return bra, ket, tau, save_tau, n_rescale

@@ -78,3 +78,20 @@ def test_ehrenfest_kernel_against_reference_gpu(api, refgpu):
     Kr = refgpu.ref_gpu_ehrenfestkernel(H, A, X)
     Ko = api.legacy_ehrenfestkernel(H, A, X)
     assert relerr(Ko, Kr) < 1e-11
+
+
+def test_reference_gpu_algorithm_as_transcribed(refgpu):
+    """SURVEY.md Appendix B, checked against the reference itself: a line-by-line numpy transcription of the GPU variant
+    (oracle/taylor_numpy.py: gpu_variant_*; one term fewer, Idamax-based test, raw powers with c_k applied in the
+    update) reproduces what the reference's own binary does on the B200 -- same converged tau, wavepackets to rounding.
+    This is what separates "the product differs from the reference GPU path by design" from "by accident"."""
+    from oracle import taylor_numpy as tn
+    N, dt = 256, 5e-6
+    w = syn.make_workload(N)
+    Hp = refgpu.sy_multiply(refgpu.sy_invert(w.S), w.h)
+    tau0 = dt / H_BAR
+    for p in range(2):
+        rb, rk, r_save = refgpu.ref_gpu_propagation(Hp, w.Psi_bra[:, p], w.Psi_ket[:, p], 0.0, dt, tau0)
+        nb, nk, _, n_save, _ = tn.gpu_variant_propagation(Hp, w.Psi_bra[:, p].copy(), w.Psi_ket[:, p].copy(), 0.0, dt, tau0)
+        assert n_save == pytest.approx(r_save, rel=1e-14)
+        assert relerr(nb, rb) < 1e-11 and relerr(nk, rk) < 1e-11

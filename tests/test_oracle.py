@@ -215,3 +215,23 @@ def test_scaled_chebyshev_vs_numpy_and_expm(oracle_mod):
     ok, b1, k1, C1, kr1, kx1 = oracle_mod.cheb_convergence(Hp, w.Psi_bra[:, 0], w.Psi_ket[:, 0], tau, 1.0)
     b3, k3, _, _, tr3 = oracle_mod.cheb_scaled_propagation(Hp, w.Psi_bra[:, 0], w.Psi_ket[:, 0], 0.0, tau * tn.H_BAR, tau, 0.0, 1.0)
     assert ok and tr3.events()[0][1] == kx1 and np.array_equal(b1, b3) and np.array_equal(k1, k3)
+
+
+def test_gpu_variant_transcription_vs_cpu_variant(oracle_mod):
+    """SURVEY.md Appendix B in numbers: the numpy transcription of the reference's GPU variant (Taylor_gpu.cpp:334-622,
+    oracle/taylor_numpy.py gpu_variant_*; pinned against the reference's own binary on the GPU box by
+    tests/test_gpu_reference_gpu.py) and the CPU variant the product follows (Taylor.f) propagate the same packet to
+    the same state within the series tolerance, with different tau schedules (the GPU variant sums one term fewer and
+    settles on a smaller tau)."""
+    from oracle import taylor_numpy as tn
+    from dynemol_b200 import synthetic as syn
+    N, dt = 128, 5e-6
+    w = syn.make_workload(N)
+    Hp = oracle_mod.sy_multiply(oracle_mod.sy_invert(w.S), w.h)
+    tau0 = dt / tn.H_BAR
+    for p in range(2):
+        gb, gk, _, g_save, _ = tn.gpu_variant_propagation(Hp, w.Psi_bra[:, p].copy(), w.Psi_ket[:, p].copy(), 0.0, dt, tau0)
+        cb, ck, _, c_save, _ = oracle_mod.propagation(Hp, w.Psi_bra[:, p], w.Psi_ket[:, p], 0.0, dt, tau0)
+        assert np.abs(gb - cb).max() / np.abs(cb).max() < 2e-7 and np.abs(gk - ck).max() / np.abs(ck).max() < 2e-7
+        assert abs(abs(np.vdot(gb, gk)) - 1.0) < 1e-7
+        assert 0.0 < g_save <= c_save <= tau0
