@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DYNEMOL_B200_LIB") or os.path.join(_HERE, "lib", "libdynemol_b200.so")   # override: tuning builds
 
 H_BAR = 6.58264e-4          # eV*ps (constants_m.f:23)
-MODE_TAYLOR, MODE_CHEBYSHEV = 0, 1
+MODE_TAYLOR, MODE_CHEBYSHEV, MODE_TAYLOR_REFGPU, MODE_CHEBYSHEV_REFGPU = 0, 1, 2, 3
 KERNEL_AUTO, KERNEL_TMA, KERNEL_LDG = 0, 1, 2
 MAX_EVENTS = 256
 
@@ -75,7 +75,7 @@ lib = _load()
 DECLARED_SYMBOLS = [
     "propagationelhl_gpucaller_", "propagationelhl2_gpucaller_", "propagation_gpucaller_", "nakedbessel_", "ehrenfestkernel_gpu_", "ehrenfestkernel2_gpu_",
     "gpu_init_", "gpu_finalize_", "gpu_pin_", "gpu_unpin_",
-    "dyb_last_error", "dyb_version", "dyb_device_count", "dyb_plan", "dyb_resident_plan", "dyb_blocked_plan", "dyb_steady_schedule", "dyb_series_coefficients", "dyb_create", "dyb_destroy", "dyb_set_kernel", "dyb_set_series_kernel",
+    "dyb_last_error", "dyb_version", "dyb_device_count", "dyb_plan", "dyb_resident_plan", "dyb_steady_schedule", "dyb_series_coefficients", "dyb_create", "dyb_destroy", "dyb_set_kernel", "dyb_set_series_kernel",
     "dyb_get_info", "dyb_upload_hprime", "dyb_upload_hprime_device", "dyb_upload_hprime_rows_device", "dyb_hprime_device", "dyb_form_hprime", "dyb_form_hprime_device", "dyb_form_hprime_from_overlap",
     "dyb_download_hprime", "dyb_set_packets", "dyb_get_packets", "dyb_propagate", "dyb_ao_bra",
     "dyb_populations", "dyb_run_terms", "dyb_dual_matvec", "dyb_sync", "dyb_launch_count",
@@ -126,13 +126,6 @@ def resident_plan(N: int, sm_count: int = 148, smem_optin: int = 232448) -> dict
     return dict(zip(["grid_side", "block", "smem_stride", "smem_bytes", "threads", "fits"], [int(v) for v in out]))
 
 
-def blocked_plan(N: int, sm_count: int = 148, smem_optin: int = 232448) -> dict:
-    """Blocking of the streamed 2-D block series kernel (host arithmetic only, works without a GPU)."""
-    out = (C.c_int64 * 6)()
-    _check(lib.dyb_blocked_plan(C.c_int(N), C.c_int(sm_count), C.c_int64(smem_optin), out))
-    return dict(zip(["grid_side", "block", "smem_stride", "smem_bytes", "chunk_cols", "fits"], [int(v) for v in out]))
-
-
 def steady_schedule(t: float, t_max: float, tau: float, max_sub: int = 4096) -> np.ndarray:
     """tau of every remaining steady sub-step (Taylor.f:81-126) if all norm tests pass; host arithmetic only."""
     out = np.zeros(max_sub)
@@ -181,8 +174,8 @@ class Propagator:
         _check(lib.dyb_set_kernel(self._h, C.c_int(kernel)))
 
     def set_series_kernel(self, kind):
-        """kind: 'auto' | 'term' | 'stream' | 'resident' (include/dynemol_b200.h: DYB_SERIES_*)."""
-        code = {"auto": 0, "term": 1, "stream": 2, "resident": 3, "blocked": 4}[kind] if isinstance(kind, str) else int(kind)
+        """kind: 'auto' | 'term' | 'resident' (include/dynemol_b200.h: DYB_SERIES_*)."""
+        code = {"auto": 0, "term": 1, "resident": 3}[kind] if isinstance(kind, str) else int(kind)
         _check(lib.dyb_set_series_kernel(self._h, C.c_int(code)))
 
     def info(self) -> dict:

@@ -14,7 +14,9 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdynemol_b200.so")
 SOURCES = ["propagator.cu", "legacy_abi.cu"]
-HEADERS = ["common.cuh", "matvec.cuh", "epilogue.cuh", os.path.join("..", "..", "include", "dynemol_b200.h")]
+import glob
+# every header the sources include: csrc/*.cuh plus the public C header
+HEADERS = sorted(os.path.basename(f) for f in glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join("..", "..", "include", "dynemol_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CUDA_LIB = "/usr/local/cuda/lib64"
 

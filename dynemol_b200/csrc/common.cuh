@@ -51,7 +51,8 @@ struct PartPass {
                          // previous one (psi <- sum ; sum <- s * psi), Taylor.f:81-126 without the host in the loop
     int    chain;        // this is the last term of a sub-step and another sub-step of the same particle follows in the
                          // same launch: a passed norm test counts the sub-step and does not latch
-    int    pad_;
+    int    test_gpu;     // term test of the reference's GPU variant (Taylor_gpu.cpp:84-89,581-587): modulus of the complex element
+                         // that holds the largest |re| or |im| (cublasIdamax over 2n reals), compared with a strict `< tol`
     double s_re, s_im;   // scale of the series sum at `begin` (c_0 of the Chebyshev series; 1 for Taylor)
     double alpha_re, alpha_im;
     double beta_re, beta_im;

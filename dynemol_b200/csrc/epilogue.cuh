@@ -71,7 +71,10 @@ __device__ __forceinline__ void decide_particle(PartState& st, const PartPass& q
     st.norm = hypot(st.dot_re, st.dot_im);
     const bool norm_ok = fabs(st.norm - q.norm_ref) < TOL_NORM;                        // Taylor.f:104,199
     if (q.check_conv) {
-        const bool conv = !(st.max_b > TOL_TERM) && !(st.max_k > TOL_TERM);            // Taylor.f:194-195
+        // CPU variant: isConverged is false as soon as one modulus is > tol (Taylor.f:194-195,290-303); GPU variant: max_* hold
+        // the modulus of the Idamax element and the test is a strict `<` (Taylor_gpu.cpp:581,587)
+        const bool conv = q.test_gpu ? (st.max_b < TOL_TERM && st.max_k < TOL_TERM)
+                                     : (!(st.max_b > TOL_TERM) && !(st.max_k > TOL_TERM));
         if (conv && norm_ok) { st.latched = 1; st.ok = 1; st.k_exit = q.k; }
         else if (q.last)     { st.latched = 1; st.ok = 0; st.k_exit = 0; }
     } else if (q.last) {
@@ -88,6 +91,29 @@ __device__ __forceinline__ void apply_decision(Ctrl* c, const PassParams& pass, 
 }
 
 constexpr int EPI_THREADS = 256;
+// Reduced scalars of a term: slots p*4 + {0: max_b, 1: max_k, 2: dot_re, 3: dot_im} for particle p.  The GPU-variant term
+// test (PartPass::test_gpu) needs an arg-max with a payload: slots 8 + 2p + {0: bra, 1: ket} carry the key
+// max(|re|,|im|) of the winning element and slots p*4 + {0, 1} its modulus.  cublasIdamax returns the FIRST index of the
+// maximum; here exact ties between different elements are resolved towards the larger modulus (no index is carried) --
+// the two rules differ only when two elements tie bit for bit in their largest component AND straddle the tolerance.
+constexpr int EPI_NS = 8, EPI_NS_RG = 12;
+__device__ __forceinline__ void argmax_merge(double& key, double& val, double okey, double oval) {
+    if (okey > key || (okey == key && oval > val)) { key = okey; val = oval; }
+}
+// a <- a (+) b over one slot set
+template <int NS>
+__device__ __forceinline__ void scal_merge(double* a, const double* b) {
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        if constexpr (NS == EPI_NS_RG) {
+            argmax_merge(a[8 + 2 * p], a[4 * p], b[8 + 2 * p], b[4 * p]);
+            argmax_merge(a[9 + 2 * p], a[4 * p + 1], b[9 + 2 * p], b[4 * p + 1]);
+        } else {
+            a[4 * p] = fmax(a[4 * p], b[4 * p]); a[4 * p + 1] = fmax(a[4 * p + 1], b[4 * p + 1]);
+        }
+        a[4 * p + 2] += b[4 * p + 2]; a[4 * p + 3] += b[4 * p + 3];
+    }
+}
 // threads per row = 4 (particle, side) x SL slab lanes; SL = 1 when few slabs contribute to a row (large N: ~20 segments
 // per panel), SL = 4 when many do (small N: every CTA of the grid is a segment of the same panel)
 constexpr int EPI_SL_WIDE = 4;
@@ -141,11 +167,13 @@ __device__ __forceinline__ Cx slab_sum_strided(const double* __restrict__ base, 
 // Thread layout: idx = ((row*2 + particle)*2 + side)*SL + slab-lane; side 0 = ket, 1 = bra.  The SL slab lanes split
 // the slab (or peer) sum and merge it with shuffles; the two sides of a (row, particle) meet with one more shuffle
 // for the <bra|ket> product.
-template <bool P2P, int SL>
+template <bool P2P, int SL, bool RG = false>
 __global__ void __launch_bounds__(EPI_THREADS)
 epilogue_kernel_t(const EpiParams E, const PeerTable T)
 {
-    __shared__ double wpart[EPI_THREADS / 32][8];
+    static_assert(!(P2P && RG), "the GPU-variant term test is single-GPU only");
+    constexpr int NS = RG ? EPI_NS_RG : EPI_NS;
+    __shared__ double wpart[EPI_THREADS / 32][NS];
     __shared__ int    is_last;
 
     if constexpr (P2P) {
@@ -189,6 +217,7 @@ epilogue_kernel_t(const EpiParams E, const PeerTable T)
 
     // ---- recurrence, accumulation, term size: slab lane 0 of every (row, particle, side)
     double mx = 0.0;            // |new - old| of this thread's side
+    double kx = 0.0;            // RG: max(|re|, |im|) of new - old (what cublasIdamax ranks, Taylor_gpu.cpp:84-89)
     Cx nw = {0.0, 0.0};         // new running sum of this thread's side
     if (live && sl == 0) {
         Cx y = cmul({pa.alpha_re, pa.alpha_im}, hx);
@@ -220,29 +249,48 @@ epilogue_kernel_t(const EpiParams E, const PeerTable T)
         nw = {so.x + t.re, so.y + t.im};                                 // new = old + term   (Taylor.f:190-191)
         *reinterpret_cast<double2*>(sum + ob) = make_double2(nw.re, nw.im);
         mx = hypot(nw.re - so.x, nw.im - so.y);                          // abs(new - old)      (Taylor.f:300)
+        if constexpr (RG) kx = fmax(fabs(nw.re - so.x), fabs(nw.im - so.y));
     }
     // partner lane = other side of the same (row, particle); idle lanes carry zeros
     const double ore = __shfl_xor_sync(0xffffffffu, nw.re, SL), oim = __shfl_xor_sync(0xffffffffu, nw.im, SL);
     const double omx = __shfl_xor_sync(0xffffffffu, mx, SL);
-    double mb = 0.0, mk = 0.0, dr = 0.0, di = 0.0;
+    double okx = 0.0;
+    if constexpr (RG) okx = __shfl_xor_sync(0xffffffffu, kx, SL);
+    double mb = 0.0, mk = 0.0, dr = 0.0, di = 0.0, kb = 0.0, kk = 0.0;
     if (side == 0 && sl == 0) {                                          // the ket lane owns the pair's contribution
-        mk = mx; mb = omx;
+        mk = mx; mb = omx; kk = kx; kb = okx;
         dr = ore * nw.re + oim * nw.im;                                  // conj(bra)*ket, dotc (Taylor.f:62,103,197)
         di = ore * nw.im - oim * nw.re;
     }
     // the rows of the warp (lane bits above the particle bit); particles (lane bit 2*SL) stay separate
 #pragma unroll
     for (int off = 4 * SL; off < 32; off <<= 1) {
-        mb = fmax(mb, __shfl_xor_sync(0xffffffffu, mb, off)); mk = fmax(mk, __shfl_xor_sync(0xffffffffu, mk, off));
+        if constexpr (RG) {
+            const double ob = __shfl_xor_sync(0xffffffffu, mb, off), okb = __shfl_xor_sync(0xffffffffu, kb, off);
+            const double ok_ = __shfl_xor_sync(0xffffffffu, mk, off), okk = __shfl_xor_sync(0xffffffffu, kk, off);
+            argmax_merge(kb, mb, okb, ob); argmax_merge(kk, mk, okk, ok_);
+        } else {
+            mb = fmax(mb, __shfl_xor_sync(0xffffffffu, mb, off)); mk = fmax(mk, __shfl_xor_sync(0xffffffffu, mk, off));
+        }
         dr += __shfl_xor_sync(0xffffffffu, dr, off);          di += __shfl_xor_sync(0xffffffffu, di, off);
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0 || lane == 2 * SL) {
         const int p = lane / (2 * SL);
         wpart[warp][p * 4 + 0] = mb; wpart[warp][p * 4 + 1] = mk; wpart[warp][p * 4 + 2] = dr; wpart[warp][p * 4 + 3] = di;
+        if constexpr (RG) { wpart[warp][8 + 2 * p] = kb; wpart[warp][9 + 2 * p] = kk; }
     }
     __syncthreads();
-    if (threadIdx.x < 8) {
+    if constexpr (RG) {
+        if (threadIdx.x == 0) {                                          // parity mode: one thread merges the 8 warps in order
+            double v[NS];
+#pragma unroll
+            for (int t = 0; t < NS; ++t) v[t] = wpart[0][t];
+            for (int w2 = 1; w2 < EPI_THREADS / 32; ++w2) scal_merge<NS>(v, wpart[w2]);
+#pragma unroll
+            for (int t = 0; t < NS; ++t) E.blockpart[(size_t)blockIdx.x * NS + t] = v[t];
+        }
+    } else if (threadIdx.x < 8) {
         const int t = threadIdx.x;
         double v = wpart[0][t];
         for (int w2 = 1; w2 < EPI_THREADS / 32; ++w2) v = ((t & 3) < 2) ? fmax(v, wpart[w2][t]) : v + wpart[w2][t];
@@ -261,26 +309,23 @@ epilogue_kernel_t(const EpiParams E, const PeerTable T)
     // ---- last block: final scalars (fixed strided order + fixed tree => deterministic), then the decision the
     //      host used to take per term
     __threadfence();
-    __shared__ double fin[EPI_THREADS][8];
+    __shared__ double fin[EPI_THREADS][NS];
     {
-        double v[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        double v[NS];
+#pragma unroll
+        for (int t = 0; t < NS; ++t) v[t] = 0.0;
         for (unsigned bb = threadIdx.x; bb < gridDim.x; bb += EPI_THREADS) {
-            const double2* bp = reinterpret_cast<const double2*>(E.blockpart + (size_t)bb * 8);
-            const double2 a0 = __ldcg(bp), a1 = __ldcg(bp + 1), a2 = __ldcg(bp + 2), a3 = __ldcg(bp + 3);
-            v[0] = fmax(v[0], a0.x); v[1] = fmax(v[1], a0.y); v[2] += a1.x; v[3] += a1.y;
-            v[4] = fmax(v[4], a2.x); v[5] = fmax(v[5], a2.y); v[6] += a3.x; v[7] += a3.y;
+            const double2* bp = reinterpret_cast<const double2*>(E.blockpart + (size_t)bb * NS);
+            double a[NS];
+#pragma unroll
+            for (int t = 0; t < NS / 2; ++t) { const double2 q = __ldcg(bp + t); a[2 * t] = q.x; a[2 * t + 1] = q.y; }
+            scal_merge<NS>(v, a);
         }
 #pragma unroll
-        for (int t = 0; t < 8; ++t) fin[threadIdx.x][t] = v[t];
+        for (int t = 0; t < NS; ++t) fin[threadIdx.x][t] = v[t];
         __syncthreads();
         for (int st = EPI_THREADS / 2; st > 0; st >>= 1) {
-            if (threadIdx.x < st) {
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    const double a = fin[threadIdx.x][t], b = fin[threadIdx.x + st][t];
-                    fin[threadIdx.x][t] = ((t & 3) < 2) ? fmax(a, b) : a + b;
-                }
-            }
+            if (threadIdx.x < st) scal_merge<NS>(fin[threadIdx.x], fin[threadIdx.x + st]);
             __syncthreads();
         }
     }

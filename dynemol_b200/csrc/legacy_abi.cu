@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <cuda_runtime.h>
 
 #include "../../include/dynemol_b200.h"
@@ -41,9 +42,12 @@ dyb_ctx* ctx_for(int N) {
 }
 
 int mode_from_env() {
+    // taylor (default, Taylor.f semantics) | chebyshev | taylor_refgpu | chebyshev_refgpu (include/dynemol_b200.h)
     const char* m = getenv("DYNEMOL_B200_MODE");
-    if (m && (m[0] == 'c' || m[0] == 'C')) return DYB_MODE_CHEBYSHEV;
-    return DYB_MODE_TAYLOR;
+    if (!m) return DYB_MODE_TAYLOR;
+    const bool refgpu = strstr(m, "refgpu") != nullptr || strstr(m, "REFGPU") != nullptr;
+    if (m[0] == 'c' || m[0] == 'C') return refgpu ? DYB_MODE_CHEBYSHEV_REFGPU : DYB_MODE_CHEBYSHEV;
+    return refgpu ? DYB_MODE_TAYLOR_REFGPU : DYB_MODE_TAYLOR;
 }
 
 void elhl(int n_part, const int* N, const double* h_S, const double* h_h, double* h_H,

@@ -25,9 +25,7 @@
 #include "common.cuh"
 #include "matvec.cuh"
 #include "epilogue.cuh"
-#include "series.cuh"
 #include "resident.cuh"
-#include "blocked.cuh"
 
 using namespace dyb;
 typedef std::complex<double> cplx;
@@ -96,9 +94,6 @@ struct dyb_ctx {
     int res_Gd = 0, res_Bs = 0, res_ldS = 0;     // resident.cuh: grid side, block size, smem column stride (0: does not fit)
     size_t res_smem = 0;
     double *res_pk = nullptr, *res_pb = nullptr, *res_dscal = nullptr, *res_psi = nullptr;
-    int blk_Gd = 0, blk_Bs = 0, blk_ldS = 0, blk_Cc = 0;    // blocked.cuh: streamed 2-D blocks for mid-size operators (0: not applicable)
-    size_t blk_smem = 0;
-    double *blk_pk = nullptr, *blk_pb = nullptr, *blk_dscal = nullptr, *blk_prv = nullptr, *blk_sum = nullptr, *blk_mag = nullptr;
     PassParams* d_passes = nullptr;      // per-term parameters of the series in flight
     unsigned long long* gbar = nullptr;  // grid barrier counter
     cudaStream_t stream = nullptr;
@@ -279,8 +274,14 @@ static int launch_epilogue(dyb_ctx* c, const EpiParams& E) {
     cudaLaunchConfig_t cfg = pdl_config(c, epi_grid(c), EPI_THREADS, 0, &attr);
     PeerTable none;
     memset(&none, 0, sizeof none);
-    if (epi_sl(c) == 1) CK(cudaLaunchKernelEx(&cfg, epilogue_kernel_t<false, 1>, E, none));
-    else CK(cudaLaunchKernelEx(&cfg, epilogue_kernel_t<false, EPI_SL_WIDE>, E, none));
+    const bool rg = E.pass.part[0].test_gpu || E.pass.part[1].test_gpu;      // reference-GPU term test (parity modes)
+    if (rg) {
+        if (epi_sl(c) == 1) CK(cudaLaunchKernelEx(&cfg, epilogue_kernel_t<false, 1, true>, E, none));
+        else CK(cudaLaunchKernelEx(&cfg, epilogue_kernel_t<false, EPI_SL_WIDE, true>, E, none));
+    } else {
+        if (epi_sl(c) == 1) CK(cudaLaunchKernelEx(&cfg, epilogue_kernel_t<false, 1, false>, E, none));
+        else CK(cudaLaunchKernelEx(&cfg, epilogue_kernel_t<false, EPI_SL_WIDE, false>, E, none));
+    }
     c->launches++;
     return DYB_OK;
 }
@@ -341,88 +342,12 @@ static int run_term(dyb_ctx* c, const EpiParams& E, int cur, int nxt, bool use_c
     return DYB_OK;
 }
 
-// Whole series in one cooperative launch (series.cuh).  Usable when every CTA owns at least TMA_STAGES tiles.
-static bool persistent_ok(const dyb_ctx* c) {
-    return c->series_kind == DYB_SERIES_STREAM && c->world == 1 && c->variant == DYB_KERNEL_TMA && c->T >= TMA_STAGES * c->grid;
-}
 // Operator resident in shared memory for the whole series (resident.cuh): small N only, single GPU.
 static bool resident_ok(const dyb_ctx* c) {
     return (c->series_kind == DYB_SERIES_RESIDENT || c->series_kind == DYB_SERIES_AUTO) && c->world == 1 && c->res_Gd > 0;
 }
 constexpr int MAX_SERIES_TERMS = 32;
 constexpr int MAX_CHAIN_PASSES = 4096;      // chained steady sub-steps of one launch (resident kernel)
-
-static int run_series_persistent(dyb_ctx* c, const std::vector<PassParams>& passes) {
-    const int n = (int)passes.size();
-    if (n < 1 || n > MAX_SERIES_TERMS) return fail(DYB_EINVAL, "series length %d out of range", n);
-    CK(cudaMemcpyAsync(c->d_passes, passes.data(), sizeof(PassParams) * n, cudaMemcpyHostToDevice, c->stream));   // pageable source: staged before return
-    CK(cudaMemsetAsync(c->gbar, 0, sizeof(unsigned long long), c->stream));
-    SeriesParams S;
-    memset(&S, 0, sizeof S);
-    S.mv = matvec_params(c, nullptr, nullptr, false);
-    S.row0 = c->row0; S.n_bra_slabs = c->NP; S.pseg_start = c->pseg_start;
-    for (int i = 0; i < 3; ++i) { S.vb[i] = c->vb[i]; S.vk[i] = c->vk[i]; }
-    S.sum_b = c->sum_b; S.sum_k = c->sum_k; S.blockpart = c->blockpart; S.ctrl = c->ctrl;
-    S.passes = c->d_passes; S.n_steps = n; S.gbar = c->gbar;
-#ifdef DYB_SERIES_PROF
-    static long long* d_prof = nullptr;
-    const size_t n_prof = (size_t)MAX_SERIES_TERMS * c->grid * 6;
-    if (!d_prof) CK(cudaMalloc(&d_prof, n_prof * 8));
-    CK(cudaMemsetAsync(d_prof, 0, n_prof * 8, c->stream));
-    S.prof = d_prof;
-#endif
-    void* args[] = {(void*)&c->tmap, (void*)&S};
-    CK(cudaLaunchCooperativeKernel((const void*)series_kernel, dim3(c->grid), dim3(TMA_THREADS), args, TmaSmem::total, c->stream));
-    c->launches++;
-#ifdef DYB_SERIES_PROF
-    {   // diagnostic build: mean / max cycles of each phase over CTAs and terms (first call of every 50 only)
-        static int calls = 0;
-        if (calls++ % 50 == 1) {
-            std::vector<long long> h(n_prof);
-            CK(cudaStreamSynchronize(c->stream));
-            CK(cudaMemcpy(h.data(), d_prof, n_prof * 8, cudaMemcpyDeviceToHost));
-            const char* name[6] = {"tiles", "barrierA", "epilogue", "barrierB", "decision", "next-term-x+gap"};
-            double mean[6] = {0}, mx[6] = {0};
-            for (int t = 0; t < n; ++t) for (int b = 0; b < c->grid; ++b) {
-                const long long* q = &h[((size_t)t * c->grid + b) * 6];
-                for (int i = 0; i < 6; ++i) {
-                    const long long nxt = (i < 5) ? q[i + 1] : ((t + 1 < n) ? h[((size_t)(t + 1) * c->grid + b) * 6] : q[5]);
-                    const double d = double(nxt - q[i]);
-                    mean[i] += d; mx[i] = std::max(mx[i], d);
-                }
-            }
-            fprintf(stderr, "series_prof N=%d grid=%d terms=%d:", c->N, c->grid, n);
-            for (int i = 0; i < 6; ++i) fprintf(stderr, "  %s mean %.0f max %.0f cyc;", name[i], mean[i] / ((double)n * c->grid), mx[i]);
-            fprintf(stderr, "\n");
-        }
-    }
-#endif
-    return DYB_OK;
-}
-
-// Mid-size operators streamed as 2-D blocks (blocked.cuh): explicit request only until AUTO's crossover is settled.
-static bool blocked_ok(const dyb_ctx* c) {
-    return c->series_kind == DYB_SERIES_BLOCKED && c->world == 1 && c->blk_Gd > 0;
-}
-
-static int run_series_blocked(dyb_ctx* c, const std::vector<PassParams>& passes) {
-    const int n = (int)passes.size();
-    if (n < 1 || n > MAX_SERIES_TERMS) return fail(DYB_EINVAL, "series length %d out of range", n);
-    CK(cudaMemcpyAsync(c->d_passes, passes.data(), sizeof(PassParams) * n, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemsetAsync(c->gbar, 0, sizeof(unsigned long long), c->stream));
-    BlockedParams R;
-    memset(&R, 0, sizeof R);
-    R.H = c->H; R.ld = c->ld; R.N = c->N; R.Gd = c->blk_Gd; R.Bs = c->blk_Bs; R.ldS = c->blk_ldS; R.Cc = c->blk_Cc;
-    R.n_chunks = (c->blk_Bs + c->blk_Cc - 1) / c->blk_Cc;
-    R.x0k = c->vk[0]; R.x0b = c->vb[0]; R.sum_b = c->sum_b; R.sum_k = c->sum_k;
-    R.pk = c->blk_pk; R.pb = c->blk_pb; R.dscal = c->blk_dscal;
-    R.st_prv = c->blk_prv; R.st_sum = c->blk_sum; R.st_mag = c->blk_mag;
-    R.ctrl = c->ctrl; R.passes = c->d_passes; R.n_steps = n; R.gbar = c->gbar;
-    void* args[] = {(void*)&R};
-    CK(cudaLaunchCooperativeKernel((const void*)blocked_series_kernel, dim3(c->blk_Gd * c->blk_Gd), dim3(BLK_THREADS), args, c->blk_smem, c->stream));
-    c->launches++;
-    return DYB_OK;
-}
 
 static int run_series_resident(dyb_ctx* c, const std::vector<PassParams>& passes) {
     const int n = (int)passes.size();
@@ -435,6 +360,8 @@ static int run_series_resident(dyb_ctx* c, const std::vector<PassParams>& passes
     R.x0k = c->vk[0]; R.x0b = c->vb[0]; R.sum_b = c->sum_b; R.sum_k = c->sum_k;
     R.pk = c->res_pk; R.pb = c->res_pb; R.dscal = c->res_dscal; R.psi_store = reinterpret_cast<double2*>(c->res_psi);
     R.ctrl = c->ctrl; R.passes = c->d_passes; R.n_steps = n; R.gbar = c->gbar;
+    bool rg = false;                           // reference-GPU term test (parity modes): the instantiation that carries arg-max keys
+    for (const PassParams& pp : passes) if (pp.part[0].test_gpu || pp.part[1].test_gpu) { rg = true; break; }
 #ifdef DYB_SERIES_PROF
     static long long* d_rprof = nullptr;
     const int rgrid = c->res_Gd * c->res_Gd;
@@ -444,7 +371,8 @@ static int run_series_resident(dyb_ctx* c, const std::vector<PassParams>& passes
     R.prof = d_rprof;
 #endif
     void* args[] = {(void*)&R};
-    CK(cudaLaunchCooperativeKernel((const void*)resident_series_kernel, dim3(c->res_Gd * c->res_Gd), dim3(RES_THREADS), args, c->res_smem, c->stream));
+    CK(cudaLaunchCooperativeKernel(rg ? (const void*)resident_series_kernel_t<true> : (const void*)resident_series_kernel_t<false>,
+                                   dim3(c->res_Gd * c->res_Gd), dim3(RES_THREADS), args, c->res_smem, c->stream));
     c->launches++;
 #ifdef DYB_SERIES_PROF
     {   // diagnostic build: mean / max cycles of each phase over CTAs and terms
@@ -472,11 +400,9 @@ static int run_series_resident(dyb_ctx* c, const std::vector<PassParams>& passes
     return DYB_OK;
 }
 
-// One series through whichever single-launch kernel applies (the caller checked resident_ok / persistent_ok).
-static bool single_launch_ok(const dyb_ctx* c) { return resident_ok(c) || blocked_ok(c) || persistent_ok(c); }
-static int run_series_single_launch(dyb_ctx* c, const std::vector<PassParams>& passes) {
-    return resident_ok(c) ? run_series_resident(c, passes) : blocked_ok(c) ? run_series_blocked(c, passes) : run_series_persistent(c, passes);
-}
+// One series in a single launch when the resident kernel applies.
+static bool single_launch_ok(const dyb_ctx* c) { return resident_ok(c); }
+static int run_series_single_launch(dyb_ctx* c, const std::vector<PassParams>& passes) { return run_series_resident(c, passes); }
 
 static int launch_series_init(dyb_ctx* c, const int adopt[2], const int active[2], int cur, const cplx* sum_scale = nullptr) {
     InitParams I;
@@ -512,6 +438,14 @@ static void taylor_coefficient(double tau, cplx* C) {
 // Taylor.f:165-171: k_max = first 1-based k >= 2 with |c(k)| < 1e-16, else order
 static int taylor_kmax(const cplx* C) {
     for (int k = 2; k <= ORDER; ++k) if (std::abs(C[k - 1]) < 1.0e-16) return k;
+    return ORDER;
+}
+
+// Taylor_gpu.cpp:553-564 (the reference's GPU variant): k_max = first 0-based k >= 1 with |c_k| < 1e-16, else 25; the series
+// then sums the terms k = 1 .. k_max-1, one fewer than Taylor.f whenever the threshold is met.
+// Returned 1-based-compatible: the caller uses n_terms = k_ref - 1 for both variants.
+static int taylor_kmax_refgpu(const cplx* C) {
+    for (int k = 1; k < ORDER; ++k) if (std::abs(C[k]) < 1.0e-16) return k;
     return ORDER;
 }
 
@@ -568,12 +502,20 @@ static int compute_norm_ref(dyb_ctx* c, double out[2]) {
 //   Taylor    (Taylor.f:182-187 / :90-95):  step s produces term k = s+2:  y = (c_k/c_{k-1}) H' x ; sum += y
 //   Chebyshev (Chebyshev_gpu.cpp:552-589):  step s produces phi_j, j = s+1: phi_1 = Ht phi_0, phi_j = 2 Ht phi_{j-1} - phi_{j-2},
 //                                           Ht = (H' - ebar)/de ; sum += c_j phi_j ; tests start at j = 2
-static void fill_pass(PartPass& a, const Particle& q, int mode, int s, double ebar, double de) {
+//   Taylor, reference GPU variant (Taylor_gpu.cpp:566-575): step s produces the raw power Psi_k = H' Psi_{k-1}, k = s+1
+//                                           (0-based), sum += c_k Psi_k ; term test of PartPass::test_gpu
+static void fill_pass(PartPass& a, const Particle& q, int mode, int s, double ebar, double de, bool refgpu = false) {
     memset(&a, 0, sizeof a);
     a.active = 1; a.norm_ref = q.norm_ref;
     a.last = (s == q.n_terms - 1) ? 1 : 0;
     a.last_ok_by_norm = q.check ? 0 : 1;
-    if (mode == DYB_MODE_TAYLOR) {
+    a.test_gpu = refgpu ? 1 : 0;
+    if (mode == DYB_MODE_TAYLOR && refgpu) {
+        const int k = s + 1;
+        a.k = k; a.alpha_re = 1.0; a.scale_term = 1;
+        a.c_re = q.C[k].real(); a.c_im = q.C[k].imag();
+        a.check_conv = q.check ? 1 : 0;
+    } else if (mode == DYB_MODE_TAYLOR) {
         const int k = s + 2;
         const cplx r = q.C[k - 1] / q.C[k - 2];               // Taylor.f:93,185
         a.k = k; a.alpha_re = r.real(); a.alpha_im = r.imag();
@@ -604,13 +546,19 @@ static std::vector<double> steady_schedule(double t, double t_max, double tau, i
 // Propagation(): Taylor.f:35-127 (identical control flow in Chebyshev_gpu.cpp:347-485), one state machine per
 // particle, all particles served by the same passes over H'.  Host decisions are taken once per series from
 // the device-side control block; per-term decisions (early exit of Convergence) are taken on the device.
-static int propagate_series(dyb_ctx* c, int mode, double t_init, double t_max, const double* tau_in, double* save_tau, dyb_trace* traces)
+static int propagate_series(dyb_ctx* c, int mode_in, double t_init, double t_max, const double* tau_in, double* save_tau, dyb_trace* traces)
 {
+    // the *_REFGPU modes follow the reference's GPU files decision for decision (Taylor_gpu.cpp:334-480,511-622 /
+    // Chebyshev_gpu.cpp:347-485,524-632): same control flow, other term count, term test and place of c_k (fill_pass)
+    const bool refgpu = (mode_in == DYB_MODE_TAYLOR_REFGPU || mode_in == DYB_MODE_CHEBYSHEV_REFGPU);
+    const int mode = (mode_in == DYB_MODE_TAYLOR || mode_in == DYB_MODE_TAYLOR_REFGPU) ? DYB_MODE_TAYLOR : DYB_MODE_CHEBYSHEV;
     Particle P[2];
     double nref[2];
     int rc = compute_norm_ref(c, nref);
     if (rc) return rc;
-    const double ebar = 0.5 * (c->emax + c->emin), de = 0.5 * (c->emax - c->emin);
+    // Chebyshev_gpu.cpp applies the series to H' itself (no spectral rescaling): ebar = 0, de = 1
+    const double ebar = (mode_in == DYB_MODE_CHEBYSHEV_REFGPU) ? 0.0 : 0.5 * (c->emax + c->emin);
+    const double de   = (mode_in == DYB_MODE_CHEBYSHEV_REFGPU) ? 1.0 : 0.5 * (c->emax - c->emin);
     for (int p = 0; p < c->n_part; ++p) {
         P[p].present = true; P[p].done = false; P[p].phase = 0;
         P[p].tau = tau_in[p]; P[p].norm_ref = nref[p]; P[p].t = t_init;
@@ -633,7 +581,7 @@ static int propagate_series(dyb_ctx* c, int mode, double t_init, double t_max, c
             active[p] = 1;
             if (q.phase == 0 || q.phase == 2) {                   // Convergence(): Taylor.f:163-173 / Chebyshev_gpu.cpp:556-575
                 coefficient(q);
-                q.k_ref = (mode == DYB_MODE_TAYLOR) ? taylor_kmax(q.C) : cheb_kmax(q.C, de * q.tau);
+                q.k_ref = (mode == DYB_MODE_TAYLOR) ? (refgpu ? taylor_kmax_refgpu(q.C) : taylor_kmax(q.C)) : cheb_kmax(q.C, de * q.tau);
                 q.check = true;
             } else {                                              // steady sub-step: Taylor.f:90 / Chebyshev_gpu.cpp:418-425
                 q.check = false;
@@ -668,7 +616,7 @@ static int propagate_series(dyb_ctx* c, int mode, double t_init, double t_max, c
                         memset(&passes[old_n], 0, sizeof(PassParams) * (pos + nt - old_n));
                     }
                     sim.check = false; sim.n_terms = nt;
-                    for (int j = 0; j < nt; ++j) fill_pass(passes[pos + j].part[p], sim, mode, j, ebar, de);
+                    for (int j = 0; j < nt; ++j) fill_pass(passes[pos + j].part[p], sim, mode, j, ebar, de, refgpu);
                     if (n_sub > 0) {
                         PartPass& first = passes[pos].part[p];
                         const cplx s0 = (mode == DYB_MODE_TAYLOR) ? cplx(1.0, 0.0) : sim.C[0];
@@ -721,14 +669,14 @@ static int propagate_series(dyb_ctx* c, int mode, double t_init, double t_max, c
             for (int s = 0; s < L; ++s) {
                 memset(&passes[s], 0, sizeof(PassParams));
                 for (int p = 0; p < 2; ++p)
-                    if (active[p] && s < P[p].n_terms) fill_pass(passes[s].part[p], P[p], mode, s, ebar, de);
+                    if (active[p] && s < P[p].n_terms) fill_pass(passes[s].part[p], P[p], mode, s, ebar, de, refgpu);
             }
             if ((rc = run_series_single_launch(c, passes))) return rc;
         } else
         for (int s = 0; s < L; ++s) {
             EpiParams E = epi_params(c, cur, prv, nxt);
             for (int p = 0; p < 2; ++p) {
-                if (active[p] && s < P[p].n_terms) fill_pass(E.pass.part[p], P[p], mode, s, ebar, de);
+                if (active[p] && s < P[p].n_terms) fill_pass(E.pass.part[p], P[p], mode, s, ebar, de, refgpu);
                 else E.pass.part[p].active = 0;
             }
             if ((rc = run_term(c, E, cur, nxt, true))) return rc;
@@ -836,31 +784,6 @@ static ResidentPlan make_resident_plan(int N, int sm_count, size_t smem_optin, s
     r.fits = r.Bs <= RES_MAX_BS && r.smem <= (size_t)RES_SMEM_MAX && r.smem + static_smem <= smem_optin;
     return r;
 }
-// Blocking of the streamed 2-D block kernel (blocked.cuh): always the full grid side; the chunk width Cc is the
-// largest that lets BLK_STAGES chunks, the two vector blocks and the partial buffers share the opt-in shared memory.
-struct BlockedPlan { int Gd, Bs, ldS, Cc; size_t smem; bool fits; };
-static BlockedPlan make_blocked_plan(int N, int sm_count, size_t smem_optin, size_t static_smem) {
-    BlockedPlan r;
-    int gd_max = 1;
-    while ((gd_max + 1) * (gd_max + 1) <= sm_count && gd_max + 1 <= RES_MAX_GD) ++gd_max;
-    r.Gd = gd_max;
-    r.Bs = (N + r.Gd - 1) / r.Gd;
-    r.ldS = r.Bs | 1;
-    r.Cc = 0; r.smem = 0; r.fits = false;
-    if (r.Bs > BLK_MAX_BS || r.Bs < 64) return r;
-    for (int Cc = std::min(r.Bs, 64); Cc >= 8; --Cc) {
-        const BlockedSmem L(r.Bs, r.ldS, Cc);
-        if (L.bytes() <= (size_t)BLK_SMEM_MAX && L.bytes() + static_smem <= smem_optin) { r.Cc = Cc; r.smem = L.bytes(); r.fits = true; break; }
-    }
-    return r;
-}
-int dyb_blocked_plan(int N, int sm_count, int64_t smem_optin, int64_t* out6) {
-    if (N <= 0 || sm_count <= 0 || smem_optin <= 0 || !out6) return fail(DYB_EINVAL, "bad argument");
-    const BlockedPlan r = make_blocked_plan(N, sm_count, (size_t)smem_optin, 2048);
-    out6[0] = r.Gd; out6[1] = r.Bs; out6[2] = r.ldS; out6[3] = (int64_t)r.smem; out6[4] = r.Cc; out6[5] = r.fits ? 1 : 0;
-    return DYB_OK;
-}
-
 int dyb_resident_plan(int N, int sm_count, int64_t smem_optin, int64_t* out6) {
     if (N <= 0 || sm_count <= 0 || smem_optin <= 0 || !out6) return fail(DYB_EINVAL, "bad argument");
     const ResidentPlan r = make_resident_plan(N, sm_count, (size_t)smem_optin, 2048);
@@ -917,7 +840,6 @@ int dyb_destroy(dyb_ctx* c) {
     if (c->ctrl) cudaFree(c->ctrl);
     if (c->d_passes) cudaFree(c->d_passes);
     if (c->gbar) cudaFree(c->gbar);
-    for (double* b : {c->blk_pk, c->blk_pb, c->blk_dscal, c->blk_prv, c->blk_sum, c->blk_mag}) if (b) cudaFree(b);
     if (c->res_pk) cudaFree(c->res_pk);
     if (c->res_pb) cudaFree(c->res_pb);
     if (c->res_dscal) cudaFree(c->res_dscal);
@@ -959,7 +881,7 @@ int dyb_create(dyb_ctx** out, int device, int N, int row0, int n_rows) {
     for (int i = 0; i < 3; ++i) { CKC(alloc_zero(&c->vb[i], c->Lq * NQ)); CKC(alloc_zero(&c->vk[i], c->Lq * NQ)); }
     CKC(alloc_zero(&c->ket_slab, (size_t)std::max(1, c->n_seg) * PANEL_ROWS * NQ));
     CKC(alloc_zero(&c->bra_slab, (size_t)c->NP * c->Ncpad * NQ));
-    CKC(alloc_zero(&c->blockpart, (size_t)epi_grid(c) * 8));
+    CKC(alloc_zero(&c->blockpart, (size_t)epi_grid(c) * EPI_NS_RG));
     CKC(alloc_zero(&c->scal, 64));
     CKC(alloc_zero(&c->io, (size_t)N * 4 * 2));            // staging for host <-> quad conversion / S^-1 solves
     CKCU(cudaMalloc(&c->ctrl, sizeof(Ctrl)));
@@ -968,52 +890,34 @@ int dyb_create(dyb_ctx** out, int device, int N, int row0, int n_rows) {
     CKCU(cudaMallocHost(&c->h_scal, 64 * sizeof(double)));
     CKC(build_tensor_map(c));
     CKCU(cudaFuncSetAttribute(dual_matvec_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TmaSmem::total));
-    CKCU(cudaFuncSetAttribute(series_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TmaSmem::total));
     CKCU(cudaMalloc(&c->d_passes, sizeof(PassParams) * MAX_CHAIN_PASSES));
     CKCU(cudaMalloc(&c->gbar, sizeof(unsigned long long)));
     if (row0 == 0 && n_rows == N) {    // resident.cuh: does a Gd x Gd blocking of H' fit the shared memories?
         int smem_optin = 0;
         CKCU(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         cudaFuncAttributes fa;
-        CKCU(cudaFuncGetAttributes(&fa, resident_series_kernel));
+        CKCU(cudaFuncGetAttributes(&fa, resident_series_kernel_t<true>));
         const ResidentPlan rp = make_resident_plan(N, c->sm_count, (size_t)smem_optin, fa.sharedSizeBytes);
         const int Gd = rp.Gd, Bs = rp.Bs;
         bool launchable = rp.fits;
         if (launchable) {   // a cooperative grid must be co-resident: one CTA per SM, and the device must support it
-            CKCU(cudaFuncSetAttribute(resident_series_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RES_SMEM_MAX));
+            CKCU(cudaFuncSetAttribute(resident_series_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RES_SMEM_MAX));
+            CKCU(cudaFuncSetAttribute(resident_series_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RES_SMEM_MAX));
             int coop = 0, per_sm = 0;
             CKCU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
-            CKCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resident_series_kernel, RES_THREADS, rp.smem));
+            CKCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resident_series_kernel_t<true>, RES_THREADS, rp.smem));
             launchable = coop && (long)per_sm * c->sm_count >= (long)Gd * Gd;
         }
         if (launchable) {
             c->res_Gd = Gd; c->res_Bs = Bs; c->res_ldS = rp.ldS; c->res_smem = rp.smem;
-            CKCU(cudaFuncSetAttribute(resident_series_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RES_SMEM_MAX));
             CKC(alloc_zero(&c->res_pk, (size_t)2 * Gd * Gd * Bs * NQ)); CKC(alloc_zero(&c->res_pb, (size_t)2 * Gd * Gd * Bs * NQ));
-            CKC(alloc_zero(&c->res_dscal, (size_t)2 * Gd * 8));
+            CKC(alloc_zero(&c->res_dscal, (size_t)2 * Gd * RES_NS));
             CKC(alloc_zero(&c->res_psi, (size_t)Gd * Gd * RES_THREADS * 2));
-        }
-    }
-    if (row0 == 0 && n_rows == N && c->res_Gd == 0) {     // blocked.cuh: mid-size operators
-        int smem_optin = 0;
-        CKCU(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-        cudaFuncAttributes fa;
-        CKCU(cudaFuncGetAttributes(&fa, blocked_series_kernel));
-        const BlockedPlan bp = make_blocked_plan(N, c->sm_count, (size_t)smem_optin, fa.sharedSizeBytes);
-        if (bp.fits) {
-            c->blk_Gd = bp.Gd; c->blk_Bs = bp.Bs; c->blk_ldS = bp.ldS; c->blk_Cc = bp.Cc; c->blk_smem = bp.smem;
-            CKCU(cudaFuncSetAttribute(blocked_series_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BLK_SMEM_MAX));
-            const size_t G = (size_t)bp.Gd * bp.Gd;
-            CKC(alloc_zero(&c->blk_pk, 2 * G * bp.Bs * NQ)); CKC(alloc_zero(&c->blk_pb, 2 * G * bp.Bs * NQ));
-            CKC(alloc_zero(&c->blk_dscal, (size_t)2 * bp.Gd * 8));
-            CKC(alloc_zero(&c->blk_prv, G * 2 * bp.Bs * NQ)); CKC(alloc_zero(&c->blk_sum, G * 2 * bp.Bs * NQ));
-            CKC(alloc_zero(&c->blk_mag, G * 2 * bp.Bs * 2));
         }
     }
     if (const char* e = getenv("DYNEMOL_B200_CHAIN")) c->chain_steady = (e[0] != '0');
     if (const char* e = getenv("DYNEMOL_B200_SERIES")) {
-        c->series_kind = !strcmp(e, "term") ? DYB_SERIES_PER_TERM : !strcmp(e, "stream") ? DYB_SERIES_STREAM
-                       : !strcmp(e, "resident") ? DYB_SERIES_RESIDENT : !strcmp(e, "blocked") ? DYB_SERIES_BLOCKED : DYB_SERIES_AUTO;
+        c->series_kind = !strcmp(e, "term") ? DYB_SERIES_PER_TERM : !strcmp(e, "resident") ? DYB_SERIES_RESIDENT : DYB_SERIES_AUTO;
     }
     CKCU(cudaDeviceSynchronize());     // the zero fills above ran on the legacy stream; c->stream is non-blocking
 #undef CKC
@@ -1033,7 +937,7 @@ int dyb_set_kernel(dyb_ctx* c, int v) {
 
 int dyb_set_series_kernel(dyb_ctx* c, int kind) {
     if (!c) return fail(DYB_EINVAL, "ctx is NULL");
-    if (kind < DYB_SERIES_AUTO || kind > DYB_SERIES_BLOCKED) return fail(DYB_EINVAL, "unknown series kernel %d", kind);
+    if (kind != DYB_SERIES_AUTO && kind != DYB_SERIES_PER_TERM && kind != DYB_SERIES_RESIDENT) return fail(DYB_EINVAL, "unknown series kernel %d", kind);
     c->series_kind = kind;
     return DYB_OK;
 }
@@ -1043,7 +947,7 @@ int dyb_get_info(dyb_ctx* c, int64_t* o) {
     memset(o, 0, 16 * sizeof(int64_t));
     o[0] = c->N; o[1] = c->ld; o[2] = c->M; o[3] = c->grid; o[4] = c->T; o[5] = c->n_seg; o[6] = c->sm_count;
     o[7] = TmaSmem::total; o[8] = c->variant; o[9] = c->NP; o[10] = c->TPP; o[11] = c->passes_last; o[12] = c->p2p ? 1 : 0;
-    o[13] = resident_ok(c) ? DYB_SERIES_RESIDENT : blocked_ok(c) ? DYB_SERIES_BLOCKED : persistent_ok(c) ? DYB_SERIES_STREAM : DYB_SERIES_PER_TERM;
+    o[13] = resident_ok(c) ? DYB_SERIES_RESIDENT : DYB_SERIES_PER_TERM;
     o[14] = c->res_Gd; o[15] = c->res_Bs;
     return DYB_OK;
 }
@@ -1386,7 +1290,10 @@ int dyb_propagate(dyb_ctx* c, int mode, double t_init, double t_max, const doubl
     if (!c || !tau || !save_tau) return fail(DYB_EINVAL, "NULL argument");
     if (c->n_part < 1) return fail(DYB_EINVAL, "dyb_set_packets must be called first");
     CK(cudaSetDevice(c->device));
-    if (mode == DYB_MODE_TAYLOR) return propagate_series(c, mode, t_init, t_max, tau, save_tau, traces);
+    if ((mode == DYB_MODE_TAYLOR_REFGPU || mode == DYB_MODE_CHEBYSHEV_REFGPU) && c->world > 1)
+        return fail(DYB_EINVAL, "the reference-GPU parity modes are single-GPU (like the reference's GPU path)");
+    if (mode == DYB_MODE_TAYLOR || mode == DYB_MODE_TAYLOR_REFGPU || mode == DYB_MODE_CHEBYSHEV_REFGPU)
+        return propagate_series(c, mode, t_init, t_max, tau, save_tau, traces);
     if (mode == DYB_MODE_CHEBYSHEV) {
         if (!c->have_bounds) return fail(DYB_EINVAL, "Chebyshev mode needs spectral bounds: dyb_set_spectral_bounds / dyb_estimate_spectral_bounds");
         return propagate_series(c, mode, t_init, t_max, tau, save_tau, traces);

@@ -31,6 +31,7 @@ constexpr int RES_THREADS = 640;          // threads 0..319: ket side, 320..639:
 constexpr int RES_HALF    = 320;
 constexpr int RES_MAX_BS  = 152;          // 152*153*8 B = 186 KB of H' per CTA
 constexpr int RES_MAX_GD  = 12;          // grid side (12 x 12 = 144 CTAs on the 148 SMs of a B200)
+constexpr int RES_NS      = EPI_NS_RG;   // scalar slots per diagonal CTA (8 + 4 arg-max keys, used by the parity modes only)
 constexpr int RES_SMEM_MAX = 227 * 1024 - 2048;   // dynamic shared memory opt-in (the kernel's static part stays below 2 KB)
 
 struct ResidentParams {
@@ -39,7 +40,7 @@ struct ResidentParams {
     const double* x0k; const double* x0b; // starting vectors (quads), written by series_init_kernel
     double* sum_b; double* sum_k;         // in: series sums at the start; out: at the latch / end of the series
     double* pk; double* pb;               // [2][Gd][Gd][Bs][NQ] partial products (parity of the term first)
-    double* dscal;                        // [2][Gd][8] scalars of the diagonal CTAs
+    double* dscal;                        // [2][Gd][RES_NS] scalars of the diagonal CTAs (slots: epilogue.cuh EPI_NS_RG)
     double2* psi_store;                   // [grid][RES_THREADS] start vector of the sub-step in progress (needed only after a failure)
     Ctrl* ctrl;
     const PassParams* passes; int n_steps;
@@ -86,8 +87,9 @@ __device__ __forceinline__ void res_grid_barrier(unsigned long long* ctr, unsign
     __syncthreads();
 }
 
+template <bool RG>        // RG: reference-GPU term test (parity modes); a separate instantiation keeps the default one lean
 __global__ void __launch_bounds__(RES_THREADS, 1)
-resident_series_kernel(const ResidentParams R)
+resident_series_kernel_t(const ResidentParams R)
 {
     extern __shared__ __align__(16) double rsm[];
     const ResidentSmem L(R.Bs, R.ldS);
@@ -95,10 +97,11 @@ resident_series_kernel(const ResidentParams R)
     double* part = rsm + L.part;
     double* sq = rsm + L.sq;
     double* mq = sq + 2 * R.Bs * NQ;
+    double* kq = mq + 2 * R.Bs * 2;                              // refgpu: max(re^2, im^2) of new - old (the Idamax key, squared)
     __shared__ Ctrl       sctrl;
     __shared__ PassParams spass[2];
-    __shared__ double     fin[8];
-    __shared__ double     wred[RES_HALF / 32][8];
+    __shared__ double     fin[RES_NS];
+    __shared__ double     wred[RES_HALF / 32][RES_NS];
     __shared__ int        stop_chain;                            // a particle failed a chained sub-step: the other one stops at
                                                                  // its next sub-step boundary so that both resume together
 
@@ -223,14 +226,21 @@ resident_series_kernel(const ResidentParams R)
             // diagonal CTAs left for term t-1: thread j takes components 2j, 2j+1 = a pair of maxima or a pair of sums.
             const bool scal = (t > 0) && (tid >= RES_THREADS - 4);
             const int  j2 = 2 * (tid - (RES_THREADS - 4));
-            const double* src = scal ? R.dscal + (size_t)((t + 1) & 1) * Gd * 8 + j2
+            const double* src = scal ? R.dscal + (size_t)((t + 1) & 1) * Gd * RES_NS + j2
                                      : (side ? R.pb : R.pk) + ((((size_t)(t & 1) * Gd) * Gd + tblock) * Bs + te) * NQ + 2 * tp;
-            const size_t stride = scal ? (size_t)8 : (size_t)Gd * Bs * NQ;
+            const size_t stride = scal ? (size_t)RES_NS : (size_t)Gd * Bs * NQ;
             if (task || scal) {
                 double2 v[RES_MAX_GD];                           // all Gd values in flight at once: one L2 round trip
 #pragma unroll
                 for (int u = 0; u < RES_MAX_GD; ++u) if (u < Gd) v[u] = __ldcg(reinterpret_cast<const double2*>(src + u * stride));
-                if (scal && (j2 & 2) == 0) {                     // maxima (of non-negative numbers)
+                if (RG && scal && (j2 & 2) == 0) {         // arg-max with payload: keys in slots 8 + j2/2, 9 + j2/2
+                    const double* ksrc = R.dscal + (size_t)((t + 1) & 1) * Gd * RES_NS + 8 + (j2 >> 1);
+                    double2 key = make_double2(0.0, 0.0);
+                    for (int u = 0; u < Gd; ++u) {
+                        const double2 ku = __ldcg(reinterpret_cast<const double2*>(ksrc + u * stride));
+                        argmax_merge(key.x, hx.x, ku.x, v[u].x); argmax_merge(key.y, hx.y, ku.y, v[u].y);
+                    }
+                } else if (scal && (j2 & 2) == 0) {              // maxima (of non-negative numbers)
 #pragma unroll
                     for (int u = 0; u < RES_MAX_GD; ++u) if (u < Gd) { hx.x = fmax(hx.x, v[u].x); hx.y = fmax(hx.y, v[u].y); }
                 } else {
@@ -253,7 +263,7 @@ resident_series_kernel(const ResidentParams R)
 
         DYB_RSTAMP(4);
         // ---------------------------------------------------------------- 4. recurrence + series sum (registers)
-        double mag = 0.0;
+        double mag = 0.0, key = 0.0;
         double2 xout = cur;                                      // what the next product multiplies
         if (task) {
             const PartPass& pa = spass[t & 1].part[tp];
@@ -274,6 +284,7 @@ resident_series_kernel(const ResidentParams R)
                 const double nw_re = sum.x + tt.re, nw_im = sum.y + tt.im;
                 const double dx = nw_re - sum.x, dy = nw_im - sum.y;
                 mag = dx * dx + dy * dy;                         // |new - old|^2 (isConverged, Taylor.f:290-303); root after the max
+                key = fmax(dx * dx, dy * dy);                    // what cublasIdamax ranks (Taylor_gpu.cpp:84-89), squared
                 prv = cur;
                 cur = make_double2(y.re, y.im);
                 sum = make_double2(nw_re, nw_im);
@@ -285,6 +296,7 @@ resident_series_kernel(const ResidentParams R)
             if (diag) {
                 *reinterpret_cast<double2*>(sq + (size_t)(side * Bs + te) * NQ + 2 * tp) = sum;
                 mq[(size_t)(side * Bs + te) * 2 + tp] = mag;
+                if constexpr (RG) kq[(size_t)(side * Bs + te) * 2 + tp] = key;
             }
         }
         __syncthreads();
@@ -293,24 +305,44 @@ resident_series_kernel(const ResidentParams R)
         if (diag) {
             if (side == 0) {                                     // 10 warps; thread = (entry te, particle tp) of block bi == bj
                 double v[4] = {0.0, 0.0, 0.0, 0.0};              // max_b, max_k, dot_re, dot_im of this particle
+                double kv[2] = {0.0, 0.0};                       // refgpu: arg-max keys of bra, ket
                 if (slot) {
                     const double2 k = *reinterpret_cast<const double2*>(sq + (size_t)te * NQ + 2 * tp);
                     const double2 b = *reinterpret_cast<const double2*>(sq + (size_t)(Bs + te) * NQ + 2 * tp);
                     v[0] = mq[(size_t)(Bs + te) * 2 + tp]; v[1] = mq[(size_t)te * 2 + tp];
+                    if constexpr (RG) { kv[0] = kq[(size_t)(Bs + te) * 2 + tp]; kv[1] = kq[(size_t)te * 2 + tp]; }
                     v[2] = b.x * k.x + b.y * k.y;                // conj(bra) * ket
                     v[3] = b.x * k.y - b.y * k.x;
                 }
 #pragma unroll
                 for (int off = 2; off < 32; off <<= 1) {         // lanes of equal particle (lane bit 0)
-                    v[0] = fmax(v[0], __shfl_xor_sync(0xffffffffu, v[0], off)); v[1] = fmax(v[1], __shfl_xor_sync(0xffffffffu, v[1], off));
+                    if constexpr (RG) {
+                        const double o0 = __shfl_xor_sync(0xffffffffu, v[0], off), k0 = __shfl_xor_sync(0xffffffffu, kv[0], off);
+                        const double o1 = __shfl_xor_sync(0xffffffffu, v[1], off), k1 = __shfl_xor_sync(0xffffffffu, kv[1], off);
+                        argmax_merge(kv[0], v[0], k0, o0); argmax_merge(kv[1], v[1], k1, o1);
+                    } else {
+                        v[0] = fmax(v[0], __shfl_xor_sync(0xffffffffu, v[0], off)); v[1] = fmax(v[1], __shfl_xor_sync(0xffffffffu, v[1], off));
+                    }
                     v[2] += __shfl_xor_sync(0xffffffffu, v[2], off);            v[3] += __shfl_xor_sync(0xffffffffu, v[3], off);
                 }
-                if (lane < 2)
+                if (lane < 2) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) wred[tl >> 5][lane * 4 + q] = v[q];
+                    if constexpr (RG) { wred[tl >> 5][8 + 2 * lane] = kv[0]; wred[tl >> 5][9 + 2 * lane] = kv[1]; }
+                }
             }
             __syncthreads();
-            if (tid < 8) {
+            if constexpr (RG) {
+                if (tid == 0) {                                  // parity mode: one thread merges the warps in order
+                    double f[RES_NS];
+#pragma unroll
+                    for (int q = 0; q < RES_NS; ++q) f[q] = wred[0][q];
+                    for (int w2 = 1; w2 < RES_HALF / 32; ++w2) scal_merge<RES_NS>(f, wred[w2]);
+#pragma unroll
+                    for (int q = 0; q < RES_NS; ++q)
+                        __stcg(R.dscal + ((size_t)(t & 1) * Gd + bi) * RES_NS + q, (q < 8 && (q & 3) < 2) ? sqrt(f[q]) : f[q]);
+                }
+            } else if (tid < 8) {
                 double wv[RES_HALF / 32];                        // all loads first: one shared-memory latency, not ten
 #pragma unroll
                 for (int w2 = 0; w2 < RES_HALF / 32; ++w2) wv[w2] = wred[w2][tid];
@@ -318,7 +350,7 @@ resident_series_kernel(const ResidentParams R)
 #pragma unroll
                 for (int w2 = 1; w2 < RES_HALF / 32; ++w2) f = ((tid & 3) < 2) ? fmax(f, wv[w2]) : f + wv[w2];
                 if ((tid & 3) < 2) f = sqrt(f);
-                __stcg(R.dscal + ((size_t)(t & 1) * Gd + bi) * 8 + tid, f);
+                __stcg(R.dscal + ((size_t)(t & 1) * Gd + bi) * RES_NS + tid, f);
             }
         }
         DYB_RSTAMP(5);
@@ -330,10 +362,14 @@ resident_series_kernel(const ResidentParams R)
         res_grid_barrier(R.gbar, bar_target);
         if (tid >= RES_THREADS - 8) {
             const int q = tid & 7;
-            const double* ds = R.dscal + (size_t)((t - 1) & 1) * Gd * 8 + q;
+            const double* ds = R.dscal + (size_t)((t - 1) & 1) * Gd * RES_NS + q;
             const bool is_max = (q & 3) < 2;
-            double v = 0.0;
-            for (int u = 0; u < Gd; ++u) { const double x = __ldcg(ds + u * 8); v = is_max ? fmax(v, x) : v + x; }
+            double v = 0.0, kbest = 0.0;
+            for (int u = 0; u < Gd; ++u) {
+                const double x = __ldcg(ds + u * RES_NS);
+                if (RG && is_max) argmax_merge(kbest, v, __ldcg(R.dscal + ((size_t)((t - 1) & 1) * Gd + u) * RES_NS + 8 + 2 * (q >> 2) + (q & 1)), x);
+                else v = is_max ? fmax(v, x) : v + x;
+            }
             fin[q] = v;
         }
         __syncthreads();

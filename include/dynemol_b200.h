@@ -98,6 +98,13 @@ void gpu_unpin_(void* ptr);
 
 #define DYB_MODE_TAYLOR     0  /* reference-parity mode: Taylor.f:35-219 semantics */
 #define DYB_MODE_CHEBYSHEV  1  /* Chebyshev/Bessel series on the spectrally rescaled H' */
+/* Parity modes that reproduce the reference's GPU files decision for decision: one term fewer
+ * per Taylor series, raw powers H'^k psi with c_k applied in the sum, cublasIdamax-style term test with a strict `<`
+ * (Taylor_gpu.cpp:334-480,511-622), and the un-rescaled Chebyshev series of Chebyshev_gpu.cpp:347-485,524-643
+ * (valid for tau * ||H'|| <~ 1 only, as in the reference).  Single GPU.  Checked on the B200 against the reference's
+ * own binaries (oracle/_ref/libref_taylor_gpu.so, libref_chebyshev_gpu.so). */
+#define DYB_MODE_TAYLOR_REFGPU     2
+#define DYB_MODE_CHEBYSHEV_REFGPU  3
 
 #define DYB_KERNEL_AUTO 0
 #define DYB_KERNEL_TMA  1   /* TMA + mbarrier staged persistent kernel (default) */
@@ -135,9 +142,6 @@ int  dyb_plan(int N, int n_rows, int sm_count, int64_t* out8, int32_t* seg_base,
 /* Host-only: blocking of the shared-memory-resident series kernel (DYB_SERIES_RESIDENT) for an N x N operator.
  * out6 = {grid side, block size, smem column stride, dynamic smem bytes, threads per CTA, fits (0/1)}. */
 int  dyb_resident_plan(int N, int sm_count, int64_t smem_optin_bytes, int64_t* out6);
-/* Same for the streamed 2-D block kernel (DYB_SERIES_BLOCKED): out6 = {grid side, block size, smem column stride,
- * dynamic smem bytes, chunk columns, fits (0/1)}. */
-int  dyb_blocked_plan(int N, int sm_count, int64_t smem_optin_bytes, int64_t* out6);
 
 /* Host-only: the tau of every remaining sub-step of the steady loop (Taylor.f:81-126: t += tau*h_bar, a last shorter
  * sub-step when less than one tau is left) assuming every norm test passes -- the schedule the library predicts when it
@@ -155,15 +159,14 @@ int  dyb_destroy(dyb_ctx* ctx);
 int  dyb_set_kernel(dyb_ctx* ctx, int kernel_variant);
 /* How the terms of one series (one Convergence() call / one steady sub-step of Taylor.f:81-126) are launched:
  *   PER_TERM  two launches per term (dual product + fused epilogue, chained by programmatic dependent launch);
- *   STREAM    one cooperative launch per series, H' streamed by TMA every term (single GPU, >= 3 tiles per CTA);
  *   RESIDENT  one cooperative launch per series, H' blocked over the shared memories of the SMs for the whole
  *             series (single GPU, N <= ~1800: the QM regions of the Ehrenfest / CSDM examples);
- *   AUTO      RESIDENT when the operator fits, else PER_TERM (default; env DYNEMOL_B200_SERIES=term|stream|resident|auto). */
+ *   AUTO      RESIDENT when the operator fits, else PER_TERM (default; env DYNEMOL_B200_SERIES=term|resident|auto).
+ * (Values 2 and 4 were the round-1 streaming-cooperative and streamed-block kernels: measured slower than PER_TERM
+ * everywhere, removed; DESIGN.md keeps the measurements.) */
 #define DYB_SERIES_AUTO     0
 #define DYB_SERIES_PER_TERM 1
-#define DYB_SERIES_STREAM   2
 #define DYB_SERIES_RESIDENT 3
-#define DYB_SERIES_BLOCKED  4   /* one cooperative launch per series, H' streamed as 12 x 12 blocks (single GPU, 768 <= N <= 6144) */
 int  dyb_set_series_kernel(dyb_ctx* ctx, int kind);
 int  dyb_get_info(dyb_ctx* ctx, int64_t* info16);   /* [0]=N [1]=ld [2]=n_rows [3]=grid [4]=tiles [5]=segments [6]=sm_count [7]=smem_bytes [8]=variant ... [13]=series kernel in effect [14]=resident grid side [15]=resident block size */
 

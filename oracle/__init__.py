@@ -26,6 +26,7 @@ _LIB = os.path.join(_HERE, "_build", "liboracle.so")
 _REF_CHEB = os.path.join(_HERE, "_ref", "libref_chebyshev_cpu.so")
 _REF_XPU = os.path.join(_HERE, "_ref", "libref_xpu_cpu.so")
 _REF_TAYLOR_GPU = os.path.join(_HERE, "_ref", "libref_taylor_gpu.so")
+_REF_CHEB_GPU = os.path.join(_HERE, "_ref", "libref_chebyshev_gpu.so")
 
 ORDER = 25
 H_BAR = 6.58264e-4  # eV*ps, constants_m.f:23
@@ -68,7 +69,7 @@ def build(force: bool = False) -> None:
     src = os.path.join(_HERE, "elhl_oracle.cpp")
     stale = (not os.path.exists(_LIB)) or os.path.getmtime(_LIB) < os.path.getmtime(src)
     need_ref = os.path.exists("/root/reference/Chebyshev_gpu.cpp") and not (
-        os.path.exists(_REF_CHEB) and os.path.exists(_REF_XPU))
+        os.path.exists(_REF_CHEB) and os.path.exists(_REF_XPU) and os.path.exists(_REF_TAYLOR_GPU) and os.path.exists(_REF_CHEB_GPU))
     if force or stale or need_ref:
         subprocess.check_call(["make", "-C", _HERE, "all"], stdout=subprocess.DEVNULL)
 
@@ -364,14 +365,39 @@ def _tgpu():
     return _ref_tgpu
 
 
-def ref_gpu_propagation(H, bra, ket, t_init, t_max, tau):
-    """propagation_gpucaller_ of /root/reference/Taylor_gpu.cpp:295-330 (one particle, H' given, host buffers).
-    Returns (bra, ket, save_tau)."""
+_ref_cgpu = None
+
+
+def ref_cheb_gpu_available() -> bool:
+    """_ref/libref_chebyshev_gpu.so present (Chebyshev_gpu.cpp + the reference's kernels) and a CUDA device."""
+    if not os.path.exists(_REF_CHEB_GPU):
+        return False
+    try:
+        return _cgpu() is not None
+    except OSError:
+        return False
+
+
+def _cgpu():
+    global _ref_cgpu
+    if _ref_cgpu is None:
+        lib_ = C.CDLL(_REF_CHEB_GPU)              # RTLD_LOCAL, own copy of the shim's globals
+        lib_.ref_gpu_init_.restype = C.c_int
+        if lib_.ref_gpu_init_() != 0:
+            raise OSError("ref_gpu_init_ failed (no CUDA device?)")
+        _ref_cgpu = lib_
+    return _ref_cgpu
+
+
+def ref_gpu_propagation(H, bra, ket, t_init, t_max, tau, chebyshev: bool = False):
+    """propagation_gpucaller_ of /root/reference/Taylor_gpu.cpp:295-330 -- or, with chebyshev=True, of
+    /root/reference/Chebyshev_gpu.cpp:308-343 -- (one particle, H' given, host buffers).  Returns (bra, ket, save_tau)."""
     Hf = _fd(H); n = C.c_int(Hf.shape[0])
     b = _fz(bra).copy(order="F"); k = _fz(ket).copy(order="F")
     tau_ = C.c_double(tau); save = C.c_double(0.0)
-    _tgpu().propagation_gpucaller_(C.byref(n), C.byref(tau_), C.byref(save), C.byref(C.c_double(t_init)), C.byref(C.c_double(t_max)),
-                                   _cp(b), _cp(k), _cp(Hf))
+    lib_ = _cgpu() if chebyshev else _tgpu()
+    lib_.propagation_gpucaller_(C.byref(n), C.byref(tau_), C.byref(save), C.byref(C.c_double(t_init)), C.byref(C.c_double(t_max)),
+                                _cp(b), _cp(k), _cp(Hf))
     return b, k, save.value
 
 

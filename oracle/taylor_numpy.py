@@ -299,3 +299,80 @@ def gpu_variant_propagation(Hp, bra, ket, t_init, t_max, tau):
             tau = (t_max - t) / H_BAR
             C = coefficient(tau)
     return bra, ket, tau, save_tau, n_rescale
+
+
+def _max_elem(d):
+    """findMax of Taylor_gpu.cpp:84-89 / Chebyshev_gpu.cpp:92-97: cublasIdamax over the 2n reals, then the modulus of the
+    complex element that owns the winning component."""
+    flat = np.abs(np.ascontiguousarray(d).view(np.float64))
+    return abs(d[int(np.argmax(flat)) // 2])
+
+
+def gpu_variant_cheb_coefficient(tau):
+    """Chebyshev_gpu.cpp:636-643: c_0 = J_0(tau), c_k = 2 J_k(tau) (-i)^k (zi_pow[k+1]); NO spectral rescaling."""
+    from scipy.special import jv
+    k = np.arange(ORDER)
+    c = 2.0 * jv(k, tau) * (-1j) ** k
+    c[0] = jv(0, tau)
+    return c
+
+
+def gpu_variant_cheb_convergence(Hp, bra, ket, tau, norm_ref):
+    """Chebyshev_gpu.cpp:524-632 (convergence_gpu), transcribed: phi_1 = H phi_0, phi_k = 2 H phi_{k-1} - phi_{k-2};
+    k_max = first k in 6..24 with |c_k nakedBessel(k,tau)| < 1e-20 else 25; tests (Idamax style, strict <) from k = 2.
+    Returns (ok, bra, ket, C, k_ref)."""
+    C = gpu_variant_cheb_coefficient(tau)
+    k_max = ORDER
+    for k in range(6, ORDER):
+        if abs(C[k] * _naked_bessel(k, tau)) < 1.0e-20:
+            k_max = k
+            break
+    b0, k0 = bra, ket
+    b1, k1 = Hp.T @ b0, Hp @ k0
+    sb = C[0] * b0 + C[1] * b1; sk = C[0] * k0 + C[1] * k1
+    for k in range(2, k_max):
+        b2 = 2.0 * (Hp.T @ b1) - b0; k2 = 2.0 * (Hp @ k1) - k0
+        nb = sb + C[k] * b2; nk = sk + C[k] * k2
+        if _max_elem(nb - sb) < ERROR and _max_elem(nk - sk) < ERROR:
+            if abs(abs(np.vdot(nb, nk)) - norm_ref) < NORM_ERROR:
+                return True, nb, nk, C, k_max
+        sb, sk = nb, nk
+        b0, b1, k0, k1 = b1, b2, k1, k2
+    return False, bra, ket, C, k_max
+
+
+def gpu_variant_cheb_propagation(Hp, bra, ket, t_init, t_max, tau):
+    """Chebyshev_gpu.cpp:347-485 (chebyshev_gpu).  Returns (bra, ket, tau, save_tau, n_rescale)."""
+    norm_ref = abs(np.vdot(bra, ket))
+    while True:
+        ok, bra, ket, C, k_ref = gpu_variant_cheb_convergence(Hp, bra, ket, tau, norm_ref)
+        if ok:
+            break
+        tau *= 0.9
+    save_tau = tau
+    t = t_init + tau * H_BAR
+    if t_max - t < tau * H_BAR:
+        tau = (t_max - t) / H_BAR
+        C = gpu_variant_cheb_coefficient(tau)
+    n_rescale = 0
+    while t < t_max:
+        b0, k0 = bra, ket
+        b1, k1 = Hp.T @ b0, Hp @ k0
+        sb = C[0] * b0 + C[1] * b1; sk = C[0] * k0 + C[1] * k1
+        for k in range(2, k_ref):
+            b2 = 2.0 * (Hp.T @ b1) - b0; k2 = 2.0 * (Hp @ k1) - k0
+            sb = sb + C[k] * b2; sk = sk + C[k] * k2
+            b0, b1, k0, k1 = b1, b2, k1, k2
+        if abs(abs(np.vdot(sb, sk)) - norm_ref) < NORM_ERROR:
+            bra, ket = sb, sk
+        else:
+            ok = False
+            while not ok:
+                tau *= 0.975
+                n_rescale += 1
+                ok, bra, ket, C, k_ref = gpu_variant_cheb_convergence(Hp, bra, ket, tau, norm_ref)
+        t += tau * H_BAR
+        if t_max - t < tau * H_BAR:
+            tau = (t_max - t) / H_BAR
+            C = gpu_variant_cheb_coefficient(tau)
+    return bra, ket, tau, save_tau, n_rescale

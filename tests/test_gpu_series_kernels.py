@@ -128,66 +128,6 @@ def test_resident_single_particle_and_unequal_series(api, oracle_mod):
     P.close()
 
 
-def test_stream_kernel_matches_per_term(api, oracle_mod):
-    """The cooperative TMA series kernel (one launch per series, H' streamed every term)."""
-    N, dt = 4096, 2e-7
-    w = syn.make_workload(N)
-    P0 = api.Propagator(N)
-    Hp = P0.form_hprime(w.S, w.h)
-    P0.close()
-    tau0 = dt / H_BAR
-    ks, st_s, tr_s, b_s, k_s, _ = run(api, "stream", Hp, w.Psi_bra, w.Psi_ket, dt, tau0)
-    kt, st_t, tr_t, b_t, k_t, _ = run(api, "term", Hp, w.Psi_bra, w.Psi_ket, dt, tau0)
-    assert ks == SERIES_STREAM and kt == SERIES_PER_TERM
-    for p in range(2):
-        assert events3(tr_s[p]) == events3(tr_t[p]) and st_s[p] == st_t[p]
-        assert relerr(b_s[:, p], b_t[:, p]) < 1e-12 and relerr(k_s[:, p], k_t[:, p]) < 1e-12
-
-
-SERIES_BLOCKED = 4
-
-
-# 1828: just above the resident limit (153-row blocks); 3000: 250-row blocks, two ket tasks per thread;
-# 4096: 342-row blocks, one ket group; 6144: the largest (512-row blocks, four tasks per thread)
-@pytest.mark.parametrize("N,dt", [(1828, 5e-7), (3000, 3e-7), (4096, 2e-7), (6144, 1e-7)])
-def test_blocked_taylor_matches_per_term(api, oracle_mod, N, dt):
-    """The streamed 2-D block series kernel (csrc/blocked.cuh) against the launch-per-term path (which the other
-    GPU tests pin against the oracle at these sizes)."""
-    w = syn.make_workload(N)
-    P0 = api.Propagator(N)
-    Hp = P0.form_hprime(w.S, w.h)
-    P0.close()
-    tau0 = dt / H_BAR
-    kb, st_b, tr_b, b_b, k_b, _ = run(api, "blocked", Hp, w.Psi_bra, w.Psi_ket, dt, tau0)
-    kt, st_t, tr_t, b_t, k_t, _ = run(api, "term", Hp, w.Psi_bra, w.Psi_ket, dt, tau0)
-    assert kb == SERIES_BLOCKED and kt == SERIES_PER_TERM
-    for p in range(2):
-        assert events3(tr_b[p]) == events3(tr_t[p]) and st_b[p] == st_t[p]
-        assert tr_b[p].n_matvec_pairs == tr_t[p].n_matvec_pairs
-        assert relerr(b_b[:, p], b_t[:, p]) < 1e-12 and relerr(k_b[:, p], k_t[:, p]) < 1e-12
-
-
-def test_blocked_chebyshev_and_single_particle(api, oracle_mod):
-    N, dt = 2048, 1e-4
-    w = syn.make_workload(N)
-    P0 = api.Propagator(N)
-    Hp = P0.form_hprime(w.S, w.h)
-    P0.upload_hprime(Hp)
-    P0.set_packets(w.Psi_bra, w.Psi_ket)
-    bounds = P0.estimate_spectral_bounds(n_iter=40, margin=0.05)
-    P0.close()
-    tau0 = dt / H_BAR
-    out = {k: run(api, k, Hp, w.Psi_bra, w.Psi_ket, dt, tau0, mode=api.MODE_CHEBYSHEV, bounds=bounds) for k in ("blocked", "term")}
-    (kb, st_b, tr_b, b_b, k_b, _), (kt, st_t, tr_t, b_t, k_t, _) = out["blocked"], out["term"]
-    assert kb == SERIES_BLOCKED and kt == SERIES_PER_TERM
-    for p in range(2):
-        assert events3(tr_b[p]) == events3(tr_t[p]) and st_b[p] == st_t[p]
-        assert relerr(b_b[:, p], b_t[:, p]) < 1e-12 and relerr(k_b[:, p], k_t[:, p]) < 1e-12
-    # electron alone: same bits as in the batched run
-    k1, st1, tr1, b1, kk1, _ = run(api, "blocked", Hp, w.Psi_bra[:, 0], w.Psi_ket[:, 0], dt, tau0, mode=api.MODE_CHEBYSHEV, bounds=bounds)
-    assert np.array_equal(b1[:, 0], b_b[:, 0]) and np.array_equal(kk1[:, 0], k_b[:, 0])
-
-
 def test_chained_steady_loop_is_bit_identical(api):
     """Small operators run the whole steady loop of a nuclear step (Taylor.f:81-126) in ONE launch: the host predicts the
     sub-step schedule, the device chains the sub-steps (PartPass::begin / chain) and stops at a failed norm test.  Against

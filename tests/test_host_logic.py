@@ -91,21 +91,6 @@ def test_resident_plan_blocking():
     assert api.resident_plan(1824, sm_count=64)["fits"] == 0
 
 
-def test_blocked_plan_blocking():
-    """Host arithmetic of the streamed 2-D block series kernel (csrc/blocked.cuh, opt-in): full 12 x 12 grid, blocks of
-    64..512 rows, three chunk stages + vector blocks + partial buffers within the opt-in shared memory."""
-    from dynemol_b200 import api
-    for N in (768, 1000, 1825, 2048, 3000, 4096, 5000, 6144):
-        p = api.blocked_plan(N)
-        assert p["fits"] == 1, N
-        assert p["grid_side"] == 12 and p["grid_side"] * p["block"] >= N and (p["grid_side"] - 1) * p["block"] < N
-        assert 64 <= p["block"] <= 512 and p["smem_stride"] % 2 == 1
-        assert 8 <= p["chunk_cols"] <= 64 and p["smem_bytes"] <= 227 * 1024 - 2048
-        assert 3 * p["chunk_cols"] * p["smem_stride"] * 8 < p["smem_bytes"]
-    for N in (100, 700, 6145, 16384):
-        assert api.blocked_plan(N)["fits"] == 0
-
-
 @pytest.mark.parametrize("name", ["prop_N64_dt5e-6", "prop_N128_dt2e-5", "cheb_N64_dt5e-4", "cheb_N128_dt5e-5"])
 def test_steady_schedule_matches_oracle_traces(golden_dir, name):
     """dyb_steady_schedule (the sub-step schedule the library predicts when it chains the steady loop of Taylor.f:81-126

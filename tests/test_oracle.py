@@ -235,3 +235,22 @@ def test_gpu_variant_transcription_vs_cpu_variant(oracle_mod):
         assert np.abs(gb - cb).max() / np.abs(cb).max() < 2e-7 and np.abs(gk - ck).max() / np.abs(ck).max() < 2e-7
         assert abs(abs(np.vdot(gb, gk)) - 1.0) < 1e-7
         assert 0.0 < g_save <= c_save <= tau0
+
+
+def test_chebyshev_gpu_variant_transcription_vs_expm(oracle_mod):
+    """The numpy transcription of the reference's un-linked Chebyshev GPU driver (Chebyshev_gpu.cpp:347-485,524-643,
+    oracle/taylor_numpy.py gpu_variant_cheb_*; pinned against the reference's own binary on the GPU box by
+    tests/test_gpu_refgpu_modes.py) agrees with expm and with the CPU-style restatement (ebar = 0, de = 1) within the
+    series tolerance; the two differ only in the term test (Idamax element + strict `<` against complex modulus + `>`)."""
+    from oracle import taylor_numpy as tn
+    N, dt = 96, 2e-6
+    w = syn.make_workload(N)
+    Hp = _hprime(oracle_mod, w)
+    tau0 = dt / tn.H_BAR
+    U = expm(-1j * tau0 * Hp)
+    for p in range(2):
+        gb, gk, _, g_save, _ = tn.gpu_variant_cheb_propagation(Hp, w.Psi_bra[:, p].copy(), w.Psi_ket[:, p].copy(), 0.0, dt, tau0)
+        cb, ck, _, c_save, _ = oracle_mod.cheb_scaled_propagation(Hp, w.Psi_bra[:, p], w.Psi_ket[:, p], 0.0, dt, tau0, 0.0, 1.0)
+        assert np.abs(gb - cb).max() / np.abs(cb).max() < 2e-7 and np.abs(gk - ck).max() / np.abs(ck).max() < 2e-7
+        assert np.abs(U @ w.Psi_ket[:, p] - gk).max() < 2e-7 and np.abs(U.T @ w.Psi_bra[:, p] - gb).max() < 2e-7
+        assert 0.0 < g_save <= tau0 and 0.0 < c_save <= tau0
