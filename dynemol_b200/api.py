@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DYNEMOL_B200_LIB") or os.path.join(_HERE, "lib", "libdynemol_b200.so")   # override: tuning builds
 
 H_BAR = 6.58264e-4          # eV*ps (constants_m.f:23)
-MODE_TAYLOR, MODE_CHEBYSHEV, MODE_TAYLOR_REFGPU, MODE_CHEBYSHEV_REFGPU = 0, 1, 2, 3
+MODE_TAYLOR, MODE_CHEBYSHEV, MODE_TAYLOR_REFGPU, MODE_CHEBYSHEV_REFGPU, MODE_CHEBYSHEV_FULL = 0, 1, 2, 3, 4
 KERNEL_AUTO, KERNEL_TMA, KERNEL_LDG = 0, 1, 2
 MAX_EVENTS = 256
 
@@ -66,6 +66,11 @@ def _load() -> C.CDLL:
     lib.dyb_launch_count.restype = C.c_int64
     lib.dyb_launch_count.argtypes = [C.c_void_p]
     lib.nakedbessel_.restype = C.c_double
+    lib.dyb_team_last_error.restype = C.c_char_p
+    lib.dyb_team_passes_last.restype = C.c_int64
+    lib.dyb_team_passes_last.argtypes = [C.c_void_p]
+    lib.dyb_unwrap_pin_bytes.restype = C.c_int64
+    lib.dyb_legacy_passes_last.restype = C.c_int64
     return lib
 
 
@@ -74,7 +79,12 @@ lib = _load()
 # every symbol include/dynemol_b200.h declares (checked by the CPU test-suite)
 DECLARED_SYMBOLS = [
     "propagationelhl_gpucaller_", "propagationelhl2_gpucaller_", "propagation_gpucaller_", "nakedbessel_", "ehrenfestkernel_gpu_", "ehrenfestkernel2_gpu_",
-    "gpu_init_", "gpu_finalize_", "gpu_pin_", "gpu_unpin_",
+    "gpu_init_", "gpu_finalize_", "gpu_pin_", "gpu_unpin_", "xpu_syinvert_", "xpu_dsymm_", "xpu_dzgemv_",
+    "dyb_team_create", "dyb_team_destroy", "dyb_team_size", "dyb_team_form_hprime", "dyb_team_wait_outputs", "dyb_team_upload_hprime",
+    "dyb_team_set_packets", "dyb_team_get_packets", "dyb_team_set_spectral_bounds", "dyb_team_estimate_spectral_bounds",
+    "dyb_team_propagate", "dyb_team_ao_bra", "dyb_team_populations", "dyb_team_quasiparticle_energies", "dyb_team_run_terms",
+    "dyb_team_passes_last", "dyb_team_last_error", "dyb_unwrap_pin_bytes", "dyb_legacy_passes_last",
+    "dyb_form_hprime_async", "dyb_wait_outputs", "dyb_download_hprime_rows_device", "dyb_comm_p2p_open_local",
     "dyb_last_error", "dyb_version", "dyb_device_count", "dyb_plan", "dyb_resident_plan", "dyb_steady_schedule", "dyb_series_coefficients", "dyb_create", "dyb_destroy", "dyb_set_kernel", "dyb_set_series_kernel",
     "dyb_get_info", "dyb_upload_hprime", "dyb_upload_hprime_device", "dyb_upload_hprime_rows_device", "dyb_hprime_device", "dyb_form_hprime", "dyb_form_hprime_device", "dyb_form_hprime_from_overlap",
     "dyb_download_hprime", "dyb_set_packets", "dyb_get_packets", "dyb_propagate", "dyb_ao_bra",
@@ -147,6 +157,101 @@ def device_count() -> int:
     return int(lib.dyb_device_count())
 
 
+def unwrap_pin_bytes(size_bytes_i32: int) -> int:
+    """The byte count gpu_pin_ recovers from the wrapped 32-bit `n*n*8` the Fortran caller passes (host arithmetic)."""
+    return int(lib.dyb_unwrap_pin_bytes(C.c_int(np.int64(size_bytes_i32).astype(np.int32))))
+
+
+def _tcheck(rc: int):
+    if rc != 0:
+        raise DynemolB200Error(rc, lib.dyb_team_last_error().decode())
+
+
+class Team:
+    """Single-process multi-GPU: `n_dev` row-sharded contexts behind one caller (include/dynemol_b200.h, dyb_team_*).
+    Same host-buffer interface as Propagator; H' = S^-1 h is formed on the first device and scattered over NVLink."""
+
+    def __init__(self, N: int, n_dev: int, devices=None):
+        self.N, self.n_dev = int(N), int(n_dev)
+        self._h = C.c_void_p()
+        devs = None if devices is None else (C.c_int * n_dev)(*devices)
+        _tcheck(lib.dyb_team_create(C.byref(self._h), C.c_int(n_dev), devs, C.c_int(N)))
+        self.n_part = 0
+
+    def close(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._h = C.c_void_p()
+            try:
+                lib.dyb_team_destroy(h)
+            except Exception:
+                pass
+
+    __del__ = close
+
+    def form_hprime(self, S, h, want_hprime: bool = True):
+        S = _fd(S); h = _fd(h)
+        out = np.empty((self.N, self.N), dtype=np.float64, order="F") if want_hprime else None
+        _tcheck(lib.dyb_team_form_hprime(self._h, _p(S), _p(h), _p(out) if want_hprime else None))
+        _tcheck(lib.dyb_team_wait_outputs(self._h))
+        return out
+
+    def upload_hprime(self, H):
+        H = _fd(H)
+        _tcheck(lib.dyb_team_upload_hprime(self._h, _p(H), C.c_int64(self.N)))
+
+    def set_packets(self, bra, ket):
+        bra = _fz(bra); ket = _fz(ket)
+        if bra.ndim == 1:
+            bra = np.asfortranarray(bra[:, None]); ket = np.asfortranarray(ket[:, None])
+        self.n_part = bra.shape[1]
+        _tcheck(lib.dyb_team_set_packets(self._h, C.c_int(self.n_part), _p(bra), _p(ket)))
+
+    def get_packets(self):
+        bra = np.empty((self.N, self.n_part), dtype=np.complex128, order="F"); ket = np.empty_like(bra, order="F")
+        _tcheck(lib.dyb_team_get_packets(self._h, C.c_int(self.n_part), _p(bra), _p(ket)))
+        return bra, ket
+
+    def set_spectral_bounds(self, emin, emax):
+        _tcheck(lib.dyb_team_set_spectral_bounds(self._h, C.c_double(emin), C.c_double(emax)))
+
+    def estimate_spectral_bounds(self, n_iter: int = 40, margin: float = 0.05):
+        lo = C.c_double(); hi = C.c_double()
+        _tcheck(lib.dyb_team_estimate_spectral_bounds(self._h, C.c_int(n_iter), C.c_double(margin), C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def propagate(self, t_init, t_max, tau, mode: int = MODE_TAYLOR):
+        tau2 = np.zeros(2); tau2[: self.n_part] = np.broadcast_to(np.asarray(tau, dtype=np.float64), (self.n_part,))
+        save = np.zeros(2)
+        traces = (Trace * 2)()
+        _tcheck(lib.dyb_team_propagate(self._h, C.c_int(mode), C.c_double(t_init), C.c_double(t_max), _p(tau2), _p(save), traces))
+        return save[: self.n_part].copy(), [traces[i] for i in range(self.n_part)]
+
+    def ao_bra(self):
+        out = np.empty((self.N, self.n_part), dtype=np.complex128, order="F")
+        _tcheck(lib.dyb_team_ao_bra(self._h, C.c_int(self.n_part), _p(out)))
+        return out
+
+    def populations(self, fragment, n_frag: int, t: float):
+        frag = np.ascontiguousarray(fragment, dtype=np.int32)
+        out = np.zeros((n_frag + 2, self.n_part), dtype=np.float64, order="F")
+        _tcheck(lib.dyb_team_populations(self._h, C.c_int(self.n_part), C.c_int(n_frag), _p(frag), C.c_double(t), _p(out)))
+        return out
+
+    def quasiparticle_energies(self):
+        out = np.zeros(4)
+        _tcheck(lib.dyb_team_quasiparticle_energies(self._h, C.c_int(self.n_part), _p(out)))
+        return (out[0::2] + 1j * out[1::2])[: self.n_part]
+
+    def run_terms(self, tau: float, n_terms: int):
+        ms = C.c_float(0.0)
+        _tcheck(lib.dyb_team_run_terms(self._h, C.c_double(tau), C.c_int(n_terms), C.byref(ms)))
+        return ms.value
+
+    def passes_last(self) -> int:
+        return int(lib.dyb_team_passes_last(self._h))
+
+
 class Propagator:
     """Native handle API: one GPU, one basis size, H' and the wavepackets resident in HBM."""
 
@@ -197,6 +302,10 @@ class Propagator:
     def upload_hprime_rows_device(self, d_ptr: int, lda: int, local_row0: int, n_rows: int):
         """A block of owned rows of H' from a device buffer holding only those rows (n_rows x N, column-major)."""
         _check(lib.dyb_upload_hprime_rows_device(self._h, C.c_void_p(d_ptr), C.c_int64(lda), C.c_int(local_row0), C.c_int(n_rows)))
+
+    def download_hprime_rows_device(self, d_ptr: int, ldd: int, local_row0: int, n_rows: int):
+        """Copy owned rows local_row0.. of the resident H' (all N columns) into a column-major device buffer (n_rows x N)."""
+        _check(lib.dyb_download_hprime_rows_device(self._h, C.c_void_p(d_ptr), C.c_int64(ldd), C.c_int(local_row0), C.c_int(n_rows)))
 
     def hprime_device(self):
         ptr = C.c_void_p(); ld = C.c_int64()
@@ -327,7 +436,7 @@ def _ref(x, ctype):
     return C.byref(ctype(x))
 
 
-def legacy_propagationelhl(S, h, PSI_bra, PSI_ket, t_init, t_max, tau, batched: bool | None = None, copy_inputs: bool = True):
+def legacy_propagationelhl(S, h, PSI_bra, PSI_ket, t_init, t_max, tau, batched: bool | None = None, copy_inputs: bool = True, out_H=None):
     """call PropagationElHl_gpucaller(N, S, h0, H_prime, AO_bra(:,p), AO_ket(:,p), Psi_t_bra(:,p), Psi_t_ket(:,p),
     t_init, t_max, tau, save_tau)  -- ElHl_Chebyshev_GPU.f:269-272.  PSI_* of shape (N,) use the per-particle
     symbol, shape (N,2) the batched el+hole symbol.  Returns dict(H_prime, AO_bra, PSI_bra, PSI_ket, save_tau)."""
@@ -340,7 +449,10 @@ def legacy_propagationelhl(S, h, PSI_bra, PSI_ket, t_init, t_max, tau, batched: 
     two = PSI_bra.ndim == 2 and PSI_bra.shape[1] == 2
     if batched is None:
         batched = two
-    Hp = np.zeros((N, N), dtype=np.float64, order="F")
+    # out_H: the caller's persistent (N, N) Fortran-ordered H_prime array (the Fortran caller allocates and pins it once,
+    # ElHl_Chebyshev_GPU.f:109-111); default: a fresh one per call
+    Hp = np.zeros((N, N), dtype=np.float64, order="F") if out_H is None else out_H
+    assert Hp.shape == (N, N) and Hp.flags.f_contiguous
     AO_bra = np.zeros_like(PSI_bra, order="F"); AO_ket = np.full_like(PSI_bra, np.nan, order="F")
     n = C.c_int(N); ti = C.c_double(t_init); tm = C.c_double(t_max)
     if batched:
@@ -390,13 +502,48 @@ def gpu_init(pid: int = 0, procs_per_dev: int = 1):
     lib.gpu_init_(C.byref(C.c_int(pid)), C.byref(C.c_int(procs_per_dev)))
 
 
+def legacy_passes_last() -> int:
+    """el+hole terms of the last propagation made through a legacy symbol."""
+    return int(lib.dyb_legacy_passes_last())
+
+
 def gpu_finalize():
     lib.gpu_finalize_()
 
 
 def gpu_pin(a: np.ndarray):
-    lib.gpu_pin_(_p(a), C.byref(C.c_int(np.int64(a.nbytes).astype(np.int32))))
+    """call GPU_Pin(a, n*n*8): the size travels as a Fortran DEFAULT integer, i.e. wrapped to 32 bits, like the caller's."""
+    lib.gpu_pin_(_p(a), C.byref(C.c_int(int(np.array(a.nbytes, dtype=np.int64).astype(np.int32)))))
 
 
 def gpu_unpin(a: np.ndarray):
     lib.gpu_unpin_(_p(a))
+
+
+def xpu_syinvert(A, uplo: str = "U"):
+    """call xPU_syInvert(A, UpLo, N, info) -- GPU_Interface.cpp:861-873 (Matrix_math.f:193).  Returns (A^-1, info)."""
+    A = np.array(A, dtype=np.float64, order="F", copy=True); n = C.c_int(A.shape[0]); info = C.c_int(0)
+    lib.xpu_syinvert_(_p(A), C.c_char_p(uplo.encode()), C.byref(n), C.byref(info))
+    return A, info.value
+
+
+def xpu_dsymm(A, B, side: str = "L", uplo: str = "U", alpha: float = 1.0, beta: float = 0.0, Cin=None):
+    """call xPU_dsymm(side, uplo, m, n, alpha, A, ldA, B, ldB, beta, C, ldC) -- GPU_Interface.cpp:574-627 (Matrix_math.f:119)."""
+    A = _fd(A); B = _fd(B); m, n = B.shape
+    out = np.zeros((m, n), dtype=np.float64, order="F") if Cin is None else np.array(Cin, dtype=np.float64, order="F", copy=True)
+    lib.xpu_dsymm_(C.c_char_p(side.encode()), C.c_char_p(uplo.encode()), C.byref(C.c_int(m)), C.byref(C.c_int(n)), C.byref(C.c_double(alpha)),
+                   _p(A), C.byref(C.c_int(A.shape[0])), _p(B), C.byref(C.c_int(m)), C.byref(C.c_double(beta)), _p(out), C.byref(C.c_int(m)))
+    return out
+
+
+def xpu_dzgemv(trans: str, A, x, alpha=1.0 + 0.0j, beta=0.0 + 0.0j, y=None):
+    """call xPU_dzgemv(trans, m, n, alpha, A, ldA, x, 1, beta, y, 1) -- GPU_Interface.cpp:405-496 (Matrix_math.f:234-300)."""
+    A = _fd(A); m, n = A.shape
+    x = _fz(x)
+    ly = n if trans.upper() in ("T", "C") else m
+    out = np.zeros(ly, dtype=np.complex128) if y is None else _fz(y)
+    a = np.array([alpha.real, alpha.imag]); b = np.array([complex(beta).real, complex(beta).imag])
+    one = C.c_int(1)
+    lib.xpu_dzgemv_(C.c_char_p(trans.encode()), C.byref(C.c_int(m)), C.byref(C.c_int(n)), _p(a), _p(A), C.byref(C.c_int(m)),
+                    _p(x), C.byref(one), _p(b), _p(out), C.byref(one))
+    return out

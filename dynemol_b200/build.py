@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdynemol_b200.so")
-SOURCES = ["propagator.cu", "legacy_abi.cu"]
+SOURCES = ["propagator.cu", "legacy_abi.cu", "team.cu", "xpu_abi.cu"]
 import glob
 # every header the sources include: csrc/*.cuh plus the public C header
 HEADERS = sorted(os.path.basename(f) for f in glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join("..", "..", "include", "dynemol_b200.h")]

@@ -30,7 +30,6 @@ struct LanczosState {
     int    ok[2][LZ_MAX_IT];           // step j has a sound successor (b2 above the breakdown threshold)
     int    alive[2];
     int    bad_start[2];               // <bra|ket> not positive: the packets are not an S-dual pair
-    double coef[2 * (LZ_MAX_IT + 2) * 4];   // coefficient lists for lz_combine_kernel: [list][q][particle](re, im)
 };
 
 // out[(q*2 + p)*2 + {0,1}] = sum_i conj(X_q[i,p]) * y[i,p]   (dotc: conjugated first argument), i over M owned rows.
@@ -63,9 +62,9 @@ lz_dots_kernel(int M, const double* __restrict__ X, size_t x_stride, const doubl
 }
 
 // y[i,p] = s_p * ( x[i,p] - sum_{q < nq} X_q[i,p] * c[q][p] )     (c complex, s real; x may alias y)
-__global__ void lz_combine_kernel(int M, const double* __restrict__ x, const double* __restrict__ X, size_t x_stride, int nq,
+__global__ void lz_combine_kernel(int M, const double* x, const double* __restrict__ X, size_t x_stride, int nq,
                                   const double* __restrict__ coef /* [nq][2](re,im) */, const double* __restrict__ scale /* [2] or null */,
-                                  double* __restrict__ y)
+                                  double* y)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = idx >> 1, p = idx & 1;
@@ -101,9 +100,10 @@ __global__ void lz_scalar_kernel(int op, int j, const double* __restrict__ d /* 
         st->beta[p][0] = 0.0;
         scale_out[p] = good ? 1.0 / sqrt(re) : 0.0;
     } else if (op == LZ_OP_ALPHA) {
-        st->alpha[p][j] = re;
-        coef_out[(0 * 2 + p) * 2] = re;               coef_out[(0 * 2 + p) * 2 + 1] = 0.0;     // * v_j
-        coef_out[(1 * 2 + p) * 2] = st->beta[p][j];   coef_out[(1 * 2 + p) * 2 + 1] = 0.0;     // * v_{j-1}
+        st->alpha[p][j] = re;                         // list over {v_{j-1}, v_j} (contiguous in the vector store); j = 0: {v_0}
+        const int qa = (j > 0) ? 1 : 0;
+        if (j > 0) { coef_out[(0 * 2 + p) * 2] = st->beta[p][j]; coef_out[(0 * 2 + p) * 2 + 1] = 0.0; }
+        coef_out[(qa * 2 + p) * 2] = re; coef_out[(qa * 2 + p) * 2 + 1] = 0.0;
     } else {
         const double a = st->alpha[p][j];
         const bool good = st->alive[p] && (re > 1e-24 * (1.0 + a * a));
@@ -113,13 +113,6 @@ __global__ void lz_scalar_kernel(int op, int j, const double* __restrict__ d /* 
         st->beta[p][j + 1] = b;
         scale_out[p] = good ? 1.0 / b : 0.0;
     }
-}
-
-// Gram-Schmidt coefficients are the dots themselves: copy [nq][2](re,im) (kept as a kernel so the run needs no host sync)
-__global__ void lz_copy_kernel(int n, const double* __restrict__ src, double* __restrict__ dst)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = src[i];
 }
 
 }  // namespace dyb

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <dlfcn.h>
@@ -26,6 +27,7 @@
 #include "matvec.cuh"
 #include "epilogue.cuh"
 #include "resident.cuh"
+#include "lanczos.cuh"
 
 using namespace dyb;
 typedef std::complex<double> cplx;
@@ -97,6 +99,11 @@ struct dyb_ctx {
     PassParams* d_passes = nullptr;      // per-term parameters of the series in flight
     unsigned long long* gbar = nullptr;  // grid barrier counter
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // host <-> device copies that overlap work on `stream` (h upload behind potrf, H' download behind the series)
+    cudaEvent_t ev_h_up = nullptr, ev_H_done = nullptr;
+    std::thread out_thread;              // runs the (possibly host-blocking, pageable) download of H' beside the series
+    int out_rc = 0;
+    std::string out_err;
     CUtensorMap tmap;
     bool have_tmap = false;
 
@@ -110,10 +117,13 @@ struct dyb_ctx {
     int *seg_base = nullptr, *pseg_start = nullptr, *frag = nullptr;
     Ctrl* ctrl = nullptr;                // device
     Ctrl* h_ctrl = nullptr;              // pinned host mirror
-    double* h_scal = nullptr;            // pinned, 64 doubles
+    double* h_scal = nullptr;            // pinned, 128 doubles
     int n_part = 0;
     bool have_bounds = false;
     double emin = 0.0, emax = 0.0;       // spectral bounds of H' for the Chebyshev mode
+    double *lz_V = nullptr, *lz_W = nullptr, *lz_dots = nullptr;     // device Lanczos: vector stores [(n_iter+1)][M][NQ], dot/coefficient scratch
+    LanczosState* lz_state = nullptr;
+    int lz_cap = 0;                      // iterations the vector stores are sized for
     int64_t launches = 0;
     int64_t passes_last = 0;             // el+hole terms (passes over H') of the last propagate / run_terms
     cublasHandle_t blas = nullptr;
@@ -126,6 +136,7 @@ struct dyb_ctx {
     double *rs_send = nullptr, *rs_recv = nullptr, *scal_all = nullptr, *full_tmp = nullptr;
     // fused peer-memory exchange (NVLink P2P through CUDA IPC): one shared buffer per rank
     bool p2p = false;
+    bool p2p_local = false;              // peers are contexts of this process (dyb_team): mapped by peer access, not by IPC
     char* comm_buf = nullptr;            // [rs_send x2 | ket vectors x3 | scalar tables x2 | ready flags | done flags]
     char* peer_base[MAX_PEERS] = {nullptr};
     size_t off_rs[2] = {0, 0}, off_vk[3] = {0, 0, 0}, off_scal[2] = {0, 0}, off_ready = 0, off_done = 0, comm_bytes = 0;
@@ -750,6 +761,122 @@ static int propagate_series(dyb_ctx* c, int mode_in, double t_init, double t_max
     return DYB_OK;
 }
 
+// ------------------------------------------------------------------------------------------ single-expansion Chebyshev
+// DYB_MODE_CHEBYSHEV_FULL: ONE Chebyshev expansion for the whole interval t_init .. t_max of a nuclear step instead of the
+// reference's chain of order-25 series (Chebyshev_gpu.cpp:347-485 caps the order at 25, so a 0.5 fs step at R = dE*tau
+// ~ 500 is cut into ~95 sub-steps of 24 terms; the Bessel coefficients only start to decay at k ~ R, which makes a
+// single expansion of R + O(R^(1/3)) terms the cheaper AND the more accurate way to cross the interval):
+//     psi(t_max) = sum_{k<K} c_k T_k(Ht) psi ,  c_0 = J_0(R) e^{-i ebar tau} , c_k = 2 (-i)^k J_k(R) e^{-i ebar tau}   (same series,
+//     Chebyshev_gpu.cpp:552-589,636-643), K = first k > R with 2|J_k(R)| < 1e-15 (beyond k = R the coefficients fall
+//     super-exponentially, so the tail is below that bound too).
+// One norm test at the end (the reference's 1e-8, Taylor.f:104).  A failed test means the spectral interval did not
+// enclose the spectrum (T_k grows outside [-1,1]) or the order is out of reach: the interval is widened once, then the
+// step is cut in two, keeping the packets of the last accepted expansion.
+static std::vector<cplx> cheb_full_coefficients(double tau, double ebar, double de) {
+    static const cplx pw[4] = {cplx(1, 0), cplx(0, -1), cplx(-1, 0), cplx(0, 1)};
+    const double R = de * tau;
+    const cplx ph = std::exp(cplx(0.0, -ebar * tau));
+    std::vector<cplx> C;
+    C.push_back(jn(0, R) * ph);
+    for (int k = 1; k < (1 << 20); ++k) {
+        const double j = jn(k, R);
+        if ((double)k > R && k >= 2 && 2.0 * fabs(j) < 1.0e-15) break;
+        C.push_back((2.0 * j) * pw[k & 3] * ph);
+    }
+    return C;
+}
+
+// the terms of one expansion through whichever path applies: the resident kernel in ONE launch, else a dual product +
+// fused epilogue per term (PDL-chained), with the three rotating vectors of the recurrence
+static int run_pass_list(dyb_ctx* c, const std::vector<PassParams>& passes) {
+    int rc;
+    if (resident_ok(c) && (int)passes.size() <= MAX_CHAIN_PASSES) return run_series_resident(c, passes);
+    int prv = 2, cur = 0, nxt = 1;
+    for (const PassParams& pp : passes) {
+        EpiParams E = epi_params(c, cur, prv, nxt);
+        E.pass = pp;
+        if ((rc = run_term(c, E, cur, nxt, true))) return rc;
+        const int old_prv = prv; prv = cur; cur = nxt; nxt = old_prv;
+    }
+    return DYB_OK;
+}
+
+static int propagate_cheb_full(dyb_ctx* c, double t_init, double t_max, const double* tau_in, double* save_tau, dyb_trace* traces)
+{
+    double nref[2];
+    int rc = compute_norm_ref(c, nref);
+    if (rc) return rc;
+    for (int p = 0; p < c->n_part; ++p) if (traces) { memset(&traces[p], 0, sizeof(dyb_trace)); traces[p].norm_ref = nref[p]; }
+    // Taylor.f:65-81: a slice of zero (or negative) length still advances by the given tau
+    double remaining = (t_max - t_init) / H_BAR;
+    if (!(remaining > 0.0)) remaining = std::max(tau_in[0], c->n_part > 1 ? tau_in[1] : tau_in[0]);
+    double emin = c->emin, emax = c->emax;
+    double tau = remaining;
+    int adopt[2] = {0, 0};
+    const int active[2] = {1, c->n_part > 1 ? 1 : 0};
+    bool first_ok = false, widened = false;
+    c->passes_last = 0;
+    for (int attempt = 0; remaining > 0.0; ++attempt) {
+        if (attempt > 64) return fail(DYB_EINVAL, "single-expansion Chebyshev step does not pass the norm test (tau=%g)", tau);
+        tau = std::min(tau, remaining);
+        const double ebar = 0.5 * (emax + emin), de = 0.5 * (emax - emin);
+        std::vector<cplx> C = cheb_full_coefficients(tau, ebar, de);
+        if (resident_ok(c) && (int)C.size() - 1 > MAX_CHAIN_PASSES) { tau *= 0.5; continue; }    // one launch holds 4096 terms
+        const int K = (int)C.size();
+        if (K < 2) C.push_back(cplx(0.0, 0.0));
+        const int n_terms = std::max(1, K - 1);
+        std::vector<PassParams> passes(n_terms);
+        for (int s = 0; s < n_terms; ++s) {
+            memset(&passes[s], 0, sizeof(PassParams));
+            for (int p = 0; p < 2; ++p) {
+                if (!active[p]) continue;
+                PartPass& a = passes[s].part[p];
+                const int j = s + 1;
+                a.active = 1; a.norm_ref = nref[p]; a.k = j; a.three_term = 1; a.scale_term = 1;
+                a.c_re = C[j].real(); a.c_im = C[j].imag();
+                if (j == 1) { a.alpha_re = 1.0 / de; a.beta_re = -ebar / de; a.gamma = 0.0; }
+                else        { a.alpha_re = 2.0 / de; a.beta_re = -2.0 * ebar / de; a.gamma = -1.0; }
+                a.last = (s == n_terms - 1) ? 1 : 0; a.last_ok_by_norm = 1;
+            }
+        }
+        const cplx sum_scale[2] = {C[0], C[0]};
+        if ((rc = launch_series_init(c, adopt, active, 0, sum_scale))) return rc;
+        adopt[0] = adopt[1] = 0;
+        if ((rc = run_pass_list(c, passes))) return rc;
+        if ((rc = read_ctrl(c))) return rc;
+        c->passes_last += n_terms;
+        bool ok = true;
+        for (int p = 0; p < c->n_part; ++p) {
+            const PartState& st = c->h_ctrl->part[p];
+            ok = ok && st.latched && st.ok;
+            if (traces) {
+                traces[p].n_convergence_calls++; traces[p].n_matvec_pairs += n_terms; traces[p].last_k_ref = K;
+                trace_event(&traces[p], 1, st.ok ? K : 0, st.ok, tau);
+            }
+        }
+        if (ok) {
+            adopt[0] = active[0]; adopt[1] = active[1];
+            if (!first_ok) { first_ok = true; for (int p = 0; p < c->n_part; ++p) save_tau[p] = tau; }
+            remaining -= tau;
+            if (remaining < 1e-12 * tau) remaining = 0.0;
+        } else if (!widened) {                                  // most likely cause: an eigenvalue outside the estimated interval
+            const double w = emax - emin;
+            emin -= 0.10 * w; emax += 0.10 * w; widened = true;
+            if (traces) for (int p = 0; p < c->n_part; ++p) traces[p].n_rescale++;
+        } else {
+            tau *= 0.5;
+            if (traces) for (int p = 0; p < c->n_part; ++p) traces[p].n_rescale++;
+        }
+    }
+    if (adopt[0] || adopt[1]) {
+        const int none[2] = {0, 0};
+        if ((rc = launch_series_init(c, adopt, none, 0))) return rc;
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    if (traces) for (int p = 0; p < c->n_part; ++p) traces[p].final_tau = tau;
+    return DYB_OK;
+}
+
 // ------------------------------------------------------------------------------------------ C ABI: native
 extern "C" {
 
@@ -824,16 +951,22 @@ int dyb_device_count(void) {
 int dyb_destroy(dyb_ctx* c) {
     if (!c) return DYB_OK;
     cudaSetDevice(c->device);
+    if (c->out_thread.joinable()) c->out_thread.join();
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->ev_h_up) cudaEventDestroy(c->ev_h_up);
+    if (c->ev_H_done) cudaEventDestroy(c->ev_H_done);
     if (c->vk_in_comm) c->vk[0] = c->vk[1] = c->vk[2] = nullptr;       // they live inside comm_buf, freed below
     double** bufs[] = {&c->H, &c->S, &c->psi_b, &c->psi_k, &c->sum_b, &c->sum_k, &c->vb[0], &c->vb[1], &c->vb[2],
                        &c->vk[0], &c->vk[1], &c->vk[2], &c->ket_slab, &c->bra_slab, &c->blockpart, &c->scal, &c->io};
     for (auto b : bufs) if (*b) cudaFree(*b);
-    if (c->p2p) for (int r = 0; r < c->world; ++r) if (r != c->rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
+    if (c->p2p && !c->p2p_local) for (int r = 0; r < c->world; ++r) if (r != c->rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
     if (c->comm_buf) cudaFree(c->comm_buf);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     for (double** b : {&c->rs_send, &c->rs_recv, &c->scal_all, &c->full_tmp}) if (*b) cudaFree(*b);
     if (c->ipiv) cudaFree(c->ipiv);
+    for (double* b : {c->lz_V, c->lz_W, c->lz_dots}) if (b) cudaFree(b);
+    if (c->lz_state) cudaFree(c->lz_state);
     if (c->seg_base) cudaFree(c->seg_base);
     if (c->pseg_start) cudaFree(c->pseg_start);
     if (c->frag) cudaFree(c->frag);
@@ -872,6 +1005,9 @@ int dyb_create(dyb_ctx** out, int device, int N, int row0, int n_rows) {
 #define CKCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int r_ = fail(e_ == cudaErrorMemoryAllocation ? DYB_ENOMEM : DYB_ECUDA, \
         "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); dyb_destroy(c); return r_; } } while (0)
     CKCU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CKCU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CKCU(cudaEventCreateWithFlags(&c->ev_h_up, cudaEventDisableTiming));
+    CKCU(cudaEventCreateWithFlags(&c->ev_H_done, cudaEventDisableTiming));
     CKC(build_plan(c));
     c->Lq = (size_t)std::max(c->NP * PANEL_ROWS, c->Ncpad) + PANEL_ROWS;
     CKCU(cudaMalloc(&c->H, (size_t)c->ld * N * sizeof(double)));
@@ -887,7 +1023,7 @@ int dyb_create(dyb_ctx** out, int device, int N, int row0, int n_rows) {
     CKCU(cudaMalloc(&c->ctrl, sizeof(Ctrl)));
     CKCU(cudaMemset(c->ctrl, 0, sizeof(Ctrl)));
     CKCU(cudaMallocHost(&c->h_ctrl, sizeof(Ctrl)));
-    CKCU(cudaMallocHost(&c->h_scal, 64 * sizeof(double)));
+    CKCU(cudaMallocHost(&c->h_scal, 128 * sizeof(double)));
     CKC(build_tensor_map(c));
     CKCU(cudaFuncSetAttribute(dual_matvec_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TmaSmem::total));
     CKCU(cudaMalloc(&c->d_passes, sizeof(PassParams) * MAX_CHAIN_PASSES));
@@ -1005,6 +1141,14 @@ int dyb_download_hprime(dyb_ctx* c, double* h_H, int64_t lda) {
     return DYB_OK;
 }
 
+int dyb_download_hprime_rows_device(dyb_ctx* c, void* d_dst, int64_t ldd, int local_row0, int n_rows) {
+    if (!c || !d_dst || n_rows < 1 || ldd < n_rows || local_row0 < 0 || local_row0 + n_rows > c->M) return fail(DYB_EINVAL, "bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpy2DAsync(d_dst, (size_t)ldd * 8, c->H + local_row0, (size_t)c->ld * 8, (size_t)n_rows * 8, c->N, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return DYB_OK;
+}
+
 static int ensure_solver(dyb_ctx* c) {
     if (!c->solver) {
         CKS(cusolverDnCreate(&c->solver));
@@ -1025,7 +1169,9 @@ struct DevScratch {                         // freed on every exit path
     ~DevScratch() { if (p) cudaFree(p); }
 };
 
-static int factor_and_solve(dyb_ctx* c, const std::function<int()>& reload_S) {
+// `load_h` brings h into c->H; it runs after the factorisation has been queued, so an upload on the copy stream (or a
+// host-blocking pageable copy) overlaps potrf.  `reload_S` restores S for the LU fallback.
+static int factor_and_solve(dyb_ctx* c, const std::function<int()>& reload_S, const std::function<int()>& load_h = nullptr) {
     const int64_t n = c->N;
     c->have_factor = false;
     size_t wd = 0, wh = 0;
@@ -1036,7 +1182,9 @@ static int factor_and_solve(dyb_ctx* c, const std::function<int()>& reload_S) {
     cusolverStatus_t st = cusolverDnXpotrf(c->solver, c->sparams, CUBLAS_FILL_MODE_UPPER, n, CUDA_R_64F, c->S, n, CUDA_R_64F,
                                            w1.p, wd, h_work.data(), wh, d_info);
     int info = 0;
-    if (st == CUSOLVER_STATUS_SUCCESS) { CK(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+    if (st == CUSOLVER_STATUS_SUCCESS) CK(cudaMemcpyAsync(c->h_scal + 100, d_info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (load_h) { int rc = load_h(); if (rc) return rc; }
+    if (st == CUSOLVER_STATUS_SUCCESS) { CK(cudaStreamSynchronize(c->stream)); info = *reinterpret_cast<int*>(c->h_scal + 100); }
     if (st != CUSOLVER_STATUS_SUCCESS) return fail(DYB_ECUDA, "cusolverDnXpotrf status %d", (int)st);
     if (info == 0) {
         CKS(cusolverDnXpotrs(c->solver, c->sparams, CUBLAS_FILL_MODE_UPPER, n, n, CUDA_R_64F, c->S, n, CUDA_R_64F, c->H, c->ld, d_info));
@@ -1061,18 +1209,57 @@ static int factor_and_solve(dyb_ctx* c, const std::function<int()>& reload_S) {
     return DYB_OK;
 }
 
-int dyb_form_hprime(dyb_ctx* c, const double* h_S, const double* h_h, double* h_H_out) {
+// Wait for the download of H' started by dyb_form_hprime_async (no-op when none is pending).
+int dyb_wait_outputs(dyb_ctx* c) {
+    if (!c) return fail(DYB_EINVAL, "ctx is NULL");
+    if (c->out_thread.joinable()) {
+        c->out_thread.join();
+        if (c->out_rc) return fail(c->out_rc, "%s", c->out_err.c_str());
+    }
+    return DYB_OK;
+}
+
+// H' = S^-1 h from host S, h with the transfers overlapped: S goes up first and its factorisation is queued; h goes up on
+// the copy stream while potrf runs; the download of H' (8 N^2 bytes) starts on the copy stream as soon as the solve ends
+// and runs beside whatever the caller queues next (Lanczos, the series).  It is issued from a helper thread because a
+// copy into pageable host memory blocks the issuing thread; with pinned buffers (GPU_Pin, ElHl_Chebyshev_GPU.f:109-111)
+// it is a plain asynchronous DMA.  dyb_wait_outputs() joins it: h_H_out is complete only after that call.
+int dyb_form_hprime_async(dyb_ctx* c, const double* h_S, const double* h_h, double* h_H_out) {
     if (!c || !h_S || !h_h) return fail(DYB_EINVAL, "NULL argument");
     if (c->M != c->N) return fail(DYB_EINVAL, "dyb_form_hprime needs the full matrix on one device (row shard given)");
     CK(cudaSetDevice(c->device));
-    int rc = ensure_solver(c);
+    int rc = dyb_wait_outputs(c);
     if (rc) return rc;
+    if ((rc = ensure_solver(c))) return rc;
     const size_t n = c->N;
     auto load_S = [&]() -> int { CK(cudaMemcpyAsync(c->S, h_S, n * n * 8, cudaMemcpyHostToDevice, c->stream)); return DYB_OK; };
+    auto load_h = [&]() -> int {
+        CK(cudaMemcpy2DAsync(c->H, (size_t)c->ld * 8, h_h, n * 8, n * 8, n, cudaMemcpyHostToDevice, c->copy_stream));
+        CK(cudaEventRecord(c->ev_h_up, c->copy_stream));
+        CK(cudaStreamWaitEvent(c->stream, c->ev_h_up, 0));
+        return DYB_OK;
+    };
+    CK(cudaStreamSynchronize(c->copy_stream));            // nothing of a previous call may still be reading c->H
     if ((rc = load_S())) return rc;
-    CK(cudaMemcpy2DAsync(c->H, (size_t)c->ld * 8, h_h, n * 8, n * 8, n, cudaMemcpyHostToDevice, c->stream));
-    if ((rc = factor_and_solve(c, load_S))) return rc;
-    if (h_H_out) CK(cudaMemcpy2DAsync(h_H_out, n * 8, c->H, (size_t)c->ld * 8, n * 8, n, cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = factor_and_solve(c, load_S, load_h))) return rc;
+    if (h_H_out) {
+        CK(cudaEventRecord(c->ev_H_done, c->stream));
+        CK(cudaStreamWaitEvent(c->copy_stream, c->ev_H_done, 0));
+        c->out_rc = 0;
+        c->out_thread = std::thread([c, h_H_out, n]() {
+            cudaError_t e = cudaSetDevice(c->device);
+            if (e == cudaSuccess) e = cudaMemcpy2DAsync(h_H_out, n * 8, c->H, (size_t)c->ld * 8, n * 8, n, cudaMemcpyDeviceToHost, c->copy_stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->copy_stream);
+            if (e != cudaSuccess) { c->out_rc = DYB_ECUDA; c->out_err = std::string("download of H' failed: ") + cudaGetErrorString(e); }
+        });
+    }
+    return DYB_OK;
+}
+
+int dyb_form_hprime(dyb_ctx* c, const double* h_S, const double* h_h, double* h_H_out) {
+    int rc = dyb_form_hprime_async(c, h_S, h_h, h_H_out);
+    if (rc) return rc;
+    if ((rc = dyb_wait_outputs(c))) return rc;
     CK(cudaStreamSynchronize(c->stream));
     return DYB_OK;
 }
@@ -1210,8 +1397,8 @@ int dyb_comm_unique_id(char* out128) {
 // ---- fused peer-memory exchange: every rank exports one IPC buffer, then maps the peers' buffers --------------
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-int dyb_comm_p2p_handle(dyb_ctx* c, char* out64) {
-    if (!c || !out64) return fail(DYB_EINVAL, "NULL argument");
+// the exchange buffer of the fused peer-memory path (allocated once; the rotating ket vectors move into it)
+static int p2p_alloc(dyb_ctx* c) {
     if (!c->comm || c->world < 2) return fail(DYB_EINVAL, "dyb_comm_init (world >= 2) must come first");
     if (c->world > MAX_PEERS) return fail(DYB_EINVAL, "at most %d ranks", MAX_PEERS);
     CK(cudaSetDevice(c->device));
@@ -1232,6 +1419,13 @@ int dyb_comm_p2p_handle(dyb_ctx* c, char* out64) {
         for (int i = 0; i < 3; ++i) { if (c->vk[i]) cudaFree(c->vk[i]); c->vk[i] = reinterpret_cast<double*>(c->comm_buf + c->off_vk[i]); }
         c->vk_in_comm = true;
     }
+    return DYB_OK;
+}
+
+int dyb_comm_p2p_handle(dyb_ctx* c, char* out64) {
+    if (!c || !out64) return fail(DYB_EINVAL, "NULL argument");
+    int rc = p2p_alloc(c);
+    if (rc) return rc;
     cudaIpcMemHandle_t h;
     CK(cudaIpcGetMemHandle(&h, c->comm_buf));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -1252,6 +1446,30 @@ int dyb_comm_p2p_open(dyb_ctx* c, const char* handles /* world x 64 bytes, rank 
         c->peer_base[r] = static_cast<char*>(ptr);
     }
     c->p2p = true;
+    return DYB_OK;
+}
+
+// Same-process peers (dyb_team: one host thread per GPU): no IPC, the peers' buffers are mapped by enabling peer access
+// between the devices.  Two phases so that every member has allocated its buffer before anybody maps it:
+// phase 0 allocates, phase 1 (after a barrier of the caller) maps.  members: world contexts in rank order.
+int dyb_comm_p2p_open_local(dyb_ctx* c, dyb_ctx* const* members, int phase) {
+    if (!c || !members) return fail(DYB_EINVAL, "NULL argument");
+    if (phase == 0) return p2p_alloc(c);
+    if (!c->comm_buf) return fail(DYB_EINVAL, "phase 0 must come first");
+    CK(cudaSetDevice(c->device));
+    for (int r = 0; r < c->world; ++r) {
+        if (!members[r] || !members[r]->comm_buf) return fail(DYB_EINVAL, "member %d has no exchange buffer", r);
+        if (r != c->rank) {
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, c->device, members[r]->device));
+            if (!can) return fail(DYB_ECUDA, "device %d cannot access device %d", c->device, members[r]->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(members[r]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(DYB_ECUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        c->peer_base[r] = members[r]->comm_buf;
+    }
+    c->p2p = true; c->p2p_local = true;
     return DYB_OK;
 }
 
@@ -1294,8 +1512,9 @@ int dyb_propagate(dyb_ctx* c, int mode, double t_init, double t_max, const doubl
         return fail(DYB_EINVAL, "the reference-GPU parity modes are single-GPU (like the reference's GPU path)");
     if (mode == DYB_MODE_TAYLOR || mode == DYB_MODE_TAYLOR_REFGPU || mode == DYB_MODE_CHEBYSHEV_REFGPU)
         return propagate_series(c, mode, t_init, t_max, tau, save_tau, traces);
-    if (mode == DYB_MODE_CHEBYSHEV) {
+    if (mode == DYB_MODE_CHEBYSHEV || mode == DYB_MODE_CHEBYSHEV_FULL) {
         if (!c->have_bounds) return fail(DYB_EINVAL, "Chebyshev mode needs spectral bounds: dyb_set_spectral_bounds / dyb_estimate_spectral_bounds");
+        if (mode == DYB_MODE_CHEBYSHEV_FULL) return propagate_cheb_full(c, t_init, t_max, tau, save_tau, traces);
         return propagate_series(c, mode, t_init, t_max, tau, save_tau, traces);
     }
     return fail(DYB_EINVAL, "unknown mode %d", mode);
@@ -1422,89 +1641,128 @@ static double tridiag_eig(const std::vector<double>& a, const std::vector<double
     return 0.5 * (lo + hi);
 }
 
+// In-place sum over the ranks of a row-sharded run (no-op on one GPU)
+static int allreduce_sum(dyb_ctx* c, double* buf, size_t n) {
+    if (c->world > 1) CKN(g_nccl.AllReduce(buf, buf, n, ncclDouble, ncclSum, c->comm, c->stream));
+    return DYB_OK;
+}
+
+// One dual product with no series state: yk[row0 + i] = (H' xk)_i for the owned rows, yb[i] = (H'^T xb)_(row0+i).
+// xk: full-length ket vector (global index, zero padded), xb: owned slice of the bra vector (zero padded to the panels).
+static int plain_dual_matvec(dyb_ctx* c, const double* xk, const double* xb, double* yk, double* yb) {
+    int rc;
+    if ((rc = launch_matvec(c, xk, xb, false))) return rc;
+    if (c->world > 1) {
+        const int n2 = 2 * c->N;
+        bra_panel_reduce_kernel<<<(n2 + 255) / 256, 256, 0, c->stream>>>(c->N, c->NP, c->Ncpad, c->bra_slab, c->rs_send);
+        c->launches++;
+        CK(cudaGetLastError());
+        CKN(g_nccl.ReduceScatter(c->rs_send, c->rs_recv, (size_t)c->M * NQ, ncclDouble, ncclSum, c->comm, c->stream));
+    }
+    EpiParams E = epi_params(c, 0, 0, 1);
+    E.nxt_k = yk; E.nxt_b = yb;
+    slab_reduce_kernel<<<(2 * c->M + 255) / 256, 256, 0, c->stream>>>(E);
+    c->launches++;
+    CK(cudaGetLastError());
+    return DYB_OK;
+}
+
+// The owned ket slices of all ranks -> one full-length vector on every rank (one GPU: a copy)
+static int gather_ket(dyb_ctx* c, const double* slice, double* full) {
+    if (c->world > 1) CKN(g_nccl.AllGather(slice, full, (size_t)c->M * NQ, ncclDouble, c->comm, c->stream));
+    else CK(cudaMemcpyAsync(full, slice, (size_t)c->M * NQ * 8, cudaMemcpyDeviceToDevice, c->stream));
+    return DYB_OK;
+}
+
 // Lanczos in the S inner product started from the current packets (w0 = Psi_bra = S v0, v0 = Psi_ket): because
 // H'^T S = S H', the left vectors stay w_j = S v_j and the recurrence is the symmetric one; every step is one
 // dual product (H' v_j and H'^T w_j) of the hot kernel.  Ritz values lie inside the spectrum, hence `margin`
-// (fraction of the width added on both sides).  Vectors live on the host (O(N) work per step).
+// (fraction of the width added on both sides).  Vectors, dot products and the scalar decisions live on the device
+// (lanczos.cuh); the host downloads the tridiagonal coefficients once at the end.  Row-sharded contexts take part with
+// their owned rows (collective call: partial dots are all-reduced, the ket vector is all-gathered before each product).
 int dyb_estimate_spectral_bounds(dyb_ctx* c, int n_iter, double margin, double* emin_out, double* emax_out) {
-    if (!c || n_iter < 2) return fail(DYB_EINVAL, "bad argument");
+    if (!c || n_iter < 2 || n_iter > LZ_MAX_IT) return fail(DYB_EINVAL, "bad argument (2 <= n_iter <= %d)", LZ_MAX_IT);
     if (c->n_part < 1) return fail(DYB_EINVAL, "dyb_set_packets must be called first (the packets start the Lanczos run)");
-    if (c->M != c->N) return fail(DYB_EINVAL, "row-sharded contexts: pass bounds with dyb_set_spectral_bounds");
-    const int np = c->n_part; const size_t n = c->N;
-    std::vector<dyb_complex> w(n * np), v(n * np), wp(n * np, dyb_complex{0, 0}), vp(n * np, dyb_complex{0, 0}), hw(n * np), hv(n * np);
-    int rc = dyb_get_packets(c, np, w.data(), v.data());
-    if (rc) return rc;
-    // host loops are O(n_iter^2 N): threaded with OpenMP.  Sums run over fixed blocks of 4096 elements (one thread per
-    // block) and the block partials are added in order: the result depends neither on the thread count nor on the schedule
-    // (an OpenMP reduction clause does not promise that), so the estimated interval is bit-reproducible run to run.
-    const long nn = (long)n;
-    auto blocked_dot = [&](const dyb_complex* x, const dyb_complex* y, double& re, double& im) {
-        const long BL = 4096, nb = (nn + BL - 1) / BL;
-        std::vector<double> pr(nb), pi(nb);
-        #pragma omp parallel for schedule(static)
-        for (long b = 0; b < nb; ++b) {
-            double sr = 0, si = 0;
-            const long i1 = std::min(nn, (b + 1) * BL);
-            for (long i = b * BL; i < i1; ++i) { sr += x[i].re * y[i].re + x[i].im * y[i].im; si += x[i].re * y[i].im - x[i].im * y[i].re; }
-            pr[b] = sr; pi[b] = si;
-        }
-        re = 0; im = 0;
-        for (long b = 0; b < nb; ++b) { re += pr[b]; im += pi[b]; }
+    if (c->world > 1 && !c->comm) return fail(DYB_EINVAL, "row-sharded context: call dyb_comm_init first");
+    CK(cudaSetDevice(c->device));
+    const int np = c->n_part, M = c->M;
+    const size_t stride = (size_t)M * NQ;
+    if (c->lz_cap < n_iter) {
+        for (double** b : {&c->lz_V, &c->lz_W}) { if (*b) cudaFree(*b); *b = nullptr; }
+        CK(cudaMalloc(&c->lz_V, (size_t)(n_iter + 1) * stride * 8));
+        CK(cudaMalloc(&c->lz_W, (size_t)(n_iter + 1) * stride * 8));
+        c->lz_cap = n_iter;
+    }
+    if (!c->lz_dots) CK(cudaMalloc(&c->lz_dots, (size_t)(2 * (LZ_MAX_IT + 1) * 4 + 16) * 8));
+    if (!c->lz_state) CK(cudaMalloc(&c->lz_state, sizeof(LanczosState)));
+    CK(cudaMemsetAsync(c->lz_state, 0, sizeof(LanczosState), c->stream));
+    double* const dots = c->lz_dots;                                   // [2 (j+1)][2](re,im): Gram-Schmidt coefficients / single dots
+    double* const coef = c->lz_dots + 2 * (LZ_MAX_IT + 1) * 4;         // three-term coefficient list (2 entries)
+    double* const scale = coef + 8;
+    const unsigned vg = (unsigned)((2 * M + 255) / 256);
+    int rc;
+    auto dots_of = [&](const double* X, int nq, const double* y, double* out) -> int {
+        lz_dots_kernel<<<nq, LZ_THREADS, 0, c->stream>>>(M, X, stride, y, out);
+        c->launches++;
+        CK(cudaGetLastError());
+        return DYB_OK;
     };
-    auto dotc_re = [&](const dyb_complex* x, const dyb_complex* y) { double re, im; blocked_dot(x, y, re, im); return re; };
-    std::vector<std::vector<double>> al(np), be(np);
-    std::vector<double> beta(np, 0.0);
-    std::vector<bool> alive(np, true);
-    // all Lanczos vectors are kept: without re-biorthogonalisation the two-sided recurrence loses the duality
-    // w_j = S v_j after ~35 steps and produces Ritz values far outside the spectrum
-    std::vector<std::vector<dyb_complex>> Wall(np), Vall(np);
-    auto dotc_c = [&](const dyb_complex* x, const dyb_complex* y, double& re, double& im) { blocked_dot(x, y, re, im); };
-    for (int p = 0; p < np; ++p) {
-        const double n0 = dotc_re(&w[p * n], &v[p * n]);
-        if (!(n0 > 0.0)) return fail(DYB_EINVAL, "<bra|ket> of particle %d is not positive: packets are not an S-dual pair", p);
-        const double sc = 1.0 / sqrt(n0);
-        for (size_t i = 0; i < n; ++i) { w[p * n + i].re *= sc; w[p * n + i].im *= sc; v[p * n + i].re *= sc; v[p * n + i].im *= sc; }
-        Wall[p].reserve((size_t)n_iter * n); Vall[p].reserve((size_t)n_iter * n);
-    }
+    auto combine = [&](const double* x, const double* X, int nq, const double* cf, const double* sc, double* y) -> int {
+        lz_combine_kernel<<<vg, 256, 0, c->stream>>>(M, x, X, stride, nq, cf, sc, y);
+        c->launches++;
+        CK(cudaGetLastError());
+        return DYB_OK;
+    };
+    auto scalar = [&](int op, int j) -> int {
+        lz_scalar_kernel<<<1, 32, 0, c->stream>>>(op, j, dots, c->lz_state, coef, scale);
+        c->launches++;
+        CK(cudaGetLastError());
+        return DYB_OK;
+    };
+    auto V = [&](int j) { return c->lz_V + (size_t)j * stride; };
+    auto W = [&](int j) { return c->lz_W + (size_t)j * stride; };
+    const double* v0 = c->psi_k + (size_t)c->row0 * NQ;                // owned slices of the packets
+    const double* w0 = c->psi_b;
+    // normalise: <w0|v0> = 1
+    if ((rc = dots_of(w0, 1, v0, dots)) || (rc = allreduce_sum(c, dots, 4)) || (rc = scalar(LZ_OP_START, 0))) return rc;
+    if ((rc = combine(v0, v0, 0, dots, scale, V(0))) || (rc = combine(w0, w0, 0, dots, scale, W(0)))) return rc;
     for (int j = 0; j < n_iter; ++j) {
-        if ((rc = dyb_dual_matvec(c, np, w.data(), v.data(), hw.data(), hv.data()))) return rc;
-        bool any = false;
-        for (int p = 0; p < np; ++p) {
-            if (!alive[p]) continue;
-            dyb_complex *W = &w[p * n], *V = &v[p * n], *WP = &wp[p * n], *VP = &vp[p * n], *HW = &hw[p * n], *HV = &hv[p * n];
-            const double a = dotc_re(W, HV);
-            Wall[p].insert(Wall[p].end(), W, W + n); Vall[p].insert(Vall[p].end(), V, V + n);
-            const double bp = beta[p];
-            #pragma omp parallel for schedule(static)
-            for (long i = 0; i < nn; ++i) {
-                const dyb_complex nv = {HV[i].re - a * V[i].re - bp * VP[i].re, HV[i].im - a * V[i].im - bp * VP[i].im};
-                const dyb_complex nw = {HW[i].re - a * W[i].re - bp * WP[i].re, HW[i].im - a * W[i].im - bp * WP[i].im};
-                VP[i] = V[i]; WP[i] = W[i]; V[i] = nv; W[i] = nw;
-            }
-            for (int q = 0; q <= j; ++q) {                       // full two-sided Gram-Schmidt: w_q^H v' = 0, v_q^H w' = 0
-                const dyb_complex *Wq = &Wall[p][(size_t)q * n], *Vq = &Vall[p][(size_t)q * n];
-                double cr, ci, dr, di;
-                dotc_c(Wq, V, cr, ci); dotc_c(Vq, W, dr, di);
-                #pragma omp parallel for schedule(static)
-                for (long i = 0; i < nn; ++i) {
-                    V[i].re -= Vq[i].re * cr - Vq[i].im * ci; V[i].im -= Vq[i].re * ci + Vq[i].im * cr;
-                    W[i].re -= Wq[i].re * dr - Wq[i].im * di; W[i].im -= Wq[i].re * di + Wq[i].im * dr;
-                }
-            }
-            const double b2 = dotc_re(W, V);
-            if (!(b2 > 1e-24 * (1.0 + a * a))) { alive[p] = false; if (j == 0) { al[p].push_back(a); be[p].push_back(0.0); } continue; }
-            al[p].push_back(a); be[p].push_back(beta[p]);        // a step is only accepted once its successor is sound
-            beta[p] = sqrt(b2);
-            const double sc = 1.0 / beta[p];
-            for (size_t i = 0; i < n; ++i) { V[i].re *= sc; V[i].im *= sc; W[i].re *= sc; W[i].im *= sc; }
-            any = true;
+        // H' v_j and H'^T w_j: one dual product
+        if ((rc = gather_ket(c, V(j), c->vk[0]))) return rc;
+        CK(cudaMemcpyAsync(c->vb[0], W(j), stride * 8, cudaMemcpyDeviceToDevice, c->stream));
+        if ((rc = plain_dual_matvec(c, c->vk[0], c->vb[0], c->vk[1], c->vb[1]))) return rc;
+        const double* hv = c->vk[1] + (size_t)c->row0 * NQ;
+        const double* hw = c->vb[1];
+        // alpha_j = <w_j|H'v_j> ; v' = H'v_j - alpha_j v_j - beta_j v_{j-1} (same for w')
+        if ((rc = dots_of(W(j), 1, hv, dots)) || (rc = allreduce_sum(c, dots, 4)) || (rc = scalar(LZ_OP_ALPHA, j))) return rc;
+        const int j0 = j > 0 ? j - 1 : 0, n3 = j > 0 ? 2 : 1;
+        if ((rc = combine(hv, V(j0), n3, coef, nullptr, V(j + 1))) || (rc = combine(hw, W(j0), n3, coef, nullptr, W(j + 1)))) return rc;
+        // full two-sided Gram-Schmidt against every previous pair, applied twice: w_q^H v' = 0, v_q^H w' = 0
+        for (int sweep = 0; sweep < 2; ++sweep) {
+            double* dA = dots; double* dB = dots + (size_t)(j + 1) * 4;
+            if ((rc = dots_of(W(0), j + 1, V(j + 1), dA)) || (rc = dots_of(V(0), j + 1, W(j + 1), dB))) return rc;
+            if ((rc = allreduce_sum(c, dots, (size_t)2 * (j + 1) * 4))) return rc;
+            if ((rc = combine(V(j + 1), V(0), j + 1, dA, nullptr, V(j + 1))) || (rc = combine(W(j + 1), W(0), j + 1, dB, nullptr, W(j + 1)))) return rc;
         }
-        if (!any) break;
+        // beta_{j+1}^2 = <w'|v'> ; breakdown test ; normalise
+        if ((rc = dots_of(W(j + 1), 1, V(j + 1), dots)) || (rc = allreduce_sum(c, dots, 4)) || (rc = scalar(LZ_OP_BETA, j))) return rc;
+        if ((rc = combine(V(j + 1), V(0), 0, dots, scale, V(j + 1))) || (rc = combine(W(j + 1), W(0), 0, dots, scale, W(j + 1)))) return rc;
     }
+    static_assert(sizeof(LanczosState) < (1 << 16), "LanczosState");
+    std::vector<char> hbuf(sizeof(LanczosState));
+    CK(cudaMemcpyAsync(hbuf.data(), c->lz_state, sizeof(LanczosState), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const LanczosState& st = *reinterpret_cast<const LanczosState*>(hbuf.data());
     double lo = 1e300, hi = -1e300;
     for (int p = 0; p < np; ++p) {
-        if (al[p].empty()) continue;
-        lo = std::min(lo, tridiag_eig(al[p], be[p], 0)); hi = std::max(hi, tridiag_eig(al[p], be[p], 1));
+        if (st.bad_start[p]) return fail(DYB_EINVAL, "<bra|ket> of particle %d is not positive: packets are not an S-dual pair", p);
+        std::vector<double> al, be;
+        for (int j = 0; j < n_iter; ++j) {            // a step is only accepted once its successor is sound
+            if (st.ok[p][j]) { al.push_back(st.alpha[p][j]); be.push_back(st.beta[p][j]); }
+            else { if (j == 0) { al.push_back(st.alpha[p][0]); be.push_back(0.0); } break; }
+        }
+        if (al.empty()) continue;
+        lo = std::min(lo, tridiag_eig(al, be, 0)); hi = std::max(hi, tridiag_eig(al, be, 1));
     }
     if (!(hi > lo)) return fail(DYB_EINVAL, "Lanczos produced a degenerate interval");
     const double width = hi - lo;
@@ -1552,17 +1810,19 @@ int dyb_ao_bra(dyb_ctx* c, int n_part, dyb_complex* h_AO_bra) {
 // one more dual product of the hot kernel and a dot product, no second pass over h.  out = (re,im) per particle.
 int dyb_quasiparticle_energies(dyb_ctx* c, int n_part, double* out_reim) {
     if (!c || !out_reim || n_part < 1 || n_part > 2) return fail(DYB_EINVAL, "bad argument");
-    if (c->M != c->N) return fail(DYB_EINVAL, "full-matrix contexts only");
+    if (c->world > 1 && !c->comm) return fail(DYB_EINVAL, "row-sharded context: call dyb_comm_init first");
     CK(cudaSetDevice(c->device));
     int rc;
-    if ((rc = launch_matvec(c, c->psi_k, c->psi_b, false))) return rc;
-    EpiParams E = epi_params(c, 0, 0, 1);
-    slab_reduce_kernel<<<(2 * c->M + 255) / 256, 256, 0, c->stream>>>(E);        // vk[1] = H' Psi_ket
+    const double* xk = c->psi_k;
+    if (c->world > 1) {                    // row-sharded (collective call): every rank needs the whole ket; partial dots are summed
+        if ((rc = gather_ket(c, c->psi_k + (size_t)c->row0 * NQ, c->vk[0]))) return rc;
+        xk = c->vk[0];
+    }
+    if ((rc = plain_dual_matvec(c, xk, c->psi_b, c->vk[1], c->vb[1]))) return rc;      // vk[1] = H' Psi_ket on the owned rows
+    dotc_kernel<<<1, 1024, 0, c->stream>>>(c->M, c->psi_b, c->vk[1] + (size_t)c->row0 * NQ, c->scal);
     c->launches++;
     CK(cudaGetLastError());
-    dotc_kernel<<<1, 1024, 0, c->stream>>>(c->M, c->psi_b, c->vk[1], c->scal);
-    c->launches++;
-    CK(cudaGetLastError());
+    if ((rc = allreduce_sum(c, c->scal, 4))) return rc;
     CK(cudaMemcpyAsync(c->h_scal, c->scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     for (int i = 0; i < 2 * n_part; ++i) out_reim[i] = c->h_scal[i];
@@ -1645,14 +1905,17 @@ int dyb_ehrenfest_kernel2(dyb_ctx* c, const dyb_complex* h_bra, const dyb_comple
 
 int dyb_populations(dyb_ctx* c, int n_part, int n_frag, const int32_t* fragment, double t, double* out) {
     if (!c || !fragment || !out || n_part < 1 || n_part > 2 || n_frag < 0 || n_frag > MAX_FRAG) return fail(DYB_EINVAL, "bad argument");
-    if (c->M != c->N) return fail(DYB_EINVAL, "full-matrix contexts only (row-sharded: gather the packets with dyb_get_packets)");
+    if (c->world > 1 && !c->comm) return fail(DYB_EINVAL, "row-sharded context: call dyb_comm_init first");
     CK(cudaSetDevice(c->device));
     if (!c->frag) CK(cudaMalloc(&c->frag, sizeof(int) * c->N));
     CK(cudaMemcpyAsync(c->frag, fragment, sizeof(int) * c->N, cudaMemcpyHostToDevice, c->stream));
     double* d_out = c->io;                                  // 2*(MAX_FRAG+1) doubles
-    populations_kernel<<<n_part, 256, 0, c->stream>>>(c->N, n_frag, c->frag, c->psi_b, c->psi_k, d_out);
+    if (n_part < 2) CK(cudaMemsetAsync(d_out, 0, sizeof(double) * 2 * (MAX_FRAG + 1), c->stream));
+    // owned rows only; a row-sharded run (collective call) sums the per-rank partials
+    populations_kernel<<<n_part, 256, 0, c->stream>>>(c->M, n_frag, c->frag + c->row0, c->psi_b, c->psi_k + (size_t)c->row0 * NQ, d_out);
     c->launches++;
     CK(cudaGetLastError());
+    { int rc = allreduce_sum(c, d_out, 2 * (MAX_FRAG + 1)); if (rc) return rc; }
     CK(cudaMemcpyAsync(c->h_scal, d_out, sizeof(double) * 2 * (MAX_FRAG + 1), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     for (int p = 0; p < n_part; ++p) {

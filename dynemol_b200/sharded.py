@@ -85,6 +85,8 @@ def synthetic_packets(N: int):
 
 
 def bench_main(args):
+    import faulthandler
+    faulthandler.dump_traceback_later(1500, exit=True)              # never hang a GPU box on a lost collective
     import torch
     import torch.distributed as dist
     from dynemol_b200 import synthetic as syn
@@ -137,6 +139,9 @@ def bench_main(args):
     if rank == 0 and not args.no_ref1:
         ref1 = single_gpu_same_workload(args, N, dev, tau, bra, ket)
     dist.barrier()
+    P.close()
+    # driver-visible correctness of the sharded path: a short checked nuclear step on the same ranks (oracle on rank 0)
+    parity = None if args.no_parity else B.sharded_parity_check(dist, local_rank, dev)       # bench.py: the oracle is its checker
 
     if rank == 0:
         peak, peak_src = B.measured_peak_gbs()
@@ -145,9 +150,9 @@ def bench_main(args):
         line = {"metric": B.METRIC, "value": round(value, 2), "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "synthetic EHT Hamiltonian N=%d basis, row-sharded H' over %d GPUs, %s per term" % (
-                               N, world, "fused NVLink peer-memory exchange (reduce-scatter by peer loads, all-gather by peer stores) inside the epilogue kernel"
-                               if info.get("p2p") else "NCCL reduce-scatter(bra)+all-gather(ket)"),
+                "config": {"workload": B.workload_name(N, world), "gpus": "%dxB200" % world,
+                           "exchange_per_term": "fused NVLink peer-memory exchange (reduce-scatter by peer loads, all-gather by peer stores) inside the epilogue kernel"
+                               if info.get("p2p") else "NCCL reduce-scatter(bra)+all-gather(ket)",
                            "exchange": "p2p-fused" if info.get("p2p") else "nccl",
                            "basis": N, "rows_per_gpu": m, "terms_per_step": B.TERMS_PER_STEP,
                            "l2": "inputs larger than L2 (%.2f GB of H' per GPU per pass)" % (per_gpu_bytes / 1e9),
@@ -157,7 +162,10 @@ def bench_main(args):
                              "alg_bytes_per_launch": per_gpu_bytes},
                 "e2e": {"value": round(e2e_terms / float(te.item()), 2), "unit": B.UNIT, "h2d_bytes_per_step": int(2 * 2 * 16 * N),
                         "d2h_bytes_per_step": int(2 * 2 * 16 * N), "call": "set_packets(host)+%d terms+get_packets(host); H' shards resident" % e2e_terms},
-                "gpu_launches": int(launches), "clocks": clocks, "single_gpu_same_workload": ref1}
+                "gpu_launches": int(launches), "clocks": clocks, "single_gpu_same_workload": ref1, "parity_check": parity}
+        if ref1 and ref1.get("value"):
+            line["speedup_same_workload"] = round(value / ref1["value"], 3)
+            line["efficiency_same_workload"] = round(value / ref1["value"] / world, 4)
         print(json.dumps(line))
     dist.destroy_process_group()
 
@@ -193,3 +201,96 @@ def single_gpu_same_workload(args, N, dev, tau, bra, ket):
     ms, _ = P1.run_terms(tau, B.TERMS_PER_STEP * steps)
     P1.close()
     return {"n_gpus": 1, "value": round(B.TERMS_PER_STEP * steps / (ms * 1e-3), 2), "unit": B.UNIT, "steps": steps}
+
+
+def config5_main(args):
+    """BASELINE config 5: N ~ 30k basis (dye-TiO2-interface size), Taylor vs Chebyshev propagator, 8 x B200.
+    H' = S^-1 h is formed on rank 0 from the synthetic EHT S, h at that size (cuSOLVER), its row blocks are scattered to the
+    ranks, and ONE nuclear step is propagated with each propagator of the library through the row-sharded path (sharded
+    Lanczos bounds included): passes over H' and seconds per nuclear step.  The Taylor series (the reference's shipped
+    propagator, Taylor.f) needs tau * rho(H') ~ 1 per series, so it is timed on a slice of the step (--config5-taylor-frac)
+    and scaled linearly in dt (every sub-step costs the same); both Chebyshev modes run the full 0.5 fs."""
+    import faulthandler
+    faulthandler.dump_traceback_later(1500, exit=True)
+    import torch
+    import torch.distributed as dist
+    from dynemol_b200 import api, synthetic as syn
+    import bench as B
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=dev)
+    N = args.basis or 30720
+    row0, m = shard_rows(N, world, rank)
+    t0 = time.time()
+    packets = torch.empty((2, N, 2), dtype=torch.float64, device=dev)       # [bra|ket][N][el,hl] (real packets)
+    blocks = None
+    form_s = None
+    if rank == 0:
+        S, h, _ = syn.make_S_h_torch(N, dev)
+        w = 64
+        C = torch.zeros((N, 2), dtype=torch.float64, device=dev)
+        C[0:w, 0] = torch.tensor(np.random.default_rng(42).normal(size=w), device=dev)
+        C[w:2 * w, 1] = torch.tensor(np.random.default_rng(43).normal(size=w), device=dev)
+        SC = S @ C
+        nrm = torch.sqrt((C * SC).sum(0))
+        packets[0] = SC / nrm; packets[1] = C / nrm
+        Pf = api.Propagator(N, device=local_rank)
+        torch.cuda.synchronize(dev); t1 = time.time()
+        Pf.form_hprime_device(S.data_ptr(), N, h.data_ptr(), N)
+        form_s = time.time() - t1
+        del S, h, SC, C
+        torch.cuda.empty_cache()
+        blocks = []
+        for r in range(world):
+            blk = torch.empty((N, m), dtype=torch.float64, device=dev)      # column-major m x N block of rows r*m ..
+            Pf.download_hprime_rows_device(blk.data_ptr(), m, r * m, m)
+            blocks.append(blk)
+        Pf.close()
+        torch.cuda.empty_cache()
+    mine = torch.empty((N, m), dtype=torch.float64, device=dev)
+    dist.scatter(mine, blocks, src=0)
+    dist.broadcast(packets, src=0)
+    del blocks
+    P, row0, m = init_sharded(N, dist, local_rank)
+    P.upload_hprime_rows_device(mine.data_ptr(), m, 0, m)
+    del mine
+    torch.cuda.empty_cache()
+    pk = packets.cpu().numpy()
+    Psi_bra = np.asfortranarray(pk[0].astype(np.complex128)); Psi_ket = np.asfortranarray(pk[1].astype(np.complex128))
+    build_s = time.time() - t0
+    dt = 5e-4
+    frac = args.config5_taylor_frac
+    res = {}
+    P.set_packets(Psi_bra, Psi_ket)
+    torch.cuda.synchronize(dev); dist.barrier(); t1 = time.perf_counter()
+    lo, hi = P.estimate_spectral_bounds(24, 0.05)
+    torch.cuda.synchronize(dev); dist.barrier(); lanczos_s = time.perf_counter() - t1
+    for name, mode, dtm in (("chebyshev_single_expansion", api.MODE_CHEBYSHEV_FULL, dt), ("chebyshev_order25_chain", api.MODE_CHEBYSHEV, dt),
+                            ("taylor", api.MODE_TAYLOR, dt * frac)):
+        tau_max = dtm / api.H_BAR
+        P.set_packets(Psi_bra, Psi_ket)
+        save, _ = P.propagate(0.0, dtm, tau_max, mode=mode)                 # first step finds tau (untimed)
+        P.set_packets(Psi_bra, Psi_ket)
+        torch.cuda.synchronize(dev); dist.barrier(); t1 = time.perf_counter()
+        save, traces = P.propagate(0.0, dtm, np.minimum(tau_max, 1.15 * save), mode=mode)
+        torch.cuda.synchronize(dev); dist.barrier(); el = time.perf_counter() - t1
+        te = torch.tensor([el], dtype=torch.float64, device=dev); dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        bra, ket = P.get_packets()
+        terms = int(P.info()["passes_last"])
+        scale = dt / dtm
+        res[name] = {"dt_ps_timed": dtm, "terms_timed": terms, "s_timed": round(float(te.item()), 4),
+                     "terms_per_0.5fs_step": int(round(terms * scale)), "s_per_0.5fs_step": round(float(te.item()) * scale, 4),
+                     "extrapolated": bool(scale != 1.0), "terms_per_s": round(terms / float(te.item()), 1),
+                     "norm_el": float(abs(np.vdot(bra[:, 0], ket[:, 0]))), "norm_hl": float(abs(np.vdot(bra[:, 1], ket[:, 1])))}
+    if rank == 0:
+        line = {"metric": "nuclear step (dt = 0.5 fs) of the el+hole propagator, Taylor vs Chebyshev", "unit": "s per nuclear step", "n_gpus": world,
+                "config": {"workload": "BASELINE config 5: synthetic EHT Hamiltonian N=%d basis (dye-TiO2-interface size), H' = S^-1 h formed on one GPU and row-sharded over %d GPUs" % (N, world),
+                           "basis": N, "rows_per_gpu": m, "exchange": "p2p-fused" if P.info()["p2p"] else "nccl",
+                           "spectral_interval_eV": [lo, hi], "R_dE_tau": round(0.5 * (hi - lo) * dt / api.H_BAR, 1)},
+                "propagators": res, "lanczos_24_steps_s": round(lanczos_s, 4), "form_hprime_s": None if form_s is None else round(form_s, 3),
+                "build_s": round(build_s, 1), "dtype": "f64", "data": "synthetic"}
+        print(json.dumps(line))
+    P.close()
+    dist.destroy_process_group()

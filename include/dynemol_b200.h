@@ -87,6 +87,15 @@ void gpu_finalize_(void);
 void gpu_pin_(void* ptr, int* size_bytes);
 void gpu_unpin_(void* ptr);
 
+/* Replace GPU_Interface.cpp:129-158 (xPU_syInvert :861-873, xPU_dsymm :574-627, xPU_dzgemv :405-496): the three
+ * dispatchers Matrix_math.f routes the path's a2 / a3 / a7 through (Matrix_math.f:183-198, 79-121, 221-301).  WEAK.
+ * Host matrices in and out (column-major); xpu_syinvert_ returns the full symmetric inverse (both triangles). */
+void xpu_syinvert_(double* A, const char* UpLo, const int* N, int* info);
+void xpu_dsymm_(const char* side, const char* UpLo, const int* M, const int* N, const double* alpha, double* hA, const int* LDA,
+                double* hB, const int* LDB, const double* beta, double* hC, const int* LDC);
+void xpu_dzgemv_(const char* transA, const int* M, const int* N, const dyb_complex* alpha, double* hA, const int* LDA,
+                 dyb_complex* hX, const int* incX, const dyb_complex* beta, dyb_complex* hY, const int* incY);
+
 /* ------------------------------------------------------------------ (B) native handle API */
 
 #define DYB_OK        0
@@ -102,9 +111,14 @@ void gpu_unpin_(void* ptr);
  * per Taylor series, raw powers H'^k psi with c_k applied in the sum, cublasIdamax-style term test with a strict `<`
  * (Taylor_gpu.cpp:334-480,511-622), and the un-rescaled Chebyshev series of Chebyshev_gpu.cpp:347-485,524-643
  * (valid for tau * ||H'|| <~ 1 only, as in the reference).  Single GPU.  Checked on the B200 against the reference's
- * own binaries (oracle/_ref/libref_taylor_gpu.so, libref_chebyshev_gpu.so). */
+ * own GPU propagators compiled in place for sm_100a (tests/test_gpu_refgpu_modes.py). */
 #define DYB_MODE_TAYLOR_REFGPU     2
 #define DYB_MODE_CHEBYSHEV_REFGPU  3
+/* ONE Chebyshev expansion per nuclear step on the rescaled H' (needs spectral bounds like DYB_MODE_CHEBYSHEV): the order
+ * is taken from the decay of the Bessel coefficients J_k(dE*tau) (K ~ R + O(R^(1/3)) terms) instead of the reference's
+ * cap of 25 (Chebyshev_gpu.cpp:119), with a single 1e-8 norm test at the end.  ~3.5x fewer passes over H' than the
+ * order-25 chain at dt = 0.5 fs, and accurate to rounding instead of to the 1e-8 term test. */
+#define DYB_MODE_CHEBYSHEV_FULL    4
 
 #define DYB_KERNEL_AUTO 0
 #define DYB_KERNEL_TMA  1   /* TMA + mbarrier staged persistent kernel (default) */
@@ -133,6 +147,9 @@ typedef struct {
 typedef struct dyb_ctx dyb_ctx;
 
 const char* dyb_last_error(void);
+const char* dyb_team_last_error(void);    /* message of the last failing dyb_team_* call on this thread */
+int64_t dyb_legacy_passes_last(void);            /* el+hole terms of the last propagation made through a legacy symbol */
+int64_t dyb_unwrap_pin_bytes(int size_bytes);   /* host-only: the byte count gpu_pin_ recovers from a wrapped Fortran default integer */
 const char* dyb_version(void);
 int  dyb_device_count(void);
 /* Host-only (no device needed): the launch plan of the dual product.  out8 = {panels, tiles_per_panel, tiles, grid,
@@ -186,6 +203,15 @@ int  dyb_form_hprime_device(dyb_ctx* ctx, const void* d_S, int64_t lds, const vo
 int  dyb_form_hprime_from_overlap(dyb_ctx* ctx, const double* h_S, const double* IP, const double* k_WH,
                                   const double* V_shift, double* h_H_out /* may be NULL */);
 int  dyb_download_hprime(dyb_ctx* ctx, double* h_H, int64_t lda);
+/* device -> device copy OUT of the resident H': owned rows local_row0..local_row0+n_rows-1, all N columns, into a
+ * column-major device buffer with leading dimension ldd >= n_rows (host layers use it to hand row blocks of an operator
+ * formed on one GPU to the ranks of a row-sharded run). */
+int  dyb_download_hprime_rows_device(dyb_ctx* ctx, void* d_dst, int64_t ldd, int local_row0, int n_rows);
+/* dyb_form_hprime with the transfers overlapped (what the legacy symbols use): h goes up while S is being factorised, and
+ * the download of H' into h_H_out starts when the solve ends and runs beside whatever is queued next (spectral bounds,
+ * the series).  h_H_out is complete only after dyb_wait_outputs(). */
+int  dyb_form_hprime_async(dyb_ctx* ctx, const double* h_S, const double* h_h, double* h_H_out /* may be NULL */);
+int  dyb_wait_outputs(dyb_ctx* ctx);
 
 /* Wavepackets: n_part (1 or 2) columns of N complex, col-major. */
 int  dyb_set_packets(dyb_ctx* ctx, int n_part, const dyb_complex* bra, const dyb_complex* ket);
@@ -244,6 +270,35 @@ int  dyb_comm_init(dyb_ctx* ctx, int rank, int world, const char* id128);
 int  dyb_comm_p2p_handle(dyb_ctx* ctx, char* out64);
 int  dyb_comm_p2p_open(dyb_ctx* ctx, const char* handles);
 int  dyb_comm_p2p_enable(dyb_ctx* ctx, int on);   /* collective: same value on every rank; 0 = NCCL collectives */
+/* Peers that live in THIS process (dyb_team): phase 0 allocates the exchange buffer, phase 1 -- after every member did
+ * phase 0 -- maps the peers by cudaDeviceEnablePeerAccess (no IPC).  members: `world` contexts in rank order. */
+int  dyb_comm_p2p_open_local(dyb_ctx* ctx, dyb_ctx* const* members, int phase);
+
+/* ------------------------------------------------------------------ single-process multi-GPU ("team")
+ * the reference ABI is ONE host process, so a Fortran caller can only reach several GPUs if the library
+ * drives them itself.  A team is `n_dev` row-sharded contexts (rank r on devices[r], rows r*N/n_dev ...) driven by one
+ * host thread per device inside every call; H' = S^-1 h is formed on the first device and its row blocks are scattered
+ * over NVLink; per term the fused peer-memory exchange of the row-sharded mode runs between the devices (peer access, no
+ * IPC), NCCL (ncclCommInitRank per thread) serves the few collectives outside the term loop.  Results are those of the
+ * one-process-per-GPU mode bit for bit.  The legacy symbols use a team when DYNEMOL_B200_GPUS=P > 1.
+ * All calls take host buffers of the FULL problem (N x N, N x n_part), like the single-GPU API. */
+typedef struct dyb_team dyb_team;
+int  dyb_team_create(dyb_team** out, int n_dev, const int* devices /* NULL: 0..n_dev-1 */, int N);
+int  dyb_team_destroy(dyb_team* team);
+int  dyb_team_size(dyb_team* team);
+int  dyb_team_form_hprime(dyb_team* team, const double* h_S, const double* h_h, double* h_H_out /* may be NULL; complete after dyb_team_wait_outputs */);
+int  dyb_team_wait_outputs(dyb_team* team);
+int  dyb_team_upload_hprime(dyb_team* team, const double* h_H, int64_t lda);
+int  dyb_team_set_packets(dyb_team* team, int n_part, const dyb_complex* bra, const dyb_complex* ket);
+int  dyb_team_get_packets(dyb_team* team, int n_part, dyb_complex* bra, dyb_complex* ket);
+int  dyb_team_set_spectral_bounds(dyb_team* team, double emin, double emax);
+int  dyb_team_estimate_spectral_bounds(dyb_team* team, int n_iter, double margin, double* emin, double* emax);
+int  dyb_team_propagate(dyb_team* team, int mode, double t_init, double t_max, const double* tau, double* save_tau, dyb_trace* traces);
+int  dyb_team_ao_bra(dyb_team* team, int n_part, dyb_complex* h_AO_bra);       /* needs dyb_team_form_hprime */
+int  dyb_team_populations(dyb_team* team, int n_part, int n_frag, const int32_t* fragment, double t, double* out);
+int  dyb_team_quasiparticle_energies(dyb_team* team, int n_part, double* out_reim);
+int  dyb_team_run_terms(dyb_team* team, double tau, int n_terms, float* elapsed_ms_max);
+int64_t dyb_team_passes_last(dyb_team* team);
 
 int  dyb_sync(dyb_ctx* ctx);
 int64_t dyb_launch_count(dyb_ctx* ctx);   /* kernels of THIS library launched so far */

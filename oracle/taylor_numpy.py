@@ -376,3 +376,39 @@ def gpu_variant_cheb_propagation(Hp, bra, ket, t_init, t_max, tau):
             tau = (t_max - t) / H_BAR
             C = gpu_variant_cheb_coefficient(tau)
     return bra, ket, tau, save_tau, n_rescale
+
+
+# ----------------------------------------------------------------------------- single-expansion Chebyshev (product spec)
+def cheb_full_coefficients(tau, ebar, de):
+    """DYB_MODE_CHEBYSHEV_FULL: the coefficients of Chebyshev_gpu.cpp:636-643 on the rescaled operator, with the order taken
+    from their decay instead of the reference's cap of 25: K = first k > R (R = de*tau) with 2|J_k(R)| < 1e-15."""
+    from scipy.special import jv
+    R = de * tau
+    ph = np.exp(-1j * ebar * tau)
+    C = [jv(0, R) * ph]
+    k = 1
+    while True:
+        j = jv(k, R)
+        if k > R and k >= 2 and 2.0 * abs(j) < 1.0e-15:
+            break
+        C.append(2.0 * j * (-1j) ** k * ph)
+        k += 1
+    return np.array(C)
+
+
+def cheb_full_propagation(Hp, bra, ket, t_init, t_max, ebar, de):
+    """One expansion over the whole interval, one norm test at the end.  Returns (bra, ket, n_terms, norm_ok)."""
+    tau = (t_max - t_init) / H_BAR
+    C = cheb_full_coefficients(tau, ebar, de)
+    norm_ref = abs(np.vdot(bra, ket))
+    ht = lambda x: (Hp @ x - ebar * x) / de
+    htT = lambda x: (Hp.T @ x - ebar * x) / de
+    b0, k0 = bra, ket
+    b1, k1 = htT(b0), ht(k0)
+    sb = C[0] * b0 + C[1] * b1; sk = C[0] * k0 + C[1] * k1
+    for k in range(2, len(C)):
+        b2 = 2.0 * htT(b1) - b0; k2 = 2.0 * ht(k1) - k0
+        sb = sb + C[k] * b2; sk = sk + C[k] * k2
+        b0, b1, k0, k1 = b1, b2, k1, k2
+    ok = abs(abs(np.vdot(sb, sk)) - norm_ref) < NORM_ERROR
+    return sb, sk, len(C) - 1, ok

@@ -159,3 +159,16 @@ def test_series_coefficients_match_oracle(oracle_mod):
         assert km == want
     with pytest.raises(Exception):
         api.series_coefficients(api.MODE_CHEBYSHEV, 0.1, 0.0, 0.0)
+
+
+def test_gpu_pin_size_recovery():
+    """gpu_pin_ receives n*n*8 as a Fortran DEFAULT integer (ElHl_Chebyshev_GPU.f:109-111): it wraps at N = 16384 and
+    loses multiples of 2^32 beyond N = 23170.  The library recovers the true byte count (N x N doubles)."""
+    from dynemol_b200 import api
+    for N in (64, 900, 10368, 16384, 23170, 23171, 30720, 32768, 46340, 60000):
+        true = N * N * 8
+        wrapped = ((true + 2 ** 31) % 2 ** 32) - 2 ** 31          # what a 32-bit signed integer holds
+        assert api.unwrap_pin_bytes(wrapped) == true, N
+    # inherent ambiguity of the wrapped value: N = 65536 and N = 32768 both arrive as 0; the smaller size is pinned (the
+    # rest of such a buffer stays pageable: slower copies, still correct)
+    assert api.unwrap_pin_bytes(0) == 32768 * 32768 * 8

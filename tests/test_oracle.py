@@ -254,3 +254,24 @@ def test_chebyshev_gpu_variant_transcription_vs_expm(oracle_mod):
         assert np.abs(gb - cb).max() / np.abs(cb).max() < 2e-7 and np.abs(gk - ck).max() / np.abs(ck).max() < 2e-7
         assert np.abs(U @ w.Psi_ket[:, p] - gk).max() < 2e-7 and np.abs(U.T @ w.Psi_bra[:, p] - gb).max() < 2e-7
         assert 0.0 < g_save <= tau0 and 0.0 < c_save <= tau0
+
+
+def test_single_expansion_chebyshev_spec_vs_expm(oracle_mod):
+    """The product's DYB_MODE_CHEBYSHEV_FULL as stated in numpy (oracle/taylor_numpy.py cheb_full_*): one expansion of
+    K ~ R + O(R^(1/3)) terms for a whole 0.5 fs step agrees with expm to rounding (1e-10 is the bar in the GPU test) with
+    several times fewer dual products than the reference's chain of order-25 series needs for the same step."""
+    N, dt = 96, 5e-4
+    w = syn.make_workload(N)
+    Hp = _hprime(oracle_mod, w)
+    e = np.linalg.eigvals(Hp).real
+    lo, hi = e.min() - 0.05 * (e.max() - e.min()), e.max() + 0.05 * (e.max() - e.min())
+    ebar, de = 0.5 * (hi + lo), 0.5 * (hi - lo)
+    U = expm(-1j * (dt / tn.H_BAR) * Hp)
+    for p in range(2):
+        b, k, n_terms, ok = tn.cheb_full_propagation(Hp, w.Psi_bra[:, p].copy(), w.Psi_ket[:, p].copy(), 0.0, dt, ebar, de)
+        assert ok
+        assert np.abs(U @ w.Psi_ket[:, p] - k).max() < 1e-11 and np.abs(U.T @ w.Psi_bra[:, p] - b).max() < 1e-11
+        _, _, _, _, tr = oracle_mod.cheb_scaled_propagation(Hp, w.Psi_bra[:, p], w.Psi_ket[:, p], 0.0, dt, dt / tn.H_BAR, ebar, de)
+        R = de * dt / tn.H_BAR
+        assert R < n_terms < R + 20.0 * R ** (1.0 / 3.0) + 30
+        assert 2 * n_terms < tr.n_matvec_pairs, (n_terms, tr.n_matvec_pairs)
