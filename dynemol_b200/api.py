@@ -111,7 +111,20 @@ def _fd(a) -> np.ndarray:
     return np.asfortranarray(a, dtype=np.float64)
 
 
+def _prefer_torch_nccl():
+    """The library binds NCCL with dlopen("libnccl.so.2"): whichever copy the process loaded first wins, and torch's
+    libtorch_cuda.so needs ITS bundled (newer) copy.  If torch is installed but not imported yet, import it before the
+    first NCCL use so that a later `import torch` in the same process still works (plumbing only)."""
+    import sys
+    if "torch" not in sys.modules:
+        try:
+            import torch  # noqa: F401
+        except Exception:
+            pass
+
+
 def comm_unique_id() -> bytes:
+    _prefer_torch_nccl()
     buf = C.create_string_buffer(128)
     _check(lib.dyb_comm_unique_id(buf))
     return buf.raw
@@ -174,6 +187,8 @@ class Team:
     def __init__(self, N: int, n_dev: int, devices=None):
         self.N, self.n_dev = int(N), int(n_dev)
         self._h = C.c_void_p()
+        if n_dev > 1:
+            _prefer_torch_nccl()
         devs = None if devices is None else (C.c_int * n_dev)(*devices)
         _tcheck(lib.dyb_team_create(C.byref(self._h), C.c_int(n_dev), devs, C.c_int(N)))
         self.n_part = 0
@@ -455,6 +470,8 @@ def legacy_propagationelhl(S, h, PSI_bra, PSI_ket, t_init, t_max, tau, batched: 
     assert Hp.shape == (N, N) and Hp.flags.f_contiguous
     AO_bra = np.zeros_like(PSI_bra, order="F"); AO_ket = np.full_like(PSI_bra, np.nan, order="F")
     n = C.c_int(N); ti = C.c_double(t_init); tm = C.c_double(t_max)
+    if int(os.environ.get("DYNEMOL_B200_GPUS", "1") or 1) > 1:
+        _prefer_torch_nccl()
     if batched:
         tau_a = np.ascontiguousarray(np.broadcast_to(np.asarray(tau, dtype=np.float64), (2,))).copy(); save = np.zeros(2)
         lib.propagationelhl2_gpucaller_(C.byref(n), _p(S), _p(h), _p(Hp), _p(AO_bra), _p(AO_ket), _p(PSI_bra), _p(PSI_ket),

@@ -80,7 +80,8 @@ struct Ctrl {
     PartState part[2];
     int       all_latched;
     unsigned  block_counter;      // epilogue "last block" ticket
-    int       pad_[2];
+    int       peer_timeout;       // sticky: a peer's flag did not arrive in time (row-sharded exchange); the host turns it into DYB_ECUDA
+    int       pad_;
 };
 
 constexpr double TOL_TERM = 1.0e-8;   // Taylor.f:21  (error)
@@ -157,11 +158,24 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// bounded spin: a peer that never arrives must not hang the GPU (trap after ~2 s)
-__device__ __forceinline__ void wait_flag_ge(const unsigned long long* p, unsigned long long target) {
-    for (long long it = 0; ld_acquire_sys(p) < target; ++it) {
+// Bounded wait on a peer's epoch flag.  The bound is wall-clock time (%globaltimer, ns), set by the host from
+// DYNEMOL_B200_PEER_TIMEOUT_S (default 30 s: peers are launched by independent host threads / processes and may lag by a
+// lazy module load or a host stall).  On timeout the kernel does NOT trap (a trap poisons the CUDA context of every rank
+// in turn): it raises the sticky Ctrl::peer_timeout flag and returns false; the caller skips its work, later kernels see
+// the flag and skip too, and the host returns DYB_ECUDA from the call in progress.
+__device__ unsigned long long g_peer_timeout_ns = 30ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ bool wait_flag_ge(const unsigned long long* p, unsigned long long target, int* timeout_flag) {
+    if (ld_acquire_sys(p) >= target) return true;
+    const unsigned long long t0 = globaltimer_ns(), limit = g_peer_timeout_ns;
+    for (;;) {
         __nanosleep(64);
-        if (it > (1ll << 22)) { printf("dynemol_b200: peer flag timeout (have %llu, want %llu)\n", ld_acquire_sys(p), target); __trap(); }
+        if (ld_acquire_sys(p) >= target) return true;
+        if (globaltimer_ns() - t0 > limit) { atomicExch(timeout_flag, 1); __threadfence(); return false; }
     }
 }
 

@@ -144,7 +144,9 @@ struct PeerTable {
 
 __global__ void signal_ready_kernel(const PeerTable T)
 {
-    // stream order guarantees the bra partial vector of this rank is complete; publish it to every peer
+    pdl_launch_dependents();
+    pdl_wait();             // the local panel sum that precedes us has completed (programmatic dependent launch)
+    // the bra partial vector of this rank is complete; publish it to every peer
     if (threadIdx.x < T.world) { __threadfence_system(); st_release_sys(T.ready[threadIdx.x], T.epoch); }
 }
 
@@ -177,8 +179,15 @@ epilogue_kernel_t(const EpiParams E, const PeerTable T)
     __shared__ int    is_last;
 
     if constexpr (P2P) {
-        if (threadIdx.x < T.world) wait_flag_ge(T.my_ready + threadIdx.x, T.epoch);     // all ranks' bra partials are visible
+        pdl_launch_dependents();        // the next dual product may be scheduled and prefetch its first H' tiles during the exchange
+        pdl_wait();                     // signal_ready_kernel (and, transitively, the local panel sum) has completed
+        __shared__ int s_abort;
+        if (threadIdx.x == 0) s_abort = *reinterpret_cast<volatile int*>(&E.ctrl->peer_timeout);
         __syncthreads();
+        if (s_abort) return;                                                             // an earlier term timed out: nothing is in step any more
+        if (threadIdx.x < T.world && !wait_flag_ge(T.my_ready + threadIdx.x, T.epoch, &E.ctrl->peer_timeout)) s_abort = 1;   // all ranks' bra partials are visible
+        __syncthreads();
+        if (s_abort) return;
     } else {
         pdl_launch_dependents();        // the next dual product may start its H' prefetch while we run
         pdl_wait();                     // slabs of the dual product that precedes us are complete and visible
@@ -337,12 +346,16 @@ epilogue_kernel_t(const EpiParams E, const PeerTable T)
         }
         __threadfence_system();
         __syncthreads();
+        __shared__ int s_abort2;
+        if (threadIdx.x == 0) s_abort2 = 0;
+        __syncthreads();
         if (threadIdx.x < T.world) {
             st_release_sys(T.done[threadIdx.x], T.epoch);                // "rank `rank` is done" on every peer
-            wait_flag_ge(T.my_done + threadIdx.x, T.epoch);              // and wait until every peer is done
+            if (!wait_flag_ge(T.my_done + threadIdx.x, T.epoch, &E.ctrl->peer_timeout)) s_abort2 = 1;   // and wait until every peer is done
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 0 && s_abort2) { E.ctrl->block_counter = 0u; __threadfence(); }
+        if (threadIdx.x == 0 && !s_abort2) {
             double v[8];
             const double* tab = T.scal_all[T.rank];
             for (int t = 0; t < 8; ++t) {
@@ -415,6 +428,8 @@ __global__ void series_init_kernel(const InitParams I)
 // ---- row-sharded H': sum this rank's bra panels into one full-length partial vector (reduce-scatter input)
 __global__ void bra_panel_reduce_kernel(int n_cols, int n_panels, int Ncpad, const double* __restrict__ bra_slab, double* __restrict__ out)
 {
+    pdl_launch_dependents();
+    pdl_wait();             // no-op unless launched with programmatic stream serialization (fused peer-memory path)
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // one double2 (particle) of one column
     if (idx >= 2 * n_cols) return;
     const Cx v = slab_sum(bra_slab + (size_t)idx * 2, (size_t)Ncpad * NQ, n_panels);

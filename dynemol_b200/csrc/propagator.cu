@@ -307,13 +307,19 @@ static int run_term(dyb_ctx* c, const EpiParams& E, int cur, int nxt, bool use_c
     const int n2 = 2 * c->N;
     if (c->p2p) {
         // fused exchange over NVLink peer memory: local panel sum -> publish -> one kernel does reduce-scatter (peer
-        // loads), epilogue, all-gather (peer stores), scalar exchange and the replicated decision
+        // loads), epilogue, all-gather (peer stores), scalar exchange and the replicated decision.  All four launches of a
+        // term are chained by programmatic dependent launch: each kernel is scheduled while its predecessor drains and
+        // blocks in griddepcontrol.wait until that one has completed, so the launch latencies (and, for the next dual
+        // product, the TMA prefetch of its first H' tiles) overlap the exchange.
         const unsigned long long epoch = ++c->epoch;
         const int par = (int)(epoch & 1);
         double* my_rs = reinterpret_cast<double*>(c->comm_buf + c->off_rs[par]);
-        bra_panel_reduce_kernel<<<(n2 + 255) / 256, 256, 0, c->stream>>>(c->N, c->NP, c->Ncpad, c->bra_slab, my_rs);
-        c->launches++;
-        CK(cudaGetLastError());
+        cudaLaunchAttribute attr;
+        {
+            cudaLaunchConfig_t cfg = pdl_config(c, (n2 + 255) / 256, 256, 0, &attr);
+            CK(cudaLaunchKernelEx(&cfg, bra_panel_reduce_kernel, c->N, c->NP, c->Ncpad, (const double*)c->bra_slab, my_rs));
+            c->launches++;
+        }
         PeerTable T;
         memset(&T, 0, sizeof T);
         T.world = c->world; T.rank = c->rank; T.epoch = epoch;
@@ -327,15 +333,19 @@ static int run_term(dyb_ctx* c, const EpiParams& E, int cur, int nxt, bool use_c
         }
         T.my_ready = reinterpret_cast<const unsigned long long*>(c->comm_buf + c->off_ready);
         T.my_done  = reinterpret_cast<const unsigned long long*>(c->comm_buf + c->off_done);
-        signal_ready_kernel<<<1, 32, 0, c->stream>>>(T);
-        c->launches++;
-        CK(cudaGetLastError());
+        {
+            cudaLaunchConfig_t cfg = pdl_config(c, 1, 32, 0, &attr);
+            CK(cudaLaunchKernelEx(&cfg, signal_ready_kernel, T));
+            c->launches++;
+        }
         EpiParams E2 = E;
         E2.defer_decision = 0;
-        if (epi_sl(c) == 1) epilogue_kernel_t<true, 1><<<epi_grid(c), EPI_THREADS, 0, c->stream>>>(E2, T);
-        else epilogue_kernel_t<true, EPI_SL_WIDE><<<epi_grid(c), EPI_THREADS, 0, c->stream>>>(E2, T);
-        c->launches++;
-        CK(cudaGetLastError());
+        {
+            cudaLaunchConfig_t cfg = pdl_config(c, epi_grid(c), EPI_THREADS, 0, &attr);
+            if (epi_sl(c) == 1) CK(cudaLaunchKernelEx(&cfg, epilogue_kernel_t<true, 1, false>, E2, T));
+            else CK(cudaLaunchKernelEx(&cfg, epilogue_kernel_t<true, EPI_SL_WIDE, false>, E2, T));
+            c->launches++;
+        }
         return DYB_OK;
     }
     bra_panel_reduce_kernel<<<(n2 + 255) / 256, 256, 0, c->stream>>>(c->N, c->NP, c->Ncpad, c->bra_slab, c->rs_send);
@@ -436,6 +446,9 @@ static int launch_series_init(dyb_ctx* c, const int adopt[2], const int active[2
 static int read_ctrl(dyb_ctx* c) {
     CK(cudaMemcpyAsync(c->h_ctrl, c->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    if (c->h_ctrl->peer_timeout)
+        return fail(DYB_ECUDA, "row-sharded exchange: a peer's flag did not arrive within the timeout (DYNEMOL_B200_PEER_TIMEOUT_S); "
+                               "the ranks are out of step, destroy the contexts");
     return DYB_OK;
 }
 
@@ -1402,6 +1415,10 @@ static int p2p_alloc(dyb_ctx* c) {
     if (!c->comm || c->world < 2) return fail(DYB_EINVAL, "dyb_comm_init (world >= 2) must come first");
     if (c->world > MAX_PEERS) return fail(DYB_EINVAL, "at most %d ranks", MAX_PEERS);
     CK(cudaSetDevice(c->device));
+    if (const char* e = getenv("DYNEMOL_B200_PEER_TIMEOUT_S")) {
+        const double sec = atof(e);
+        if (sec > 0.0) { const unsigned long long ns = (unsigned long long)(sec * 1e9); CK(cudaMemcpyToSymbol(g_peer_timeout_ns, &ns, sizeof ns)); }
+    }
     if (!c->comm_buf) {
         const size_t vec = align_up(c->Lq * NQ * sizeof(double), 4096);
         size_t off = 0;
@@ -1576,6 +1593,7 @@ int dyb_run_terms(dyb_ctx* c, double tau, int n_terms, float* elapsed_ms, float*
     }
     CK(cudaEventRecord(c->ev[1], c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    if (c->world > 1 && (rc = read_ctrl(c))) return rc;             // a peer-flag timeout surfaces here
     c->passes_last = n_terms;
     if (elapsed_ms) CK(cudaEventElapsedTime(elapsed_ms, c->ev[0], c->ev[1]));
     if (per_kernel) {

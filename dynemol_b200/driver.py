@@ -30,7 +30,11 @@ class SliceChebDriver:
         self.save_tau = np.zeros(2)                   # ElHl_Chebyshev.f:35
         self.AO_bra = self.AO_ket = self.DUAL_bra = self.DUAL_ket = None
         self.Net_Charge = np.zeros(self.n_atoms)
-        self.frame = frame_step
+        # Chebyshev_driver.f:100-102: do frame = frame_init, frame_final, frame_step with frame_init = frame_step + 1
+        # (frame_restart + 1 after a restart); `frame` is the loop value of the step in progress / last executed, which
+        # is what Security_Copy stores (:165)
+        self.frame = 1
+        self._next_frame = frame_step + 1
 
     # -------------------------------------------------------------------------------------------------- start
     def preprocess(self, S, AO_bra, AO_ket):
@@ -49,6 +53,7 @@ class SliceChebDriver:
         Psi_bra = DUAL_ket, Psi_ket = AO_ket; first_call_ is true again, so the next step starts from tau_max."""
         st = read_restart_copy(path)
         self.frame, self.it, self.t, self.eh_tag = st.frame, st.it, st.t, st.eh_tag
+        self._next_frame = st.frame + 1                                       # Chebyshev_driver.f:100: frame_init = frame_restart + 1
         self.DUAL_bra, self.DUAL_ket, self.AO_bra, self.AO_ket = st.DUAL_bra, st.DUAL_ket, st.AO_bra, st.AO_ket
         self.Net_Charge = st.Net_Charge
         self.P.set_packets(self.DUAL_ket, self.AO_ket)
@@ -58,13 +63,14 @@ class SliceChebDriver:
     # -------------------------------------------------------------------------------------------------- one frame
     def step(self, S, h, want_hprime: bool = False):
         """One pass of the loop body Chebyshev_driver.f:102-108 -> ElHl_Chebyshev (ElHl_Chebyshev.f:148-291)."""
+        self.frame = self._next_frame; self._next_frame += self.frame_step    # Chebyshev_driver.f:102
         self.it += 1                                                          # Chebyshev_driver.f:106
         t_init = self.t
         t_max = self.delta_t * self.frame_step * (self.it - 1)                # ElHl_Chebyshev.f:176
         tau_max = self.delta_t / H_BAR                                        # :178
         tau = np.full(2, tau_max) if self.first_call else np.minimum(tau_max, 1.15 * self.save_tau)   # :182-184
         Hp = self.P.form_hprime(S, h, want_hprime=want_hprime)                # :206-210 on the device
-        if self.mode == api.MODE_CHEBYSHEV:
+        if self.mode in (api.MODE_CHEBYSHEV, api.MODE_CHEBYSHEV_FULL):
             self.P.estimate_spectral_bounds(24, 0.05)
         self.save_tau[: self.P.n_part], traces = self.P.propagate(t_init, t_max, tau[: self.P.n_part], mode=self.mode)   # :228,253
         self.t = t_init + self.delta_t * self.frame_step                      # :266
@@ -75,7 +81,6 @@ class SliceChebDriver:
         pops = self.P.populations(self.fragment, self.n_frag, self.t)         # :281 on the device
         self._net_charge(self.DUAL_bra, self.DUAL_ket)
         self.first_call = False
-        self.frame += self.frame_step
         return dict(pops=pops, erg=erg, traces=traces, t=self.t, H_prime=Hp)
 
     # -------------------------------------------------------------------------------------------------- helpers

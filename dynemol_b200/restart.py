@@ -35,8 +35,39 @@ class ChebState:
     Net_Charge: np.ndarray    # (n_atoms,) float64
 
 
+# Records longer than 2^31 - 9 bytes are split into subrecords by the gfortran / ifort runtimes: every subrecord is framed
+# by its own 4-byte markers holding its length; the LEADING marker is negative when another subrecord follows, the
+# TRAILING marker is negative when a subrecord precedes.  (Net_Charge is written size(Net_Charge) times, backup.f:392:
+# n_atoms^2 * 8 bytes, i.e. exactly 2 GiB at 16384 atoms.)
+MAX_SUBRECORD = 2147483639
+
+
 def _rec(f, payload: bytes):
-    f.write(struct.pack("<i", len(payload))); f.write(payload); f.write(struct.pack("<i", len(payload)))
+    _rec_stream(f, len(payload), iter((payload,)))
+
+
+def _rec_stream(f, total: int, pieces):
+    """One Fortran record of `total` bytes whose payload arrives as an iterable of bytes objects (never materialised whole)."""
+    buf = b""
+    remaining = total
+    first = True
+    while True:
+        sub = min(remaining, MAX_SUBRECORD)
+        more = remaining > sub
+        f.write(struct.pack("<i", -sub if more else sub))
+        left = sub
+        while left > 0:
+            if not buf:
+                buf = next(pieces)
+            take = buf[:left]
+            f.write(take)
+            left -= len(take)
+            buf = buf[len(take):]
+        f.write(struct.pack("<i", sub if first else -sub))
+        remaining -= sub
+        first = False
+        if not more:
+            break
 
 
 def write_security_copy(path: str, st: ChebState) -> None:
@@ -56,19 +87,45 @@ def write_security_copy(path: str, st: ChebState) -> None:
                 inter[:, 0] = a[:, j]; inter[:, 1] = b[:, j]
                 _rec(f, inter.astype("<c16").tobytes())
         nc = np.ascontiguousarray(st.Net_Charge, dtype="<f8")
-        _rec(f, nc.tobytes() * nc.size)
+        one = nc.tobytes()
+        _rec_stream(f, len(one) * nc.size, (one for _ in range(nc.size)))      # the array, size(Net_Charge) times, streamed
 
 
-def _read_rec(f) -> bytes:
-    head = f.read(4)
-    if len(head) != 4:
-        raise EOFError("truncated Fortran record")
-    (n,) = struct.unpack("<i", head)
-    payload = f.read(n)
-    (m,) = struct.unpack("<i", f.read(4))
-    if m != n or len(payload) != n:
-        raise ValueError("corrupt Fortran record framing")
-    return payload
+def _read_rec(f, keep: int | None = None):
+    """One Fortran record (all its subrecords).  keep=None: returns the payload.  keep=k: returns (first k bytes, total
+    length) without holding the rest in memory (the Net_Charge record can be 2 GiB of repeats)."""
+    out = []
+    kept = 0
+    total = 0
+    first = True
+    while True:
+        head = f.read(4)
+        if len(head) != 4:
+            raise EOFError("truncated Fortran record")
+        (n,) = struct.unpack("<i", head)
+        sub = abs(n)
+        if keep is None:
+            data = f.read(sub)
+            if len(data) != sub:
+                raise ValueError("corrupt Fortran record framing")
+            out.append(data)
+        else:
+            take = min(sub, keep - kept)
+            if take > 0:
+                out.append(f.read(take)); kept += take
+            f.seek(sub - take, 1)
+        total += sub
+        tail = f.read(4)
+        if len(tail) != 4:
+            raise ValueError("corrupt Fortran record framing")
+        (m,) = struct.unpack("<i", tail)
+        if abs(m) != sub or (m < 0) == first:
+            raise ValueError("corrupt Fortran record framing")
+        first = False
+        if n >= 0:
+            break
+    payload = b"".join(out)
+    return payload if keep is None else (payload, total)
 
 
 def read_restart_copy(path: str) -> ChebState:
@@ -87,10 +144,13 @@ def read_restart_copy(path: str) -> ChebState:
             for k in (0, 2):
                 inter = np.frombuffer(_read_rec(f), dtype="<c16").reshape(N, 2)
                 arrs[k][:, j] = inter[:, 0]; arrs[k + 1][:, j] = inter[:, 1]
-        nc_raw = np.frombuffer(_read_rec(f), dtype="<f8")
-        n_atoms = int(round(np.sqrt(nc_raw.size)))
-        if n_atoms * n_atoms != nc_raw.size:
+        pos = f.tell()
+        _, total = _read_rec(f, keep=0)
+        n_atoms = int(round(np.sqrt(total // 8)))
+        if n_atoms * n_atoms * 8 != total:
             raise ValueError("Net_Charge record is not size(Net_Charge) copies of the array")
-        nc = nc_raw[:n_atoms].copy()
+        f.seek(pos)
+        head, _ = _read_rec(f, keep=8 * n_atoms)
+        nc = np.frombuffer(head, dtype="<f8").copy()
     assert n_tag >= n_part
     return ChebState(frame, it, t, tags, arrs[0], arrs[1], arrs[2], arrs[3], nc)

@@ -60,6 +60,7 @@ def test_stop_and_restart_matches_oracle(api, oracle_mod, tmp_path):
     drv2 = SliceChebDriver(N, frag, np.arange(N) // 4, 4, dt)
     st = drv2.from_restart(path)                        # "mv Security_copy.dat Restart_copy.dat" + restart = .true.
     assert st.it == n1 + 1 and abs(st.t - n1 * dt) < 1e-18
+    assert st.frame == n1 + 1                           # the loop value of the last executed step (frame_step = 1: 2 .. n1+1)
 
     # oracle stopped and restarted the same way: Psi_bra = DUAL_ket, Psi_ket = AO_ket, first_call again
     o = oracle_mod.ElHlState(S0.T @ C, C)
@@ -76,4 +77,31 @@ def test_stop_and_restart_matches_oracle(api, oracle_mod, tmp_path):
         assert [t.n_matvec_pairs for t in out["traces"]] == [t.n_matvec_pairs for t in ref["traces"]]
         erg_ref = oracle_mod.quasiparticle_energies(ref["AO_bra"], ref["AO_ket"], geo(step)[1])
         assert np.abs(out["erg"] - erg_ref).max() < 1e-8 * np.abs(erg_ref).max()
+    drv2.close()
+
+
+def test_frame_numbers_follow_the_reference_loop(api, tmp_path):
+    """Chebyshev_driver.f:100-165: do frame = frame_step+1, frame_final, frame_step, and Security_Copy stores the loop
+    value; after a restart the loop starts at frame_restart + 1.  With frame_step = 3: 4, 7, 10 | restart at 10 -> 11, 14."""
+    from dynemol_b200.driver import SliceChebDriver
+    from dynemol_b200.restart import read_restart_copy
+    N, dt, fs = 64, 1e-6, 3
+    pos, species, S0, C = _setup(N)
+    frag = syn.fragments(N)
+    S, h = syn.workload_at(pos, species)
+    drv = SliceChebDriver(N, frag, np.arange(N) // 4, 4, dt, frame_step=fs)
+    drv.preprocess(S0, C, C)
+    seen = []
+    for _ in range(3):
+        drv.step(S, h); seen.append(drv.frame)
+    assert seen == [4, 7, 10]
+    path = str(tmp_path / "Security_copy.dat")
+    drv.security_copy(path)
+    drv.close()
+    assert read_restart_copy(path).frame == 10
+    drv2 = SliceChebDriver(N, frag, np.arange(N) // 4, 4, dt, frame_step=fs)
+    drv2.from_restart(path)
+    drv2.step(S, h); a = drv2.frame
+    drv2.step(S, h); b = drv2.frame
+    assert (a, b) == (11, 14)
     drv2.close()

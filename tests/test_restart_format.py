@@ -46,3 +46,27 @@ def test_round_trip(tmp_path):
     assert (back.frame, back.it, back.t, back.eh_tag) == (st.frame, st.it, st.t, st.eh_tag)
     for name in ("DUAL_bra", "DUAL_ket", "AO_bra", "AO_ket", "Net_Charge"):
         assert np.array_equal(getattr(back, name), getattr(st, name)), name
+
+
+def test_long_records_are_split_into_subrecords(tmp_path, monkeypatch):
+    """Records beyond 2^31 - 9 bytes (Net_Charge at >= 16384 atoms: n_atoms^2 * 8 B) are written as subrecords the way
+    the gfortran / ifort runtimes do it: negative leading marker = "continued", negative trailing marker = "has a
+    predecessor".  Exercised with a tiny limit."""
+    import dynemol_b200.restart as R
+    monkeypatch.setattr(R, "MAX_SUBRECORD", 100)
+    st = _state(N=6, n_atoms=7, seed=5)                       # Net_Charge record: 7*7*8 = 392 B -> 100+100+100+92
+    path = tmp_path / "Security_copy.dat"
+    R.write_security_copy(str(path), st)
+    raw = path.read_bytes()
+    tail = raw[-(392 + 4 * 8):]                               # the last record: 4 subrecords, 8 marker bytes each
+    subs, off = [], 0
+    while off < len(tail):
+        (lead,) = struct.unpack_from("<i", tail, off)
+        n = abs(lead)
+        (trail,) = struct.unpack_from("<i", tail, off + 4 + n)
+        subs.append((lead, trail)); off += 8 + n
+    assert subs == [(-100, 100), (-100, -100), (-100, -100), (92, -92)]
+    back = R.read_restart_copy(str(path))
+    assert np.array_equal(back.Net_Charge, st.Net_Charge) and np.array_equal(back.AO_ket, st.AO_ket)
+    # the interleaved packet records (6*2*16 = 192 B) were split as well and read back intact
+    assert np.array_equal(back.DUAL_bra, st.DUAL_bra)
