@@ -448,6 +448,66 @@ def sharded_parity_check(dist, local_rank, dev, N=4096):
         return {"ok": False, "error": repr(e)[:300]}
 
 
+def run_team_legacy(args):
+    """Single-process multi-GPU through the PRIMARY symbol: propagationelhl2_gpucaller_ with DYNEMOL_B200_GPUS=P (the way a
+    one-process Fortran caller reaches the GPUs of a box): pinned host S, h in; H', packets, AO_bra out; H'
+    formed on the first GPU, row-sharded over P GPUs by peer copies, propagated with the fused NVLink exchange.
+    Default size: BASELINE config 5 (N = 30720).  Run as a plain `python bench.py --team P` (NOT under torchrun)."""
+    import torch
+    from dynemol_b200 import api, synthetic as syn
+    N, P = args.basis or 30720, args.team
+    dev = torch.device("cuda", 0)
+    t0 = time.time()
+    S_t, h_t, _ = syn.make_S_h_torch(N, dev)
+    Sh = torch.empty((N, N), dtype=torch.float64, pin_memory=True); hh = torch.empty((N, N), dtype=torch.float64, pin_memory=True)
+    Sh.copy_(S_t); hh.copy_(h_t)
+    w = 64
+    C = torch.zeros((N, 2), dtype=torch.float64, device=dev)
+    C[0:w, 0] = torch.tensor(np.random.default_rng(42).normal(size=w), device=dev)
+    C[w:2 * w, 1] = torch.tensor(np.random.default_rng(43).normal(size=w), device=dev)
+    SC = S_t @ C
+    nrm = torch.sqrt((C * SC).sum(0))
+    Psi_ket = np.asfortranarray((C / nrm).cpu().numpy().astype(np.complex128))
+    Psi_bra = np.asfortranarray((SC / nrm).cpu().numpy().astype(np.complex128))
+    del S_t, h_t, SC, C
+    torch.cuda.empty_cache()
+    gen_s = time.time() - t0
+    S = Sh.numpy().T; h = hh.numpy().T
+    Hp = np.zeros((N, N), dtype=np.float64, order="F")
+    api.gpu_pin(Hp)
+    dt = 5e-4; tau_max = dt / H_BAR
+    res = {}
+    os.environ["DYNEMOL_B200_GPUS"] = str(P)
+    try:
+        for mode in ("chebyshev", "chebyshev25"):
+            os.environ["DYNEMOL_B200_MODE"] = mode
+            t1 = time.perf_counter()
+            o = api.legacy_propagationelhl(S, h, Psi_bra, Psi_ket, 0.0, dt, tau_max, copy_inputs=False, out_H=Hp)   # first step (+ team set-up)
+            first_s = time.perf_counter() - t1
+            tau = np.minimum(tau_max, 1.15 * o["save_tau"])
+            n_calls = max(1, args.e2e_steps)
+            terms = 0
+            t1 = time.perf_counter()
+            for _ in range(n_calls):
+                o = api.legacy_propagationelhl(S, h, Psi_bra, Psi_ket, 0.0, dt, tau, copy_inputs=False, out_H=Hp)
+                terms += api.legacy_passes_last()
+            t = time.perf_counter() - t1
+            resid = float(np.abs(S[:, :512] @ Hp[:, :8] - h[:, :8]).max() / np.abs(h[:, :8]).max()) if N <= 512 else \
+                float(np.abs(S @ Hp[:, :4] - h[:, :4]).max() / np.abs(h[:, :4]).max())
+            res[mode] = {"s_per_call": round(t / n_calls, 4), "terms_per_call": terms // n_calls, "terms_per_s": round(terms / t, 1),
+                         "nuclear_steps_per_s": round(n_calls / t, 4), "first_call_s": round(first_s, 2),
+                         "norm_el": float(abs(np.vdot(o["PSI_bra"][:, 0], o["PSI_ket"][:, 0]))), "S_Hprime_minus_h_rel": resid}
+    finally:
+        os.environ.pop("DYNEMOL_B200_MODE", None); os.environ.pop("DYNEMOL_B200_GPUS", None)
+        api.gpu_finalize()
+        api.gpu_unpin(Hp)
+    line = {"metric": "nuclear step (dt = 0.5 fs) through propagationelhl2_gpucaller_ on a single-process team", "unit": "s per call", "n_gpus": P,
+            "config": {"workload": "synthetic EHT Hamiltonian N=%d basis, host S, h -> H', packets, AO_bra; DYNEMOL_B200_GPUS=%d" % (N, P), "basis": N,
+                       "h2d_bytes_per_call": int(16 * N * N + 2 * 2 * 16 * N), "d2h_bytes_per_call": int(8 * N * N + 3 * 2 * 16 * N), "gen_s": round(gen_s, 1)},
+            "modes": res, "dtype": "f64", "data": "synthetic"}
+    print(json.dumps(line))
+
+
 def cpu_baseline(Hp_np, Psi_bra, Psi_ket, tau, budget_s=15.0):
     import oracle                                                    # the checker, timed as the CPU baseline only
     oracle.build()
@@ -543,6 +603,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="multi-GPU: skip the checked N=4096 step on the shards")
     ap.add_argument("--config5", action="store_true", help="multi-GPU: BASELINE config 5 (N~30k, Taylor vs Chebyshev nuclear step) instead of the throughput line")
     ap.add_argument("--config5-taylor-frac", type=float, default=0.02, help="fraction of the 0.5 fs step the Taylor propagator is timed on (scaled linearly)")
+    ap.add_argument("--team", type=int, default=0, help="single process: time the primary legacy symbol on a team of this many GPUs (DYNEMOL_B200_GPUS)")
     ap.add_argument("--skip-small", action="store_true", help="N=1: skip the N=900 small-operator side measurement")
     ap.add_argument("--skip-65k", action="store_true", help="N=1: skip the N=65536 single-GPU side measurement")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: no CPU baseline leg")
@@ -550,6 +611,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.team > 1:
+        return run_team_legacy(args)
     if args.gpus == 1:
         return run_ours_single(args)
     from dynemol_b200 import sharded

@@ -73,6 +73,19 @@ def init_sharded(N: int, dist, local_rank: int):
     return P, row0, m
 
 
+def nvlink_counters_kib(index: int):
+    """(tx_KiB, rx_KiB) summed over the NVLink links of GPU `index` (nvidia-smi nvlink -gt d), or None."""
+    import re
+    import subprocess
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True, timeout=20).stdout
+        tx = sum(int(v) for v in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out))
+        rx = sum(int(v) for v in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out))
+        return (tx, rx) if (tx or rx) else None
+    except Exception:
+        return None
+
+
 def synthetic_packets(N: int):
     """el on orbitals 0..63, hole on 64..127; unnormalised S-free variant for the throughput configs."""
     w = 64
@@ -109,12 +122,14 @@ def bench_main(args):
 
     for _ in range(max(args.warmup, 3)):
         P.run_terms(tau, B.TERMS_PER_STEP)
+    nv0 = nvlink_counters_kib(local_rank) if rank == 0 else None      # BEFORE the barrier: the subprocess must not delay rank 0's launches
     dist.barrier(); torch.cuda.synchronize(dev)
     l0 = P.launch_count()
     with B.ClockSampler(local_rank) as cs:
         ms, _ = P.run_terms(tau, B.TERMS_PER_STEP * args.steps)       # CUDA events on the launching stream
         torch.cuda.synchronize(dev)
     dist.barrier()
+    nv1 = nvlink_counters_kib(local_rank) if rank == 0 else None
     launches = P.launch_count() - l0
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)                          # max over ranks of the device-timed region
@@ -124,7 +139,7 @@ def bench_main(args):
     clocks = cs.result()
 
     # end-to-end through the host-buffer API: packets from host memory each call, result read back
-    e2e_terms = B.TERMS_PER_STEP * 4
+    e2e_terms = B.TERMS_PER_STEP * 32          # ~ one nuclear step of dt = 0.5 fs with the single-expansion Chebyshev propagator
     dist.barrier(); torch.cuda.synchronize(dev)
     t1 = time.perf_counter()
     P.set_packets(bra, ket)
@@ -163,6 +178,11 @@ def bench_main(args):
                 "e2e": {"value": round(e2e_terms / float(te.item()), 2), "unit": B.UNIT, "h2d_bytes_per_step": int(2 * 2 * 16 * N),
                         "d2h_bytes_per_step": int(2 * 2 * 16 * N), "call": "set_packets(host)+%d terms+get_packets(host); H' shards resident" % e2e_terms},
                 "gpu_launches": int(launches), "clocks": clocks, "single_gpu_same_workload": ref1, "parity_check": parity}
+        if nv0 and nv1:
+            # NVLink traffic of rank 0's GPU over the timed region (driver counters, all links): the algorithm moves, per
+            # term and GPU, (P-1)/P * N * 32 B of bra partials in (peer loads) and as many ket bytes out (peer stores)
+            line["nvlink"] = {"tx_kib_per_term": round((nv1[0] - nv0[0]) / n_terms, 1), "rx_kib_per_term": round((nv1[1] - nv0[1]) / n_terms, 1),
+                              "algorithmic_kib_per_term_each_way": round((world - 1) / world * N * 32 / 1024.0, 1), "source": "nvidia-smi nvlink -gt d, GPU of rank 0"}
         if ref1 and ref1.get("value"):
             line["speedup_same_workload"] = round(value / ref1["value"], 3)
             line["efficiency_same_workload"] = round(value / ref1["value"] / world, 4)
