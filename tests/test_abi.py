@@ -81,3 +81,19 @@ def test_product_never_imports_oracle():
     for f in os.listdir(tools):
         txt = open(os.path.join(tools, f), errors="ignore").read()
         assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt and "libref_" not in txt, f
+
+
+def test_fortran_caller_patch_applies(tmp_path):
+    """integration/ElHl_Chebyshev_GPU.patch (the refreshed Fortran caller: current FMO_analysis interface, one batched
+    call) applies cleanly to the reference's file.  Only where the reference tree exists (not on the GPU box)."""
+    ref = "/root/reference/ElHl_Chebyshev_GPU.f"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree not present")
+    import shutil
+    shutil.copy(ref, tmp_path / "ElHl_Chebyshev_GPU.f")
+    patch = os.path.join(ROOT, "integration", "ElHl_Chebyshev_GPU.patch")
+    res = subprocess.run(["patch", "-p1", "-i", patch], cwd=tmp_path, capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    out = (tmp_path / "ElHl_Chebyshev_GPU.f").read_text()
+    assert "MO=wv_FMO" not in out and 'bind(C, name="propagationelhl2_gpucaller_")' in out
+    assert out.count("call PropagationElHl2_gpucaller(") == 1 and "call PropagationElHl_gpucaller(" not in out
