@@ -84,7 +84,8 @@ DECLARED_SYMBOLS = [
     "dyb_team_set_packets", "dyb_team_get_packets", "dyb_team_set_spectral_bounds", "dyb_team_estimate_spectral_bounds",
     "dyb_team_propagate", "dyb_team_ao_bra", "dyb_team_populations", "dyb_team_quasiparticle_energies", "dyb_team_run_terms",
     "dyb_team_passes_last", "dyb_team_last_error", "dyb_unwrap_pin_bytes", "dyb_legacy_passes_last",
-    "dyb_form_hprime_async", "dyb_wait_outputs", "dyb_download_hprime_rows_device", "dyb_comm_p2p_open_local",
+    "dyb_form_hprime_async", "dyb_wait_outputs", "dyb_factor_overlap", "dyb_factor_device", "dyb_upload_column_block",
+    "dyb_solve_column_block", "dyb_column_block_device", "dyb_take_rows_from_column_blocks", "dyb_download_hprime_rows_device", "dyb_comm_p2p_open_local",
     "dyb_last_error", "dyb_version", "dyb_device_count", "dyb_plan", "dyb_resident_plan", "dyb_steady_schedule", "dyb_series_coefficients", "dyb_create", "dyb_destroy", "dyb_set_kernel", "dyb_set_series_kernel",
     "dyb_get_info", "dyb_upload_hprime", "dyb_upload_hprime_device", "dyb_upload_hprime_rows_device", "dyb_hprime_device", "dyb_form_hprime", "dyb_form_hprime_device", "dyb_form_hprime_from_overlap",
     "dyb_download_hprime", "dyb_set_packets", "dyb_get_packets", "dyb_propagate", "dyb_ao_bra",

@@ -109,6 +109,7 @@ struct dyb_ctx {
 
     double* H = nullptr;                 // ld x N
     double* S = nullptr;                 // N x N factor of S (Cholesky or LU) kept for S^-1 applications
+    double* colblk = nullptr;            // N x M column block of h / H' (distributed formation on a team, dyb_solve_column_block)
     int64_t* ipiv = nullptr;             // LU pivots (fallback)
     bool have_factor = false, factor_is_lu = false;
     double *psi_b = nullptr, *psi_k = nullptr, *sum_b = nullptr, *sum_k = nullptr;
@@ -978,6 +979,7 @@ int dyb_destroy(dyb_ctx* c) {
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     for (double** b : {&c->rs_send, &c->rs_recv, &c->scal_all, &c->full_tmp}) if (*b) cudaFree(*b);
     if (c->ipiv) cudaFree(c->ipiv);
+    if (c->colblk) cudaFree(c->colblk);
     for (double* b : {c->lz_V, c->lz_W, c->lz_dots}) if (b) cudaFree(b);
     if (c->lz_state) cudaFree(c->lz_state);
     if (c->seg_base) cudaFree(c->seg_base);
@@ -1274,6 +1276,102 @@ int dyb_form_hprime(dyb_ctx* c, const double* h_S, const double* h_h, double* h_
     if (rc) return rc;
     if ((rc = dyb_wait_outputs(c))) return rc;
     CK(cudaStreamSynchronize(c->stream));
+    return DYB_OK;
+}
+
+// ---- distributed formation on a team (team.cu): the Cholesky factor of S is computed once (first device), every member
+// solves S X = h for ITS block of columns (2 N^3 / P flops each, in parallel) and the column blocks are then exchanged
+// into row blocks by peer copies.  2.33 N^3 flops on one GPU become N^3/3 + 2 N^3/P.
+// Factorisation only: S (host) -> Cholesky factor in ctx->S.  Full-matrix contexts.  DYB_ESINGULAR if S is not
+// numerically positive definite (the caller then takes the single-GPU route with its LU fallback).
+int dyb_factor_overlap(dyb_ctx* c, const double* h_S) {
+    if (!c || !h_S) return fail(DYB_EINVAL, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    int rc = dyb_wait_outputs(c);
+    if (rc) return rc;
+    if ((rc = ensure_solver(c))) return rc;
+    const int64_t n = c->N;
+    c->have_factor = false;
+    CK(cudaMemcpyAsync(c->S, h_S, (size_t)n * n * 8, cudaMemcpyHostToDevice, c->stream));
+    size_t wd = 0, wh = 0;
+    int* d_info = reinterpret_cast<int*>(c->scal + 32);
+    CKS(cusolverDnXpotrf_bufferSize(c->solver, c->sparams, CUBLAS_FILL_MODE_UPPER, n, CUDA_R_64F, c->S, n, CUDA_R_64F, &wd, &wh));
+    DevScratch w1; std::vector<char> h_work(wh ? wh : 1);
+    if (wd) CK(cudaMalloc(&w1.p, wd));
+    CKS(cusolverDnXpotrf(c->solver, c->sparams, CUBLAS_FILL_MODE_UPPER, n, CUDA_R_64F, c->S, n, CUDA_R_64F, w1.p, wd, h_work.data(), wh, d_info));
+    CK(cudaMemcpyAsync(c->h_scal + 100, d_info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (*reinterpret_cast<int*>(c->h_scal + 100) != 0) return fail(DYB_ESINGULAR, "S is not numerically positive definite (potrf info=%d)", *reinterpret_cast<int*>(c->h_scal + 100));
+    c->have_factor = true; c->factor_is_lu = false;
+    return DYB_OK;
+}
+
+int dyb_factor_device(dyb_ctx* c, void** d_U, int64_t* ldu) {
+    if (!c || !d_U || !ldu) return fail(DYB_EINVAL, "NULL argument");
+    if (!c->have_factor || c->factor_is_lu) return fail(DYB_EINVAL, "no Cholesky factor in this context");
+    *d_U = c->S; *ldu = c->N;
+    return DYB_OK;
+}
+
+// Member of a row-sharded team: bring columns row0 .. row0+M-1 of the host matrix h into the member's column block.
+int dyb_upload_column_block(dyb_ctx* c, const double* h_h) {
+    if (!c || !h_h) return fail(DYB_EINVAL, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    int rc = dyb_wait_outputs(c);
+    if (rc) return rc;
+    if (!c->colblk) CK(cudaMalloc(&c->colblk, (size_t)c->N * c->M * 8));
+    CK(cudaMemcpyAsync(c->colblk, h_h + (size_t)c->row0 * c->N, (size_t)c->N * c->M * 8, cudaMemcpyHostToDevice, c->stream));   // contiguous in column-major
+    return DYB_OK;
+}
+
+// X = S^-1 h[:, block] with the Cholesky factor d_U (possibly on another device: copied over NVLink first); the solved
+// block (= columns row0.. of H') is sent to h_H_out[:, block] beside whatever comes next (dyb_wait_outputs joins it).
+int dyb_solve_column_block(dyb_ctx* c, const void* d_U, int64_t ldu, double* h_H_out) {
+    if (!c || !d_U || ldu < c->N) return fail(DYB_EINVAL, "bad argument");
+    if (!c->colblk) return fail(DYB_EINVAL, "dyb_upload_column_block must come first");
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_solver(c);
+    if (rc) return rc;
+    const int64_t n = c->N;
+    if (d_U != c->S) CK(cudaMemcpy2DAsync(c->S, (size_t)n * 8, d_U, (size_t)ldu * 8, (size_t)n * 8, n, cudaMemcpyDefault, c->stream));
+    int* d_info = reinterpret_cast<int*>(c->scal + 32);
+    CKS(cusolverDnXpotrs(c->solver, c->sparams, CUBLAS_FILL_MODE_UPPER, n, c->M, CUDA_R_64F, c->S, n, CUDA_R_64F, c->colblk, n, d_info));
+    if (h_H_out) {
+        CK(cudaEventRecord(c->ev_H_done, c->stream));
+        CK(cudaStreamWaitEvent(c->copy_stream, c->ev_H_done, 0));
+        c->out_rc = 0;
+        double* dst = h_H_out + (size_t)c->row0 * n;
+        const size_t bytes = (size_t)n * c->M * 8;
+        c->out_thread = std::thread([c, dst, bytes]() {
+            cudaError_t e = cudaSetDevice(c->device);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(dst, c->colblk, bytes, cudaMemcpyDeviceToHost, c->copy_stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->copy_stream);
+            if (e != cudaSuccess) { c->out_rc = DYB_ECUDA; c->out_err = std::string("download of H' failed: ") + cudaGetErrorString(e); }
+        });
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return DYB_OK;
+}
+
+int dyb_column_block_device(dyb_ctx* c, void** d_X) {
+    if (!c || !d_X) return fail(DYB_EINVAL, "NULL argument");
+    *d_X = c->colblk;
+    return DYB_OK;
+}
+
+// The member's row block of H' out of the P solved column blocks (d_X[q] = columns q*M .. of H', N rows, ld N): P peer
+// copies of M x M sub-blocks over NVLink (the block-transposed all-to-all of the distributed formation).
+int dyb_take_rows_from_column_blocks(dyb_ctx* c, void* const* d_X, int n_blocks) {
+    if (!c || !d_X || n_blocks != c->world) return fail(DYB_EINVAL, "bad argument");
+    CK(cudaSetDevice(c->device));
+    const size_t n = c->N, M = c->M;
+    for (int q = 0; q < n_blocks; ++q) {
+        if (!d_X[q]) return fail(DYB_EINVAL, "column block %d missing", q);
+        CK(cudaMemcpy2DAsync(c->H + (size_t)q * M * c->ld, (size_t)c->ld * 8, static_cast<const double*>(d_X[q]) + c->row0, n * 8,
+                             M * 8, M, cudaMemcpyDefault, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    c->have_factor = false;              // members keep a copy of the factor only as scratch; S^-1 applications go through the first device
     return DYB_OK;
 }
 

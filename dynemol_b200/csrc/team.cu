@@ -122,9 +122,38 @@ int dyb_team_form_hprime(dyb_team* t, const double* h_S, const double* h_h, doub
     if (!t || !h_S || !h_h) return tfail(DYB_EINVAL, "NULL argument");
     int rc = ensure_form(t);
     if (rc) return rc;
+    if (t->P == 1) {
+        if ((rc = dyb_form_hprime_async(t->form, h_S, h_h, h_H_out)) || (rc = dyb_sync(t->form))) return tfail(rc, dyb_last_error());
+        return DYB_OK;
+    }
+    const bool distributed = !(getenv("DYNEMOL_B200_TEAM_FORM") && !strcmp(getenv("DYNEMOL_B200_TEAM_FORM"), "single"));
+    if (distributed) {
+        // 1. every member uploads ITS block of columns of h over its own PCIe link while the first device factorises S
+        int rc_factor = DYB_OK;
+        std::string factor_err;
+        rc = team_run(t, [&](dyb_ctx* c, int r) -> int {
+            int q = dyb_upload_column_block(c, h_h);
+            if (q) return q;
+            if (r == 0) { rc_factor = dyb_factor_overlap(t->form, h_S); if (rc_factor) factor_err = dyb_last_error(); }
+            return dyb_sync(c);
+        });
+        if (rc) return rc;
+        if (rc_factor == DYB_OK) {
+            void* dU = nullptr; int64_t ldu = 0;
+            if ((rc = dyb_factor_device(t->form, &dU, &ldu))) return tfail(rc, dyb_last_error());
+            // 2. S X = h[:, block] on every member with a copy of the factor (pulled over NVLink): 2 N^3 / P flops each;
+            //    the solved block goes down to the host columns it belongs to, beside what follows
+            if ((rc = team_run(t, [&](dyb_ctx* c, int) -> int { return dyb_solve_column_block(c, dU, ldu, h_H_out); }))) return rc;
+            // 3. column blocks -> row blocks: every member pulls its M x M sub-blocks out of the peers' blocks
+            std::vector<void*> X(t->P, nullptr);
+            for (int r = 0; r < t->P; ++r) dyb_column_block_device(t->m[r], &X[r]);
+            return team_run(t, [&](dyb_ctx* c, int) -> int { return dyb_take_rows_from_column_blocks(c, X.data(), t->P); });
+        }
+        if (rc_factor != DYB_ESINGULAR) return tfail(rc_factor, factor_err);
+        // S is not numerically positive definite: the single-device route below has the LU fallback
+    }
     if ((rc = dyb_form_hprime_async(t->form, h_S, h_h, h_H_out))) return tfail(rc, dyb_last_error());
     if ((rc = dyb_sync(t->form))) return tfail(rc, dyb_last_error());       // the solve is done; the download of H' may still run
-    if (t->P == 1) return DYB_OK;
     void* d = nullptr; int64_t ld = 0;
     dyb_hprime_device(t->form, &d, &ld);
     // every member pulls its row block out of the first device's H' (peer copy over NVLink)
@@ -133,9 +162,10 @@ int dyb_team_form_hprime(dyb_team* t, const double* h_S, const double* h_h, doub
 
 int dyb_team_wait_outputs(dyb_team* t) {
     if (!t) return tfail(DYB_EINVAL, "team is NULL");
-    if (!t->form) return DYB_OK;
-    int rc = dyb_wait_outputs(t->form);
-    return rc ? tfail(rc, dyb_last_error()) : DYB_OK;
+    int rc;
+    for (dyb_ctx* c : t->m) if ((rc = dyb_wait_outputs(c))) return tfail(rc, dyb_last_error());
+    if (t->form && (rc = dyb_wait_outputs(t->form))) return tfail(rc, dyb_last_error());
+    return DYB_OK;
 }
 
 int dyb_team_upload_hprime(dyb_team* t, const double* h_H, int64_t lda) {

@@ -81,8 +81,11 @@ def test_legacy_symbol_on_a_team(api, oracle_mod):
     for p in range(2):
         ref.append(oracle_mod.propagation(Hp1, Psi_bra[:, p], Psi_ket[:, p], 0.0, dt, tau0))
     try:
-        for P in team_sizes(api):
+        # formation: distributed (factor on the first GPU, column-block solves on every GPU, block exchange) by default;
+        # "single" = whole solve on the first GPU, row blocks scattered -- both must give the same H'
+        for P, form in [(p, "distributed") for p in team_sizes(api)] + [(2, "single")]:
             os.environ["DYNEMOL_B200_GPUS"] = str(P)
+            os.environ["DYNEMOL_B200_TEAM_FORM"] = form
             out = api.legacy_propagationelhl(S, h, Psi_bra, Psi_ket, 0.0, dt, tau0)
             assert relerr(out["H_prime"], Hp1) < 1e-12
             Sx = lambda z: (S @ z.real) + 1j * (S @ z.imag)
@@ -93,7 +96,7 @@ def test_legacy_symbol_on_a_team(api, oracle_mod):
                 assert np.abs(Sx(out["AO_bra"][:, p]) - out["PSI_bra"][:, p]).max() < 1e-10      # AO_bra = S^-1 PSI_bra
             api.gpu_finalize()
     finally:
-        os.environ.pop("DYNEMOL_B200_GPUS", None)
+        os.environ.pop("DYNEMOL_B200_GPUS", None); os.environ.pop("DYNEMOL_B200_TEAM_FORM", None)
         api.gpu_finalize()
 
 
