@@ -109,6 +109,7 @@ struct dyb_ctx {
 
     double* H = nullptr;                 // ld x N
     double* S = nullptr;                 // N x N factor of S (Cholesky or LU) kept for S^-1 applications
+    double *ehr_A = nullptr, *ehr_X = nullptr, *ehr_K = nullptr, *ehr_vec = nullptr;   // Ehrenfest kernel scratch (3 N x N + packets), allocated on first use
     double* colblk = nullptr;            // N x M column block of h / H' (distributed formation on a team, dyb_solve_column_block)
     int64_t* ipiv = nullptr;             // LU pivots (fallback)
     bool have_factor = false, factor_is_lu = false;
@@ -980,6 +981,7 @@ int dyb_destroy(dyb_ctx* c) {
     for (double** b : {&c->rs_send, &c->rs_recv, &c->scal_all, &c->full_tmp}) if (*b) cudaFree(*b);
     if (c->ipiv) cudaFree(c->ipiv);
     if (c->colblk) cudaFree(c->colblk);
+    for (double* b : {c->ehr_A, c->ehr_X, c->ehr_K, c->ehr_vec}) if (b) cudaFree(b);
     for (double* b : {c->lz_V, c->lz_W, c->lz_dots}) if (b) cudaFree(b);
     if (c->lz_state) cudaFree(c->lz_state);
     if (c->seg_base) cudaFree(c->seg_base);
@@ -1954,14 +1956,24 @@ __global__ void hadamard_minus_kernel(size_t n_elem, const double* __restrict__ 
     if (i < n_elem) K[i] = X[i] * A[i] - K[i];
 }
 
+// the three N x N scratch matrices (and the packet staging) of the Ehrenfest kernels live in the context: allocated on the
+// first call, reused by every nuclear step (the reference allocates and frees them per call, Taylor_gpu.cpp:351-356 style)
+static int ensure_ehrenfest_scratch(dyb_ctx* c) {
+    const size_t bytes = (size_t)c->N * c->N * 8;
+    if (!c->ehr_A) CK(cudaMalloc(&c->ehr_A, bytes));
+    if (!c->ehr_X) CK(cudaMalloc(&c->ehr_X, bytes));
+    if (!c->ehr_K) CK(cudaMalloc(&c->ehr_K, bytes));
+    if (!c->ehr_vec) CK(cudaMalloc(&c->ehr_vec, (size_t)c->N * 2 * sizeof(dyb_complex) * 2));
+    return DYB_OK;
+}
+
 int dyb_ehrenfest_kernel(dyb_ctx* c, const double* h_A, const double* h_X, double* h_K) {
     if (!c || !h_A || !h_X || !h_K) return fail(DYB_EINVAL, "NULL argument");
     if (c->M != c->N) return fail(DYB_EINVAL, "full-matrix contexts only");
     CK(cudaSetDevice(c->device));
     const size_t n = c->N, bytes = n * n * 8;
-    DevScratch bA, bX, bK;
-    CK(cudaMalloc(&bA.p, bytes)); CK(cudaMalloc(&bX.p, bytes)); CK(cudaMalloc(&bK.p, bytes));
-    double *A = static_cast<double*>(bA.p), *X = static_cast<double*>(bX.p), *K = static_cast<double*>(bK.p);
+    { int rc0 = ensure_ehrenfest_scratch(c); if (rc0) return rc0; }
+    double *A = c->ehr_A, *X = c->ehr_X, *K = c->ehr_K;
     int rc = DYB_OK;
     do {
         if (!c->blas) { if (cublasCreate(&c->blas) != CUBLAS_STATUS_SUCCESS || cublasSetStream(c->blas, c->stream) != CUBLAS_STATUS_SUCCESS) { rc = fail(DYB_ECUDA, "cublasCreate failed"); break; } }
@@ -1997,10 +2009,9 @@ int dyb_ehrenfest_kernel2(dyb_ctx* c, const dyb_complex* h_bra, const dyb_comple
     if (c->M != c->N) return fail(DYB_EINVAL, "full-matrix contexts only");
     CK(cudaSetDevice(c->device));
     const size_t n = c->N, bytes = n * n * 8, vbytes = n * 2 * sizeof(dyb_complex);
-    DevScratch bA, bX, bK, bB, bKt;
-    CK(cudaMalloc(&bA.p, bytes)); CK(cudaMalloc(&bX.p, bytes)); CK(cudaMalloc(&bK.p, bytes));
-    CK(cudaMalloc(&bB.p, vbytes)); CK(cudaMalloc(&bKt.p, vbytes));
-    double *A = static_cast<double*>(bA.p), *X = static_cast<double*>(bX.p), *K = static_cast<double*>(bK.p);
+    { int rc0 = ensure_ehrenfest_scratch(c); if (rc0) return rc0; }
+    struct { void* p; } bB = {c->ehr_vec}, bKt = {reinterpret_cast<char*>(c->ehr_vec) + vbytes};
+    double *A = c->ehr_A, *X = c->ehr_X, *K = c->ehr_K;
     int rc = DYB_OK;
     do {
         if (!c->blas) { if (cublasCreate(&c->blas) != CUBLAS_STATUS_SUCCESS || cublasSetStream(c->blas, c->stream) != CUBLAS_STATUS_SUCCESS) { rc = fail(DYB_ECUDA, "cublasCreate failed"); break; } }
