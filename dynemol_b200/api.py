@@ -86,7 +86,7 @@ DECLARED_SYMBOLS = [
     "dyb_team_passes_last", "dyb_team_last_error", "dyb_unwrap_pin_bytes", "dyb_legacy_passes_last",
     "dyb_form_hprime_async", "dyb_wait_outputs", "dyb_factor_overlap", "dyb_factor_device", "dyb_upload_column_block",
     "dyb_solve_column_block", "dyb_column_block_device", "dyb_take_rows_from_column_blocks", "dyb_download_hprime_rows_device", "dyb_comm_p2p_open_local",
-    "dyb_last_error", "dyb_version", "dyb_device_count", "dyb_plan", "dyb_resident_plan", "dyb_steady_schedule", "dyb_series_coefficients", "dyb_create", "dyb_destroy", "dyb_set_kernel", "dyb_set_series_kernel",
+    "dyb_last_error", "dyb_version", "dyb_device_count", "dyb_plan", "dyb_resident_plan", "dyb_mid_plan", "dyb_steady_schedule", "dyb_series_coefficients", "dyb_create", "dyb_destroy", "dyb_set_kernel", "dyb_set_series_kernel",
     "dyb_get_info", "dyb_upload_hprime", "dyb_upload_hprime_device", "dyb_upload_hprime_rows_device", "dyb_hprime_device", "dyb_form_hprime", "dyb_form_hprime_device", "dyb_form_hprime_from_overlap",
     "dyb_download_hprime", "dyb_set_packets", "dyb_get_packets", "dyb_propagate", "dyb_ao_bra",
     "dyb_populations", "dyb_run_terms", "dyb_dual_matvec", "dyb_sync", "dyb_launch_count",
@@ -148,6 +148,17 @@ def resident_plan(N: int, sm_count: int = 148, smem_optin: int = 232448) -> dict
     out = (C.c_int64 * 6)()
     _check(lib.dyb_resident_plan(C.c_int(N), C.c_int(sm_count), C.c_int64(smem_optin), out))
     return dict(zip(["grid_side", "block", "smem_stride", "smem_bytes", "threads", "fits"], [int(v) for v in out]))
+
+
+def mid_plan(N: int, sm_count: int = 148, smem_optin: int = 232448) -> dict:
+    """Blocking of the streamed one-launch series kernel for mid-size operators (csrc/mid.cuh); host arithmetic only."""
+    out = (C.c_int64 * 12)()
+    diag = (C.c_int32 * 160)()
+    _check(lib.dyb_mid_plan(C.c_int(N), C.c_int(sm_count), C.c_int64(smem_optin), out, diag))
+    d = dict(zip(["block_rows", "tile_cols", "grid_rows", "grid_cols", "block_cols", "tiles_per_term", "stages", "log2_lanes_ket",
+                  "log2_lanes_bra", "n_diag", "smem_bytes", "fits"], [int(v) for v in out]))
+    d["diag"] = [int(diag[i]) for i in range(min(d["n_diag"], 160))]
+    return d
 
 
 def steady_schedule(t: float, t_max: float, tau: float, max_sub: int = 4096) -> np.ndarray:
@@ -295,8 +306,8 @@ class Propagator:
         _check(lib.dyb_set_kernel(self._h, C.c_int(kernel)))
 
     def set_series_kernel(self, kind):
-        """kind: 'auto' | 'term' | 'resident' (include/dynemol_b200.h: DYB_SERIES_*)."""
-        code = {"auto": 0, "term": 1, "resident": 3}[kind] if isinstance(kind, str) else int(kind)
+        """kind: 'auto' | 'term' | 'resident' | 'mid' (include/dynemol_b200.h: DYB_SERIES_*)."""
+        code = {"auto": 0, "term": 1, "resident": 3, "mid": 5}[kind] if isinstance(kind, str) else int(kind)
         _check(lib.dyb_set_series_kernel(self._h, C.c_int(code)))
 
     def info(self) -> dict:

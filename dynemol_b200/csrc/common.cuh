@@ -118,6 +118,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) { }
 }
+// bounded variant for the cooperative one-launch kernels: a copy that never lands must end in a trap, not in a hung GPU
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
+    for (long long it = 0; !mbar_try_wait(bar, parity); ++it)
+        if (it > (1ll << 28)) __trap();
+}
 // 3-D tiled TMA load, global -> shared, completion on an mbarrier, with an L2 cache-policy hint
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar,
                                             int c0, int c1, int c2, uint64_t policy) {

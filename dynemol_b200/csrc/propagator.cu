@@ -27,6 +27,7 @@
 #include "matvec.cuh"
 #include "epilogue.cuh"
 #include "resident.cuh"
+#include "mid.cuh"
 #include "lanczos.cuh"
 
 using namespace dyb;
@@ -96,6 +97,14 @@ struct dyb_ctx {
     int res_Gd = 0, res_Bs = 0, res_ldS = 0;     // resident.cuh: grid side, block size, smem column stride (0: does not fit)
     size_t res_smem = 0;
     double *res_pk = nullptr, *res_pb = nullptr, *res_dscal = nullptr, *res_psi = nullptr;
+    // mid.cuh: streamed one-launch series kernel for mid-size operators (plan + buffers; mid_fits: launchable on this device)
+    bool mid_fits = false;
+    int mid_auto_max = 6144;             // DYB_SERIES_AUTO selects it for resident range < N <= this (env DYNEMOL_B200_MID_MAX)
+    double mid_l2_mb = 96.0;             // MB of H' the loads ask the L2 to keep (evict_last), env DYNEMOL_B200_MID_L2MB
+    MidParams mid_P;                     // constant part of the launch parameters
+    size_t mid_smem = 0;
+    CUtensorMap tmap_mid;
+    double *mid_pk = nullptr, *mid_pb = nullptr, *mid_dscal = nullptr, *mid_psi = nullptr;
     PassParams* d_passes = nullptr;      // per-term parameters of the series in flight
     unsigned long long* gbar = nullptr;  // grid barrier counter
     cudaStream_t stream = nullptr;
@@ -176,6 +185,24 @@ static int build_tensor_map(dyb_ctx* c) {
                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(DYB_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     c->have_tmap = true;
+    return DYB_OK;
+}
+
+// mid.cuh streams blocks of 256*WR rows x TC columns: same 3-D view of H', another box
+static int build_tensor_map_mid(dyb_ctx* c, int WR, int TC) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(DYB_ECUDA, "cuTensorMapEncodeTiled not available");
+    if (c->ld % MID_SUB) return fail(DYB_EINVAL, "leading dimension %lld is not a multiple of %d", c->ld, MID_SUB);
+    cuuint64_t dims[3]    = {(cuuint64_t)MID_SUB, (cuuint64_t)(c->ld / MID_SUB), (cuuint64_t)c->N};
+    cuuint64_t strides[2] = {(cuuint64_t)MID_SUB * 8, (cuuint64_t)c->ld * 8};
+    cuuint32_t box[3]     = {(cuuint32_t)MID_SUB, (cuuint32_t)WR, (cuuint32_t)TC};
+    cuuint32_t estr[3]    = {1, 1, 1};
+    CUresult r = ((PFN_encodeTiled)fn)(&c->tmap_mid, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, c->H, dims, strides, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DYB_ECUDA, "cuTensorMapEncodeTiled (mid) failed with CUresult %d", (int)r);
     return DYB_OK;
 }
 
@@ -423,9 +450,64 @@ static int run_series_resident(dyb_ctx* c, const std::vector<PassParams>& passes
     return DYB_OK;
 }
 
-// One series in a single launch when the resident kernel applies.
-static bool single_launch_ok(const dyb_ctx* c) { return resident_ok(c); }
-static int run_series_single_launch(dyb_ctx* c, const std::vector<PassParams>& passes) { return run_series_resident(c, passes); }
+// Mid-size operators streamed by ONE launch per series (mid.cuh): single GPU; not for the reference-GPU term test.
+// Blocking (pure host arithmetic, exported as dyb_mid_plan for the CPU tests): R = 512 rows per CTA, Gr = ceil(N / R) block
+// rows, Gc = sm_count / Gr block columns of Cnp = roundup(ceil(N / Gc), 8) columns, Gc = ceil(N / Cnp).
+struct MidPlan { int WR, R, TC, Gr, Gc, Cnp, NT, ST, lslk, lslb, nd; int diag[MID_MAX_DIAG]; size_t smem; bool fits; };
+static int ceil_log2_lanes(int n_partials) { int l = 0; while (((n_partials + (1 << l) - 1) >> l) > 8) ++l; return l; }
+static MidPlan make_mid_plan(int N, int sm_count, size_t smem_optin, size_t static_smem) {
+    MidPlan m;
+    memset(&m, 0, sizeof m);
+    m.WR = 2; m.R = m.WR * MID_SUB; m.TC = (MID_WARPS / m.WR) * MID_CPW;
+    m.Gr = (N + m.R - 1) / m.R;
+    const int gc0 = sm_count / std::max(1, m.Gr);
+    if (gc0 < 1) return m;
+    const int cn = (N + gc0 - 1) / gc0;
+    m.Cnp = (cn + m.TC - 1) / m.TC * m.TC;
+    m.Gc = (N + m.Cnp - 1) / m.Cnp;
+    m.NT = m.Cnp / m.TC;
+    m.lslk = ceil_log2_lanes(m.Gc); m.lslb = ceil_log2_lanes(m.Gr);
+    for (int b = 0; b < m.Gr * m.Gc; ++b) {                   // CTAs that hold bra AND ket entries of some index
+        const int bi = b / m.Gc, bj = b % m.Gc;
+        const int i0 = std::max(bi * m.R, bj * m.Cnp), i1 = std::min(std::min(bi * m.R + m.R, bj * m.Cnp + m.Cnp), N);
+        if (i0 < i1) { if (m.nd < MID_MAX_DIAG) m.diag[m.nd] = b; m.nd++; }
+    }
+    const size_t budget = std::min((size_t)MID_SMEM_MAX, smem_optin > static_smem ? smem_optin - static_smem : 0);
+    for (m.ST = MID_MAX_ST; m.ST >= 2; --m.ST) { m.smem = (size_t)MidSmem(m.ST, m.R, m.Cnp).total; if (m.smem <= budget) break; }
+    m.fits = m.ST >= 2 && m.nd <= MID_MAX_DIAG && m.lslk <= 5 && m.lslb <= 5 && m.Gr * m.Gc <= sm_count
+             && (size_t)m.WR * m.Cnp * NQ * 8 <= (size_t)MID_U_BYTES && (size_t)(m.Cnp + m.R) * 2 * 8 <= (size_t)MID_U_BYTES;
+    return m;
+}
+static bool mid_ok(const dyb_ctx* c, bool refgpu) {
+    if (!c->mid_fits || c->world != 1 || refgpu) return false;
+    if (c->series_kind == DYB_SERIES_MID) return true;
+    return c->series_kind == DYB_SERIES_AUTO && c->res_Gd == 0 && c->N <= c->mid_auto_max;
+}
+
+static int run_series_mid(dyb_ctx* c, const std::vector<PassParams>& passes) {
+    const int n = (int)passes.size();
+    if (n < 1 || n > MAX_CHAIN_PASSES) return fail(DYB_EINVAL, "series length %d out of range", n);
+    CK(cudaMemcpyAsync(c->d_passes, passes.data(), sizeof(PassParams) * n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->gbar, 0, sizeof(unsigned long long), c->stream));
+    MidParams P = c->mid_P;
+    P.x0k = c->vk[0]; P.x0b = c->vb[0]; P.sum_b = c->sum_b; P.sum_k = c->sum_k;
+    P.pk = c->mid_pk; P.pb = c->mid_pb; P.dscal = c->mid_dscal; P.psi_store = c->mid_psi;
+    P.ctrl = c->ctrl; P.passes = c->d_passes; P.n_steps = n; P.gbar = c->gbar;
+    void* args[] = {(void*)&c->tmap_mid, (void*)&P};
+    CK(cudaLaunchCooperativeKernel((const void*)mid_series_kernel_t<2>, dim3(P.Gr * P.Gc), dim3(MID_THREADS), args, c->mid_smem, c->stream));
+    c->launches++;
+    return DYB_OK;
+}
+
+// One series in a single cooperative launch when the resident or the mid-size kernel applies.
+static bool passes_refgpu(const std::vector<PassParams>& passes) {
+    for (const PassParams& pp : passes) if (pp.part[0].test_gpu || pp.part[1].test_gpu) return true;
+    return false;
+}
+static bool single_launch_ok(const dyb_ctx* c, bool refgpu = false) { return resident_ok(c) || mid_ok(c, refgpu); }
+static int run_series_single_launch(dyb_ctx* c, const std::vector<PassParams>& passes) {
+    return resident_ok(c) ? run_series_resident(c, passes) : run_series_mid(c, passes);
+}
 
 static int launch_series_init(dyb_ctx* c, const int adopt[2], const int active[2], int cur, const cplx* sum_scale = nullptr) {
     InitParams I;
@@ -623,7 +705,7 @@ static int propagate_series(dyb_ctx* c, int mode_in, double t_init, double t_max
         // Taylor.f:81-126 goes into ONE launch.  The sub-step schedule (tau, the shortened last sub-step and its
         // coefficients, Taylor.f:116-121) is predicted with the very operations the state machine below performs;
         // the device chains the sub-steps (PartPass::begin / chain) and stops a particle at the first failed norm test.
-        bool all_steady = resident_ok(c) && c->chain_steady;
+        bool all_steady = single_launch_ok(c, refgpu) && c->chain_steady;
         for (int p = 0; p < 2; ++p) if (active[p] && P[p].phase != 1) all_steady = false;
         if (all_steady) {
             std::vector<PassParams> passes;
@@ -655,7 +737,7 @@ static int propagate_series(dyb_ctx* c, int mode_in, double t_init, double t_max
             }
             if ((rc = launch_series_init(c, adopt, active, 0, mode == DYB_MODE_TAYLOR ? nullptr : sum_scale))) return rc;
             adopt[0] = adopt[1] = 0;
-            if ((rc = run_series_resident(c, passes))) return rc;
+            if ((rc = run_series_single_launch(c, passes))) return rc;
             if ((rc = read_ctrl(c))) return rc;
             c->passes_last += std::max(active[0] ? c->h_ctrl->part[0].n_terms : 0, active[1] ? c->h_ctrl->part[1].n_terms : 0);
             for (int p = 0; p < 2; ++p) {
@@ -690,7 +772,7 @@ static int propagate_series(dyb_ctx* c, int mode_in, double t_init, double t_max
         int prv = 2, cur = 0, nxt = 1;
         if ((rc = launch_series_init(c, adopt, active, cur, mode == DYB_MODE_TAYLOR ? nullptr : sum_scale))) return rc;
         adopt[0] = adopt[1] = 0;
-        if (single_launch_ok(c) && L <= MAX_SERIES_TERMS) {
+        if (single_launch_ok(c, refgpu) && L <= MAX_SERIES_TERMS) {
             std::vector<PassParams> passes(L);
             for (int s = 0; s < L; ++s) {
                 memset(&passes[s], 0, sizeof(PassParams));
@@ -805,7 +887,7 @@ static std::vector<cplx> cheb_full_coefficients(double tau, double ebar, double 
 // fused epilogue per term (PDL-chained), with the three rotating vectors of the recurrence
 static int run_pass_list(dyb_ctx* c, const std::vector<PassParams>& passes) {
     int rc;
-    if (resident_ok(c) && (int)passes.size() <= MAX_CHAIN_PASSES) return run_series_resident(c, passes);
+    if (single_launch_ok(c, passes_refgpu(passes)) && (int)passes.size() <= MAX_CHAIN_PASSES) return run_series_single_launch(c, passes);
     int prv = 2, cur = 0, nxt = 1;
     for (const PassParams& pp : passes) {
         EpiParams E = epi_params(c, cur, prv, nxt);
@@ -836,7 +918,7 @@ static int propagate_cheb_full(dyb_ctx* c, double t_init, double t_max, const do
         tau = std::min(tau, remaining);
         const double ebar = 0.5 * (emax + emin), de = 0.5 * (emax - emin);
         std::vector<cplx> C = cheb_full_coefficients(tau, ebar, de);
-        if (resident_ok(c) && (int)C.size() - 1 > MAX_CHAIN_PASSES) { tau *= 0.5; continue; }    // one launch holds 4096 terms
+        if (single_launch_ok(c) && (int)C.size() - 1 > MAX_CHAIN_PASSES) { tau *= 0.5; continue; }    // one launch holds 4096 terms
         const int K = (int)C.size();
         if (K < 2) C.push_back(cplx(0.0, 0.0));
         const int n_terms = std::max(1, K - 1);
@@ -933,6 +1015,18 @@ int dyb_resident_plan(int N, int sm_count, int64_t smem_optin, int64_t* out6) {
     return DYB_OK;
 }
 
+// Host-only: the blocking of the streamed one-launch series kernel (mid.cuh).  out12 = {block rows R, tile columns TC, grid rows
+// Gr, grid columns Gc, block columns Cnp, tiles per term, ring stages, log2 gather lanes (ket), log2 gather lanes (bra),
+// intersecting CTAs, dynamic smem bytes, fits (0/1)}; diag[out12[9]] (when non-NULL) receives their block indices.
+int dyb_mid_plan(int N, int sm_count, int64_t smem_optin, int64_t* out12, int32_t* diag) {
+    if (N <= 0 || sm_count <= 0 || smem_optin <= 0 || !out12) return fail(DYB_EINVAL, "bad argument");
+    const MidPlan m = make_mid_plan(N, sm_count, (size_t)smem_optin, 2048);
+    out12[0] = m.R; out12[1] = m.TC; out12[2] = m.Gr; out12[3] = m.Gc; out12[4] = m.Cnp; out12[5] = m.NT; out12[6] = m.ST;
+    out12[7] = m.lslk; out12[8] = m.lslb; out12[9] = m.nd; out12[10] = (int64_t)m.smem; out12[11] = m.fits ? 1 : 0;
+    if (diag) for (int d = 0; d < std::min(m.nd, (int)MID_MAX_DIAG); ++d) diag[d] = m.diag[d];
+    return DYB_OK;
+}
+
 // Host-only: the 25 series coefficients the library uses for a given tau and the number of terms k_max it would sum
 // (Taylor.f:224-239 + :165-171 ; Chebyshev_gpu.cpp:636-643 + :565-574 on the interval ebar +- de).  For the CPU tests.
 int dyb_series_coefficients(int mode, double tau, double ebar, double de, dyb_complex* out25, int* k_max) {
@@ -994,6 +1088,7 @@ int dyb_destroy(dyb_ctx* c) {
     if (c->res_pb) cudaFree(c->res_pb);
     if (c->res_dscal) cudaFree(c->res_dscal);
     if (c->res_psi) cudaFree(c->res_psi);
+    for (double* b : {c->mid_pk, c->mid_pb, c->mid_dscal, c->mid_psi}) if (b) cudaFree(b);
     if (c->h_ctrl) cudaFreeHost(c->h_ctrl);
     if (c->h_scal) cudaFreeHost(c->h_scal);
     for (auto e : c->ev) cudaEventDestroy(e);
@@ -1068,9 +1163,41 @@ int dyb_create(dyb_ctx** out, int device, int N, int row0, int n_rows) {
             CKC(alloc_zero(&c->res_psi, (size_t)Gd * Gd * RES_THREADS * 2));
         }
     }
+    if (row0 == 0 && n_rows == N && c->ld % MID_SUB == 0) {    // mid.cuh: blocking, buffers, tensor map of the streamed one-launch kernel
+        int smem_optin = 0, coop = 0, per_sm = 0;
+        CKCU(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        CKCU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+        cudaFuncAttributes fa;
+        CKCU(cudaFuncGetAttributes(&fa, mid_series_kernel_t<2>));
+        const MidPlan mp = make_mid_plan(N, c->sm_count, (size_t)smem_optin, fa.sharedSizeBytes);
+        bool launchable = mp.fits && coop;
+        if (launchable) {
+            CKCU(cudaFuncSetAttribute(mid_series_kernel_t<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_SMEM_MAX));
+            CKCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mid_series_kernel_t<2>, MID_THREADS, mp.smem));
+            launchable = (long)per_sm * c->sm_count >= (long)mp.Gr * mp.Gc;
+        }
+        if (launchable) {
+            if (const char* e = getenv("DYNEMOL_B200_MID_MAX")) c->mid_auto_max = atoi(e);
+            if (const char* e = getenv("DYNEMOL_B200_MID_L2MB")) c->mid_l2_mb = atof(e);
+            MidParams& P = c->mid_P;
+            memset(&P, 0, sizeof P);
+            P.N = N; P.Gr = mp.Gr; P.Gc = mp.Gc; P.Cnp = mp.Cnp; P.NT = mp.NT; P.ST = mp.ST; P.lslk = mp.lslk; P.lslb = mp.lslb; P.nd = mp.nd;
+            for (int d = 0; d < mp.nd; ++d) P.diag[d] = mp.diag[d];
+            const double bytes = 8.0 * (double)c->ld * N;
+            P.l2_frac = c->mid_l2_mb <= 0.0 ? 0.f : (float)std::min(1.0, c->mid_l2_mb * 1.0e6 / bytes);
+            c->mid_smem = mp.smem;
+            CKC(build_tensor_map_mid(c, mp.WR, mp.TC));
+            const size_t G = (size_t)mp.Gr * mp.Gc;
+            CKC(alloc_zero(&c->mid_pk, 2 * G * mp.R * NQ)); CKC(alloc_zero(&c->mid_pb, 2 * G * mp.Cnp * NQ));
+            CKC(alloc_zero(&c->mid_dscal, 2 * G * 8));
+            CKC(alloc_zero(&c->mid_psi, (size_t)2 * N * NQ));
+            c->mid_fits = true;
+        }
+    }
     if (const char* e = getenv("DYNEMOL_B200_CHAIN")) c->chain_steady = (e[0] != '0');
     if (const char* e = getenv("DYNEMOL_B200_SERIES")) {
-        c->series_kind = !strcmp(e, "term") ? DYB_SERIES_PER_TERM : !strcmp(e, "resident") ? DYB_SERIES_RESIDENT : DYB_SERIES_AUTO;
+        c->series_kind = !strcmp(e, "term") ? DYB_SERIES_PER_TERM : !strcmp(e, "resident") ? DYB_SERIES_RESIDENT
+                       : !strcmp(e, "mid") ? DYB_SERIES_MID : DYB_SERIES_AUTO;
     }
     CKCU(cudaDeviceSynchronize());     // the zero fills above ran on the legacy stream; c->stream is non-blocking
 #undef CKC
@@ -1090,7 +1217,9 @@ int dyb_set_kernel(dyb_ctx* c, int v) {
 
 int dyb_set_series_kernel(dyb_ctx* c, int kind) {
     if (!c) return fail(DYB_EINVAL, "ctx is NULL");
-    if (kind != DYB_SERIES_AUTO && kind != DYB_SERIES_PER_TERM && kind != DYB_SERIES_RESIDENT) return fail(DYB_EINVAL, "unknown series kernel %d", kind);
+    if (kind != DYB_SERIES_AUTO && kind != DYB_SERIES_PER_TERM && kind != DYB_SERIES_RESIDENT && kind != DYB_SERIES_MID)
+        return fail(DYB_EINVAL, "unknown series kernel %d", kind);
+    if (kind == DYB_SERIES_MID && !c->mid_fits) return fail(DYB_EINVAL, "the mid-size series kernel does not apply to this context (N=%d, rows=%d)", c->N, c->M);
     c->series_kind = kind;
     return DYB_OK;
 }
@@ -1100,7 +1229,7 @@ int dyb_get_info(dyb_ctx* c, int64_t* o) {
     memset(o, 0, 16 * sizeof(int64_t));
     o[0] = c->N; o[1] = c->ld; o[2] = c->M; o[3] = c->grid; o[4] = c->T; o[5] = c->n_seg; o[6] = c->sm_count;
     o[7] = TmaSmem::total; o[8] = c->variant; o[9] = c->NP; o[10] = c->TPP; o[11] = c->passes_last; o[12] = c->p2p ? 1 : 0;
-    o[13] = resident_ok(c) ? DYB_SERIES_RESIDENT : DYB_SERIES_PER_TERM;
+    o[13] = resident_ok(c) ? DYB_SERIES_RESIDENT : mid_ok(c, false) ? DYB_SERIES_MID : DYB_SERIES_PER_TERM;
     o[14] = c->res_Gd; o[15] = c->res_Bs;
     return DYB_OK;
 }

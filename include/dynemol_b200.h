@@ -160,6 +160,12 @@ int  dyb_plan(int N, int n_rows, int sm_count, int64_t* out8, int32_t* seg_base,
  * out6 = {grid side, block size, smem column stride, dynamic smem bytes, threads per CTA, fits (0/1)}. */
 int  dyb_resident_plan(int N, int sm_count, int64_t smem_optin_bytes, int64_t* out6);
 
+/* Host-only: blocking of the streamed one-launch series kernel (DYB_SERIES_MID) for an N x N operator: a Gr x Gc grid of
+ * CTAs, CTA (bi, bj) owns rows [bi*R, bi*R+R) x columns [bj*Cnp, bj*Cnp+Cnp).  out12 = {R, tile columns, Gr, Gc, Cnp, tiles
+ * per term, ring stages, log2 gather lanes (ket), log2 gather lanes (bra), number of CTAs whose row and column ranges
+ * intersect, dynamic smem bytes, fits (0/1)}; diag (when non-NULL, >= 160 entries) receives the block indices of those CTAs. */
+int  dyb_mid_plan(int N, int sm_count, int64_t smem_optin_bytes, int64_t* out12, int32_t* diag);
+
 /* Host-only: the tau of every remaining sub-step of the steady loop (Taylor.f:81-126: t += tau*h_bar, a last shorter
  * sub-step when less than one tau is left) assuming every norm test passes -- the schedule the library predicts when it
  * chains the sub-steps of a small operator into one launch.  Returns the number of sub-steps written (<= max_sub). */
@@ -178,12 +184,18 @@ int  dyb_set_kernel(dyb_ctx* ctx, int kernel_variant);
  *   PER_TERM  two launches per term (dual product + fused epilogue, chained by programmatic dependent launch);
  *   RESIDENT  one cooperative launch per series, H' blocked over the shared memories of the SMs for the whole
  *             series (single GPU, N <= ~1800: the QM regions of the Ehrenfest / CSDM examples);
- *   AUTO      RESIDENT when the operator fits, else PER_TERM (default; env DYNEMOL_B200_SERIES=term|resident|auto).
+ *   MID       one cooperative launch per series, H' STREAMED per term by a TMA ring that runs across the terms, one grid
+ *             barrier per term (single GPU, mid-size operators: resident range < N <~ 6000; csrc/mid.cuh).  Replaces the
+ *             per-term GEMV launches and host round trips of Taylor_gpu.cpp:570-600 for the operators whose pass over H'
+ *             (5 ... 40 us) is of the order of the launch overheads;
+ *   AUTO      RESIDENT when the operator fits the shared memories, MID up to DYNEMOL_B200_MID_MAX (default 6144), else
+ *             PER_TERM (default; env DYNEMOL_B200_SERIES=term|resident|mid|auto).
  * (Values 2 and 4 were the round-1 streaming-cooperative and streamed-block kernels: measured slower than PER_TERM
  * everywhere, removed; DESIGN.md keeps the measurements.) */
 #define DYB_SERIES_AUTO     0
 #define DYB_SERIES_PER_TERM 1
 #define DYB_SERIES_RESIDENT 3
+#define DYB_SERIES_MID      5
 int  dyb_set_series_kernel(dyb_ctx* ctx, int kind);
 int  dyb_get_info(dyb_ctx* ctx, int64_t* info16);   /* [0]=N [1]=ld [2]=n_rows [3]=grid [4]=tiles [5]=segments [6]=sm_count [7]=smem_bytes [8]=variant ... [13]=series kernel in effect [14]=resident grid side [15]=resident block size */
 
