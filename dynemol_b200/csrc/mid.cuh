@@ -58,8 +58,15 @@ struct MidParams {
     Ctrl* ctrl;
     const PassParams* passes; int n_steps;
     unsigned long long* gbar;
+    long long* prof;                        // DYB_SERIES_PROF builds: [32][grid][8] clock64 stamps (else null)
     int diag[MID_MAX_DIAG];
 };
+
+#ifdef DYB_SERIES_PROF
+#define DYB_MSTAMP(i) do { if (threadIdx.x == 0 && t < 32) P.prof[((size_t)t * G + blockIdx.x) * 8 + (i)] = clock64(); } while (0)
+#else
+#define DYB_MSTAMP(i) do { } while (0)
+#endif
 
 struct MidSmem {                            // dynamic shared memory carve-up (byte offsets)
     int bars, U, xk, prvk, sumk, xb, prvb, sumb, total;
@@ -193,6 +200,7 @@ mid_series_kernel_t(const __grid_constant__ CUtensorMap tmap, const MidParams P)
             if (t + 1 < P.n_steps) pass_word = reinterpret_cast<const double*>(P.passes + t + 1)[tid];
         }
         const int par = t & 1;
+        DYB_MSTAMP(0);
 
         // ---------------------------------------------------------------- 1. both products of the block, streamed
         {
@@ -236,6 +244,7 @@ mid_series_kernel_t(const __grid_constant__ CUtensorMap tmap, const MidParams P)
                 if (++sc == ST) { sc = 0; phc ^= 1; }
             }
             retire(qc - 1);
+            DYB_MSTAMP(1);
             __syncthreads();                                     // bra partials of all row groups are in U
 
             // bra partial of block column bj from block row bi -> pb[par][bj][bi][.]
@@ -293,8 +302,10 @@ mid_series_kernel_t(const __grid_constant__ CUtensorMap tmap, const MidParams P)
         }
 
         // ---------------------------------------------------------------- 2. the one grid barrier of the term
+        DYB_MSTAMP(2);
         bar_target += G;
         res_grid_barrier(P.gbar, bar_target);
+        DYB_MSTAMP(3);
 
         // ---------------------------------------------------------------- 3. decision on term t-1 (identical in every CTA)
         if (t > 0) {
@@ -328,6 +339,7 @@ mid_series_kernel_t(const __grid_constant__ CUtensorMap tmap, const MidParams P)
             if (tid == 0 && ((sctrl.part[0].latched && !sctrl.part[0].ok) || (sctrl.part[1].latched && !sctrl.part[1].ok))) stop_chain = 1;
         }
 
+        DYB_MSTAMP(4);
         // ---------------------------------------------------------------- 4. gather + recurrence + series sum
         // A gather task = (entry, particle) of one side; 2^lsl lanes split its partials (<= 8 each, fixed order), a lane
         // butterfly adds them up, the first lane applies the update to this CTA's copy of the state.
@@ -419,6 +431,7 @@ mid_series_kernel_t(const __grid_constant__ CUtensorMap tmap, const MidParams P)
             }
         }
         __syncthreads();
+        DYB_MSTAMP(5);
 
         // ---------------------------------------------------------------- 5. scalars of the indices this CTA holds on both sides
         if (diag) {
@@ -451,6 +464,7 @@ mid_series_kernel_t(const __grid_constant__ CUtensorMap tmap, const MidParams P)
             }
             __syncthreads();                                     // the magnitudes in U have been read: the next product may reuse U
         }
+        DYB_MSTAMP(6);
     }
 
     // ---- decision on the last term (one more barrier), unless the series was decided on the way

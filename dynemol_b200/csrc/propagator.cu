@@ -493,9 +493,43 @@ static int run_series_mid(dyb_ctx* c, const std::vector<PassParams>& passes) {
     P.x0k = c->vk[0]; P.x0b = c->vb[0]; P.sum_b = c->sum_b; P.sum_k = c->sum_k;
     P.pk = c->mid_pk; P.pb = c->mid_pb; P.dscal = c->mid_dscal; P.psi_store = c->mid_psi;
     P.ctrl = c->ctrl; P.passes = c->d_passes; P.n_steps = n; P.gbar = c->gbar;
+#ifdef DYB_SERIES_PROF
+    static long long* d_mprof = nullptr;
+    const int mgrid = P.Gr * P.Gc;
+    const size_t n_mprof = (size_t)MAX_SERIES_TERMS * mgrid * 8;
+    if (!d_mprof) CK(cudaMalloc(&d_mprof, (size_t)MAX_SERIES_TERMS * 512 * 8 * 8));
+    CK(cudaMemsetAsync(d_mprof, 0, n_mprof * 8, c->stream));
+    P.prof = d_mprof;
+#else
+    P.prof = nullptr;
+#endif
     void* args[] = {(void*)&c->tmap_mid, (void*)&P};
     CK(cudaLaunchCooperativeKernel((const void*)mid_series_kernel_t<2>, dim3(P.Gr * P.Gc), dim3(MID_THREADS), args, c->mid_smem, c->stream));
     c->launches++;
+#ifdef DYB_SERIES_PROF
+    {   // diagnostic build: mean / max cycles of each phase over CTAs and terms
+        static int calls = 0;
+        if (calls++ % 50 == 1) {
+            std::vector<long long> h(n_mprof);
+            CK(cudaStreamSynchronize(c->stream));
+            CK(cudaMemcpy(h.data(), d_mprof, n_mprof * 8, cudaMemcpyDeviceToHost));
+            const char* name[7] = {"product", "reduce+store", "barrier", "decide", "gather", "scalars", "loop-gap"};
+            double mean[7] = {0}, mx[7] = {0};
+            const int nt = std::min(n, MAX_SERIES_TERMS);
+            for (int t = 1; t + 1 < nt; ++t) for (int b = 0; b < mgrid; ++b) {
+                const long long* q = &h[((size_t)t * mgrid + b) * 8];
+                for (int i = 0; i < 7; ++i) {
+                    const long long nx = (i < 6) ? q[i + 1] : h[((size_t)(t + 1) * mgrid + b) * 8];
+                    const double d = double(nx - q[i]);
+                    mean[i] += d; mx[i] = std::max(mx[i], d);
+                }
+            }
+            fprintf(stderr, "mid_prof N=%d grid=%dx%d Cnp=%d NT=%d ST=%d terms=%d:", c->N, P.Gr, P.Gc, P.Cnp, P.NT, P.ST, n);
+            for (int i = 0; i < 7; ++i) fprintf(stderr, "  %s mean %.0f max %.0f cyc;", name[i], mean[i] / ((double)std::max(1, nt - 2) * mgrid), mx[i]);
+            fprintf(stderr, "\n");
+        }
+    }
+#endif
     return DYB_OK;
 }
 
