@@ -153,12 +153,9 @@ def resident_plan(N: int, sm_count: int = 148, smem_optin: int = 232448) -> dict
 def mid_plan(N: int, sm_count: int = 148, smem_optin: int = 232448) -> dict:
     """Blocking of the streamed one-launch series kernel for mid-size operators (csrc/mid.cuh); host arithmetic only."""
     out = (C.c_int64 * 12)()
-    diag = (C.c_int32 * 160)()
-    _check(lib.dyb_mid_plan(C.c_int(N), C.c_int(sm_count), C.c_int64(smem_optin), out, diag))
-    d = dict(zip(["block_rows", "tile_cols", "grid_rows", "grid_cols", "block_cols", "tiles_per_term", "stages", "log2_lanes_ket",
-                  "log2_lanes_bra", "n_diag", "smem_bytes", "fits"], [int(v) for v in out]))
-    d["diag"] = [int(diag[i]) for i in range(min(d["n_diag"], 160))]
-    return d
+    _check(lib.dyb_mid_plan(C.c_int(N), C.c_int(sm_count), C.c_int64(smem_optin), out))
+    return dict(zip(["block_rows", "tile_cols", "grid_rows", "grid_cols", "block_cols", "tiles_per_term", "stages",
+                     "owned", "owners", "collect_words", "smem_bytes", "fits"], [int(v) for v in out]))
 
 
 def steady_schedule(t: float, t_max: float, tau: float, max_sub: int = 4096) -> np.ndarray:

@@ -1,4 +1,5 @@
-// mid.cuh -- mid-size operators (roughly 1800 < N < 6000): ONE cooperative launch per series, H' STREAMED per term.
+// mid.cuh -- mid-size operators (roughly 1800 < N < 7000): ONE cooperative launch per series, H' STREAMED per term,
+// NO grid barrier: the CTAs talk through epoch-tagged words in the L2.
 //
 // Between the shared-memory-resident kernel (resident.cuh, N <= 1824) and the bandwidth regime of the two-launch path
 // (matvec.cuh + epilogue.cuh, N >~ 8000) a term is neither: H' (27 ... 300 MB) sits in or near the 126 MB L2, one pass over
@@ -10,17 +11,25 @@
 //   * a Gr x Gc grid of CTAs (<= one per SM); CTA (bi, bj) owns the block rows [bi*R, bi*R+R) x cols [bj*Cn, bj*Cn+Cn) of
 //     H' for the whole series.  R = 256*WR rows, Cn = a multiple of the tile width;
 //   * a TMA ring (cp.async.bulk.tensor.3d, mbarrier full/empty pairs) that streams the block as tiles of R rows x TC
-//     columns (32 KiB) and RUNS ACROSS THE TERMS: H' does not change, so the first tiles of term t+1 are in flight while the
-//     grid barrier and the gather of term t run; the L2 policy keeps as much of H' as fits resident (evict_last on a
-//     fraction of the lines, evict_first on the rest), so that most of a pass is served by the L2, not by HBM;
+//     columns (32 KiB) and RUNS ACROSS THE TERMS: H' does not change, so the first tiles of term t+1 are in flight while
+//     the exchange of term t runs;
 //   * the tile engine of the dual product (matvec.cuh): 8 rows x 2 columns per thread and tile, ket sums in registers,
-//     bra sums by a lane butterfly (transpose_reduce) -- one pass serves H'x_ket and H'^T x_bra of electron and hole;
-//   * ONE grid barrier per term and the redundant-gather protocol of resident.cuh: after the barrier every CTA rebuilds,
-//     in the same order (bit-identical copies), exactly the vector entries it multiplies next -- x_ket on its columns from
-//     the Gc ket partials of that block row, x_bra on its rows from the Gr bra partials of that block column -- and applies
-//     the recurrence / series sum to its copy of the state (x, x_prev, sum: shared memory);
-//   * the convergence scalars come from the CTAs whose row and column ranges intersect (they hold bra AND ket sums of
-//     those indices) and are consumed one term late, with the decision code of the other two paths (decide_particle).
+//     bra sums by a lane butterfly (transpose_reduce) that is software-pipelined one tile behind the FMAs -- one pass
+//     serves H'x_ket and H'^T x_bra of electron and hole;
+//   * an OWNER-REDUCE exchange without any grid-wide barrier.  Every index g has one owner CTA (g / E).  Per term a CTA
+//       1. publishes its partial products (R ket entries of its block row, Cn bra entries of its block column),
+//       2. as OWNER: collects the Gc ket partials and the Gr bra partials of its E indices, applies the recurrence and
+//          the series sum to ITS copy of the state (x, x_prev, sum, start vector: shared memory, 2 x E entries), and
+//          publishes the new vector entries and its 8 convergence scalars,
+//       3. as CONSUMER: collects the R + Cn new entries it multiplies next.
+//     Every published double travels as a 16-byte word {lo32, epoch, hi32, epoch} written and read with ONE 128-bit
+//     relaxed access whose two 64-bit halves are single-copy atomic (the LL protocol of NCCL): a reader polls the word
+//     itself until both tags carry the epoch of the term -- no fence, no flag, no counter.  Epochs grow across launches,
+//     buffers are double-buffered by term parity (scalars: four deep); the data dependencies of the recurrence guarantee
+//     that a slot is never overwritten before its readers are done (a CTA needs x(t+2) from exactly the owners that read
+//     its partials of term t);
+//   * the decision on term t-1 (decide_particle, the code of the other two paths) is taken by every CTA, identically,
+//     from the owners' scalars before term t is applied: a latched particle skips the update.
 //
 // Same PassParams / Ctrl contract as resident.cuh: propagate_series does not know which kernel ran.  Chained steady
 // sub-steps (PartPass::begin / chain) are supported; the reference-GPU term test (PartPass::test_gpu) is not -- those parity
@@ -29,7 +38,6 @@
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "matvec.cuh"
-#include "resident.cuh"
 
 namespace dyb {
 
@@ -40,95 +48,369 @@ constexpr int MID_MPT         = 4;
 constexpr int MID_CPW         = 2;          // columns per warp and tile
 constexpr int MID_STAGE_BYTES = 32768;      // R x TC x 8 B with R*TC = 4096 for every WR
 constexpr int MID_MAX_ST      = 5;
-constexpr int MID_U_BYTES     = 32768;      // union region: bra partials of the row groups / ket tree reduction / term magnitudes
-constexpr int MID_MAX_DIAG    = 160;
-constexpr int MID_GB          = 4;          // gather: slots a thread keeps in flight
+constexpr int MID_U_BYTES     = 32768;      // union region: bra partials of the row groups / ket tree reduction
+constexpr int MID_MAX_E       = 64;         // indices an owner may hold
+constexpr int MID_CW          = 12;         // owner: words a thread has in flight per collect pass
+constexpr int MID_XU          = 16;         // consumer: words per thread ((R + Cn) * 4 <= 256 * 16)
+constexpr int MID_SCU         = 10;         // decision: owners per thread (16 * 10 >= owner CTAs)
 constexpr int MID_SMEM_MAX    = 227 * 1024 - 2048;
+#ifndef DYB_LL_SLEEP
+#define DYB_LL_SLEEP 300                    // ns between two polling rounds of a thread
+#endif
+constexpr long long MID_SPIN_LIMIT = 1ll << 22;     // polls before a reader gives up (a word that never arrives must end in a
+                                                    // trap, not in a hung GPU)
 
 struct MidParams {
     int N, Gr, Gc, Cnp, NT, ST;             // grid, block width (multiple of TC), tiles per term, ring depth
-    int lslk, lslb;                         // log2 of the lanes that share a gather task (ket: Gc partials, bra: Gr partials)
-    int nd;                                 // CTAs whose row and column ranges intersect, in blockIdx order
+    int E, n_own;                           // indices per owner CTA (ceil(N / grid)), CTAs that own at least one index
+    unsigned epoch0;                        // the epoch of this launch's term t is epoch0 + t + 1
     float l2_frac;                          // fraction of the H' lines loaded with L2::evict_last (0: plain evict_first stream)
     const double* x0k; const double* x0b;   // starting vectors (quads), written by series_init_kernel
     double* sum_b; double* sum_k;           // in: series sums at the start; out: at the latch / end of the series
-    double* pk; double* pb;                 // [2][Gr][Gc][R][NQ] / [2][Gc][Gr][Cnp][NQ] partial products (parity of the term first)
-    double* dscal;                          // [2][grid][8] scalars of the intersecting CTAs
-    double* psi_store;                      // [2][N][NQ] start vector of the sub-step in progress (ket, bra), needed after a failure
+    ulonglong2* pk; ulonglong2* pb;         // [2][Gr][Gc][R][NQ] / [2][Gc][Gr][Cnp][NQ] tagged partial products (term parity first)
+    ulonglong2* xx;                         // [2][2][N][NQ] tagged new vector entries (parity, side: 0 ket / 1 bra)
+    ulonglong2* sc;                         // [4][grid][8] tagged scalars of the owners (term mod 4)
     Ctrl* ctrl;
     const PassParams* passes; int n_steps;
-    unsigned long long* gbar;
     long long* prof;                        // DYB_SERIES_PROF builds: [32][grid][8] clock64 stamps (else null)
-    int diag[MID_MAX_DIAG];
 };
 
 #ifdef DYB_SERIES_PROF
-#define DYB_MSTAMP(i) do { if (threadIdx.x == 0 && t < 32) P.prof[((size_t)t * G + blockIdx.x) * 8 + (i)] = clock64(); } while (0)
+#define DYB_MSTAMP(i) do { if (threadIdx.x == 0 && t < 32) P.prof[((size_t)t * G + blockIdx.x) * 16 + (i)] = clock64(); } while (0)
+#define DYB_MSTAMP_T(i, thr, tt) do { if (threadIdx.x == (thr) && (tt) < 32 && (tt) >= 0) P.prof[((size_t)(tt) * G + blockIdx.x) * 16 + (i)] = clock64(); } while (0)
 #else
 #define DYB_MSTAMP(i) do { } while (0)
+#define DYB_MSTAMP_T(i, thr, tt) do { } while (0)
 #endif
 
 struct MidSmem {                            // dynamic shared memory carve-up (byte offsets)
-    int bars, U, xk, prvk, sumk, xb, prvb, sumb, total;
-    __host__ __device__ MidSmem(int ST, int R, int Cnp) {
+    int bars, U, xk, xb, own, total;
+    __host__ __device__ MidSmem(int ST, int R, int Cnp, int E, int Gsum) {     // Gsum = Gr + Gc
         bars = ST * MID_STAGE_BYTES;
-        U    = bars + 128;
-        xk   = U + MID_U_BYTES;
-        prvk = xk + Cnp * 32;  sumk = prvk + Cnp * 32;
-        xb   = sumk + Cnp * 32;
-        prvb = xb + R * 32;    sumb = prvb + R * 32;
-        total = sumb + R * 32;
+        U    = bars + 128;                  // union region; also holds the (Gr + Gc) * E * 4 partials an owner collects
+        const int ub = Gsum * E * NQ * 8;
+        xk   = U + (ub > MID_U_BYTES ? (ub + 127) & ~127 : MID_U_BYTES);
+        xb   = xk + Cnp * 32;               // [Cnp][NQ] then [R][NQ]: contiguous (the consumer fills both as one array)
+        own  = xb + R * 32;                 // owner state: cur, prev, sum, start [2 sides][E][NQ] + magnitudes [2][E][2]
+        total = own + E * (4 * 2 * NQ * 8 + 2 * 2 * 8);
     }
 };
 
-// 64 FMAs of one column: the thread's 8 rows against the 4 reals of x_ket (-> acc) and of x_bra (-> p)
-__device__ __forceinline__ void mid_fma_column(double (&acc)[MID_MPT][2][NQ], const double (&xb)[MID_MPT][2][NQ],
-                                               const double2 (&h)[MID_MPT], const double (&xk)[NQ], double* p) {
-    double p1[NQ];
+// ---- epoch-tagged words: one double per 16 B, {lo32 | epoch << 32, hi32 | epoch << 32}
+__device__ __forceinline__ void ll_store(ulonglong2* p, double v, unsigned ep) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v), e = (unsigned long long)ep << 32;
+    asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"((b & 0xffffffffull) | e), "l"((b >> 32) | e) : "memory");
+}
+__device__ __forceinline__ ulonglong2 ll_load(const ulonglong2* p) {
+    ulonglong2 r;
+    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void ll_load2(const ulonglong2* p, unsigned long long& x, unsigned long long& y) {
+    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "l"(p) : "memory");
+}
+__device__ __forceinline__ bool ll_valid(const ulonglong2& r, unsigned ep) {
+    return (unsigned)(r.x >> 32) == ep && (unsigned)(r.y >> 32) == ep;
+}
+__device__ __forceinline__ double ll_value(const ulonglong2& r) {
+    return __longlong_as_double((long long)((r.x & 0xffffffffull) | (r.y << 32)));
+}
+// Batched polling.  The words whose bit is set in `pend` (bit i: address ADDR(i)) are requested TOGETHER, tested, and the
+// missing ones requested again together -- a round costs one L2 round trip whatever the number of words; OUT(i, value) consumes
+// word i as soon as it is valid.  A macro on purpose: the 16-byte words must live in REGISTERS (an array that ends up in local
+// memory -- lambdas / references did that -- puts a store behind every load and serialises them, one round trip each).
+#define DYB_LL_POLL(NW, pend, ep_, ADDR, OUT)                                                                     \
+    do {                                                                                                          \
+        for (long long it_ = 0;; ++it_) {                                                                         \
+            unsigned long long rx_[NW], ry_[NW];                                                                  \
+            _Pragma("unroll") for (int i = 0; i < (NW); ++i) {                                                    \
+                rx_[i] = 0ull; ry_[i] = 0ull;                                                                     \
+                if (((pend) >> i) & 1u) ll_load2(ADDR(i), rx_[i], ry_[i]);                                        \
+            }                                                                                                     \
+            _Pragma("unroll") for (int i = 0; i < (NW); ++i)                                                      \
+                if ((((pend) >> i) & 1u) && (unsigned)(rx_[i] >> 32) == (ep_) && (unsigned)(ry_[i] >> 32) == (ep_)) { \
+                    OUT(i, __longlong_as_double((long long)((rx_[i] & 0xffffffffull) | (ry_[i] << 32))));         \
+                    (pend) &= ~(1u << i);                                                                         \
+                }                                                                                                 \
+            if (!(pend)) break;                                                                                   \
+            if (it_ > MID_SPIN_LIMIT) __trap();                                                                   \
+            if (DYB_LL_SLEEP > 0) __nanosleep(DYB_LL_SLEEP);                                                      \
+        }                                                                                                         \
+    } while (0)
+
+// 32 FMAs of half a column: rows of m = M0, M0 + 1 against the 4 reals of x_ket (-> acc) and of x_bra (-> p, p1)
+template <int M0>
+__device__ __forceinline__ void mid_fma_half(double (&acc)[MID_MPT][2][NQ], const double (&xb)[MID_MPT][2][NQ],
+                                             const double2 (&h)[MID_MPT], const double (&xk)[NQ], double (&p)[NQ], double (&p1)[NQ]) {
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) { p[q] = h[0].x * xb[0][0][q]; p1[q] = h[0].y * xb[0][1][q]; }
-#pragma unroll
-    for (int m = 0; m < MID_MPT; ++m) {
+    for (int m = M0; m < M0 + 2; ++m) {
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
             acc[m][0][q] = fma(h[m].x, xk[q], acc[m][0][q]);
             acc[m][1][q] = fma(h[m].y, xk[q], acc[m][1][q]);
-            if (m > 0) { p[q] = fma(h[m].x, xb[m][0][q], p[q]); p1[q] = fma(h[m].y, xb[m][1][q], p1[q]); }
+            if (m == 0) { p[q] = h[m].x * xb[m][0][q]; p1[q] = h[m].y * xb[m][1][q]; }
+            else        { p[q] = fma(h[m].x, xb[m][0][q], p[q]); p1[q] = fma(h[m].y, xb[m][1][q], p1[q]); }
         }
     }
+}
+
+// static shared state of a CTA (one instance in the kernel; the exchange functions get a pointer)
+struct MidShared {
+    Ctrl       sctrl;
+    PassParams spass[2];
+    double     wsc[4][8];
+    int        stop_chain;                  // a particle failed a chained sub-step: the other one stops at its next sub-step
+};                                          // boundary so that both resume together
+
+// The exchange of a term lives in functions that are NOT inlined into the kernel: the tile engine keeps ~230 registers busy,
+// and inlined next to it ptxas parked the 16-byte words of the polling loops in local memory (a store behind every load =
+// the loads of a thread serialised, one L2 round trip each: 10 000 cycles to request 16 words).  On their own these functions
+// need few registers and every polling round is one batch of independent loads.
+
+// Decision on term td: scalars of all owners, fixed combination order, identical in every CTA (decide_particle = the code
+// of the two other paths, Taylor.f:194-207 / :102-105).
+__device__ __noinline__ void mid_decide(const MidParams& P, MidShared* sh, int td, bool allow_chain) {
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int G = P.Gr * P.Gc;
+    if (tid >= 128) {
+        const int j = tid - 128, s = j & 7, ob = j >> 3;
+        const unsigned epd = P.epoch0 + td + 1;
+        const ulonglong2* src = P.sc + ((size_t)(td & 3) * G) * 8 + s;
+        unsigned need = 0;
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) p[q] += p1[q];
+        for (int i = 0; i < MID_SCU; ++i) if (ob + 16 * i < P.n_own) need |= 1u << i;
+        double sv[MID_SCU];
+#define DYB_SC_ADDR(i) (src + (size_t)(ob + 16 * (i)) * 8)
+#define DYB_SC_OUT(i, v) sv[i] = (v)
+        unsigned pend = need;
+        DYB_LL_POLL(MID_SCU, pend, epd, DYB_SC_ADDR, DYB_SC_OUT);
+#undef DYB_SC_ADDR
+#undef DYB_SC_OUT
+        double a = 0.0;
+#pragma unroll
+        for (int i = 0; i < MID_SCU; ++i)
+            if ((need >> i) & 1u) a = ((s & 3) < 2) ? fmax(a, sv[i]) : a + sv[i];
+#pragma unroll
+        for (int off = 8; off < 32; off <<= 1) {
+            const double o = __shfl_xor_sync(0xffffffffu, a, off);
+            a = ((s & 3) < 2) ? fmax(a, o) : a + o;
+        }
+        if (lane < 8) sh->wsc[w - 4][lane] = a;
+    }
+    __syncthreads();
+    if (tid == 0 || tid == 32) {
+        const int p = tid >> 5;
+        double fin[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int s = 4 * p + q;
+            fin[q] = (q < 2) ? fmax(fmax(sh->wsc[0][s], sh->wsc[1][s]), fmax(sh->wsc[2][s], sh->wsc[3][s]))
+                             : (sh->wsc[0][s] + sh->wsc[1][s]) + (sh->wsc[2][s] + sh->wsc[3][s]);
+        }
+        decide_particle(sh->sctrl.part[p], sh->spass[td & 1].part[p], fin, allow_chain);
+    }
+    __syncthreads();
+}
+
+// Owner: collect the partials of the owned indices into val[] (shared memory).
+// Word w = k * E4 + e * 4 + q: source k (0 .. Gc-1: ket partial of block column k; Gc .. Gc+Gr-1: bra partial of block row
+// k - Gc), owned index e, real q.  Thread tid takes the words tid + 256 j, MID_CW per pass, all in flight at once.
+template <int R>
+__device__ __noinline__ void mid_collect(const MidParams& P, double* val, int t) {
+    const int tid = threadIdx.x;
+    const int Gr = P.Gr, Gc = P.Gc, Cnp = P.Cnp, N = P.N;
+    const int E4 = P.E * NQ, W = (Gc + Gr) * E4, o0 = blockIdx.x * P.E;
+    const int par = t & 1;
+    const unsigned ep = P.epoch0 + t + 1;
+    const int ckstep = MID_THREADS / E4, cremstep = MID_THREADS - ckstep * E4;
+    const int obc0 = o0 / Cnp, obc_next = (obc0 + 1) * Cnp;     // block column of the first owned index, first index of the next one
+    const ulonglong2* pkb = P.pk + (size_t)par * Gr * Gc * R * NQ;
+    const ulonglong2* pbb = P.pb + (size_t)par * Gc * Gr * Cnp * NQ;
+    int k = tid / E4, rem = tid - k * E4;                       // source and (e, q) of the thread's next word
+    for (int w0 = 0; w0 < W; w0 += MID_THREADS * MID_CW) {
+        int off[MID_CW];                                         // word offset from pkb (ket, >= 0) or pbb (bra, stored as ~offset)
+        unsigned pend = 0;
+#pragma unroll
+        for (int j = 0; j < MID_CW; ++j) {
+            const int wj = w0 + j * MID_THREADS + tid;
+            const int g = o0 + (rem >> 2), q = rem & 3;
+            off[j] = 0;
+            if (wj < W && g < N) {
+                pend |= 1u << j;
+                if (k < Gc) {                                    // ket entry g: block row g / R, partial of block column k
+                    const int br = g / R, rr = g - br * R;
+                    off[j] = ((br * Gc + k) * R + rr) * NQ + q;
+                } else {                                         // bra entry g: block column bc (at most two per owner), partial of block row k - Gc
+                    const int bc = obc0 + (g >= obc_next ? 1 : 0), cc = g - bc * Cnp;
+                    off[j] = ~(((bc * Gr + (k - Gc)) * Cnp + cc) * NQ + q);
+                }
+            }
+            k += ckstep; rem += cremstep;
+            if (rem >= E4) { rem -= E4; ++k; }
+        }
+#define DYB_CO_ADDR(j) (off[j] >= 0 ? pkb + off[j] : pbb + ~off[j])
+#define DYB_CO_OUT(j, v) val[w0 + (j) * MID_THREADS + tid] = (v)
+        DYB_LL_POLL(MID_CW, pend, ep, DYB_CO_ADDR, DYB_CO_OUT);
+#undef DYB_CO_ADDR
+#undef DYB_CO_OUT
+    }
+}
+
+// Owner: sums of the collected partials (fixed order), recurrence, series sum, publication of the new entries and of the
+// convergence scalars.  own = owner state in shared memory: cur, prev, sum, start [2 sides][E][NQ] + magnitudes [2][E][2].
+__device__ __noinline__ void mid_update(const MidParams& P, MidShared* sh, const double* val, double* own, int t) {
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int Gr = P.Gr, Gc = P.Gc, N = P.N, E = P.E, G = Gr * Gc;
+    const int E4 = E * NQ, o0 = blockIdx.x * E, par = t & 1;
+    const unsigned ep = P.epoch0 + t + 1;
+    double* ocur = own;
+    double* oprv = ocur + 2 * E * NQ;
+    double* osum = oprv + 2 * E * NQ;
+    double* opsi = osum + 2 * E * NQ;
+    double* omag = opsi + 2 * E * NQ;
+    // task = (side, e, q); the two reals of a complex value sit in neighbouring lanes
+#pragma unroll 1
+    for (int task = tid; task < ((2 * E4 + 31) & ~31); task += MID_THREADS) {
+        const int side = task >= E4 ? 1 : 0;
+        const int eq = task - side * E4, e = eq >> 2, q = eq & 3;
+        const bool ok = task < 2 * E4 && o0 + e < N;
+        double hx = 0.0;
+        if (ok) {
+            const double* vp = val + (side ? Gc * E4 : 0) + eq;
+            const int np = side ? Gr : Gc;
+            for (int kk = 0; kk < np; ++kk) hx += vp[(size_t)kk * E4];          // fixed order
+        }
+        const double ho = __shfl_xor_sync(0xffffffffu, hx, 1);  // the other real of the complex value
+        const int p = q >> 1, cmp = q & 1;
+        const Cx hc = cmp ? Cx{ho, hx} : Cx{hx, ho};
+        const size_t o = ((size_t)side * E + e) * NQ + 2 * p;
+        double xnew = 0.0, n_cur = 0.0, n_prv = 0.0, n_sum = 0.0, n_psi = 0.0, mag = 0.0;
+        bool upd = false, beg = false;
+        if (ok) {
+            const PartPass& pa = sh->spass[par].part[p];
+            double2 cur = *reinterpret_cast<const double2*>(ocur + o);
+            xnew = cmp ? cur.y : cur.x;
+            if (pa.active && !sh->sctrl.part[p].latched) {
+                double2 sum = *reinterpret_cast<const double2*>(osum + o);
+                if (pa.begin) {                                  // next steady sub-step: adopt the previous sum (Taylor.f:105,:83-86);
+                    beg = true;                                  // hx was computed from it (x of the chain term)
+                    n_psi = cmp ? sum.y : sum.x;
+                    cur = sum;
+                    const Cx s0 = cmul({pa.s_re, pa.s_im}, {sum.x, sum.y});
+                    sum = make_double2(s0.re, s0.im);
+                }
+                Cx y = cmul({pa.alpha_re, pa.alpha_im}, hc);
+                if (pa.three_term) {
+                    const Cx bc = cmul({pa.beta_re, pa.beta_im}, {cur.x, cur.y});
+                    y.re += bc.re; y.im += bc.im;
+                    if (pa.gamma != 0.0) {
+                        const double2 prv = *reinterpret_cast<const double2*>(oprv + o);
+                        y.re += pa.gamma * prv.x; y.im += pa.gamma * prv.y;
+                    }
+                }
+                Cx tt = y;
+                if (pa.scale_term) tt = cmul({pa.c_re, pa.c_im}, y);
+                const double nw_re = sum.x + tt.re, nw_im = sum.y + tt.im;
+                const double dx = nw_re - sum.x, dy = nw_im - sum.y;
+                mag = dx * dx + dy * dy;                         // |new - old|^2 (isConverged, Taylor.f:290-303); root after the max
+                upd = true;
+                n_prv = cmp ? cur.y : cur.x;
+                // what the next product multiplies: the new vector, or (speculatively) the sum the next sub-step starts from
+                n_cur = pa.chain ? (cmp ? nw_im : nw_re) : (cmp ? y.im : y.re);
+                n_sum = cmp ? nw_im : nw_re;
+                xnew = n_cur;
+            }
+        }
+        __syncwarp();                                            // both lanes of a complex value have read the old state
+        if (ok) {
+            if (upd) {
+                oprv[o + cmp] = n_prv; ocur[o + cmp] = n_cur; osum[o + cmp] = n_sum;
+                if (beg) opsi[o + cmp] = n_psi;
+            }
+            if (cmp == 0) omag[((size_t)side * E + e) * 2 + p] = mag;
+            ll_store(P.xx + (((size_t)((t + 1) & 1) * 2 + side) * N + (o0 + e)) * NQ + q, xnew, ep);
+        }
+    }
+    __syncthreads();
+
+    // scalars of the owned indices
+    if (w == 0 && blockIdx.x < P.n_own) {
+        double v[4] = {0.0, 0.0, 0.0, 0.0};                      // max_b, max_k, dot_re, dot_im of particle (lane & 1)
+        for (int idx = lane; idx < E * 2; idx += 32) {
+            const int e = idx >> 1, p = idx & 1;
+            if (o0 + e < N) {
+                const double2 k = *reinterpret_cast<const double2*>(osum + (size_t)e * NQ + 2 * p);
+                const double2 b = *reinterpret_cast<const double2*>(osum + ((size_t)E + e) * NQ + 2 * p);
+                v[0] = fmax(v[0], omag[((size_t)E + e) * 2 + p]); v[1] = fmax(v[1], omag[(size_t)e * 2 + p]);
+                v[2] += b.x * k.x + b.y * k.y;                   // conj(bra) * ket
+                v[3] += b.x * k.y - b.y * k.x;
+            }
+        }
+#pragma unroll
+        for (int off = 2; off < 32; off <<= 1) {                 // lanes of equal particle (lane bit 0)
+            v[0] = fmax(v[0], __shfl_xor_sync(0xffffffffu, v[0], off)); v[1] = fmax(v[1], __shfl_xor_sync(0xffffffffu, v[1], off));
+            v[2] += __shfl_xor_sync(0xffffffffu, v[2], off);            v[3] += __shfl_xor_sync(0xffffffffu, v[3], off);
+        }
+        if (lane < 2) {
+            ulonglong2* dst = P.sc + ((size_t)(t & 3) * G + blockIdx.x) * 8 + lane * 4;
+            ll_store(dst + 0, sqrt(v[0]), ep); ll_store(dst + 1, sqrt(v[1]), ep);
+            ll_store(dst + 2, v[2], ep);       ll_store(dst + 3, v[3], ep);
+        }
+    }
+}
+
+// Consumer: the Cnp ket entries and the R bra entries the next product multiplies -> sx (sxk [Cnp][NQ] then sxb [R][NQ],
+// contiguous: word wi of the list is double wi of that array)
+template <int R>
+__device__ __noinline__ void mid_consume(const MidParams& P, double* sx, int t) {
+    const int tid = threadIdx.x;
+    const int Cnp = P.Cnp, N = P.N;
+    const int bi = blockIdx.x / P.Gc, bj = blockIdx.x % P.Gc;
+    const int row0 = bi * R, col0 = bj * Cnp;
+    const unsigned ep = P.epoch0 + t + 1;
+    const ulonglong2* xk_src = P.xx + (((size_t)((t + 1) & 1) * 2 + 0) * N + col0) * NQ;
+    const ulonglong2* xb_src = P.xx + (((size_t)((t + 1) & 1) * 2 + 1) * N + row0) * NQ - (size_t)Cnp * NQ;    // indexed by wi
+    const int nwk = min(Cnp, max(0, N - col0)) * NQ, nwb = min(R, max(0, N - row0)) * NQ;
+    unsigned pend = 0;
+#pragma unroll
+    for (int u = 0; u < MID_XU; ++u) {
+        const int wi = tid + u * MID_THREADS;
+        if (wi < Cnp * NQ ? wi < nwk : wi - Cnp * NQ < nwb) pend |= 1u << u;
+    }
+#define DYB_X_ADDR(u) (((tid + (u) * MID_THREADS) < Cnp * NQ ? xk_src : xb_src) + (tid + (u) * MID_THREADS))
+#define DYB_X_OUT(u, v) sx[tid + (u) * MID_THREADS] = (v)
+    DYB_LL_POLL(MID_XU, pend, ep, DYB_X_ADDR, DYB_X_OUT);
+#undef DYB_X_ADDR
+#undef DYB_X_OUT
 }
 
 template <int WR>        // row groups of 256 rows per CTA; WC = 8 / WR column groups
 __global__ void __launch_bounds__(MID_THREADS, 1)
-mid_series_kernel_t(const __grid_constant__ CUtensorMap tmap, const MidParams P)
+mid_series_kernel_t(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MidParams P)
 {
     constexpr int WC = MID_WARPS / WR, TC = WC * MID_CPW, R = WR * MID_SUB;
     static_assert(R * TC * 8 == MID_STAGE_BYTES, "stage size");
     extern __shared__ __align__(128) uint8_t msm[];
-    const MidSmem L(P.ST, R, P.Cnp);
+    const MidSmem L(P.ST, R, P.Cnp, P.E, P.Gr + P.Gc);
     uint64_t* bar_full  = reinterpret_cast<uint64_t*>(msm + L.bars);
     uint64_t* bar_empty = bar_full + 8;
     double* U    = reinterpret_cast<double*>(msm + L.U);
     double* sxk  = reinterpret_cast<double*>(msm + L.xk);
     double* sxb  = reinterpret_cast<double*>(msm + L.xb);
-    __shared__ Ctrl       sctrl;
-    __shared__ PassParams spass[2];
-    __shared__ double     fin[8];
-    __shared__ double     wred[MID_WARPS][8];
-    __shared__ int        stop_chain;
+    double* ocur = reinterpret_cast<double*>(msm + L.own);     // [side][E][NQ]
+    __shared__ MidShared sh;
 
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int wr = w / WC, wc = w % WC;
-    const int Gr = P.Gr, Gc = P.Gc, Cnp = P.Cnp, NT = P.NT, ST = P.ST, N = P.N;
+    const int Gr = P.Gr, Gc = P.Gc, Cnp = P.Cnp, NT = P.NT, ST = P.ST, N = P.N, E = P.E;
     const int G = Gr * Gc;
     const int bi = blockIdx.x / Gc, bj = blockIdx.x % Gc;
     const int row0 = bi * R, col0 = bj * Cnp;
+    const int o0 = blockIdx.x * E;                             // first owned index
     const int total_tiles = P.n_steps * NT;
-    // indices whose bra AND ket entries this CTA holds
-    const int i0 = max(row0, col0), i1 = min(min(row0 + R, col0 + Cnp), N);
-    const bool diag = i0 < i1;
+    double* oprv = ocur + 2 * E * NQ;
+    double* osum = oprv + 2 * E * NQ;
+    double* opsi = osum + 2 * E * NQ;                          // start vector of the sub-step in progress (handed back after a failure)
 
     uint64_t policy;
     if (P.l2_frac > 0.f) asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(policy) : "f"(P.l2_frac));
@@ -145,36 +427,42 @@ mid_series_kernel_t(const __grid_constant__ CUtensorMap tmap, const MidParams P)
         for (int s = 0; s < ST; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], MID_WARPS); }
         fence_barrier_init();
         for (int q = 0; q < ST && q < total_tiles; ++q) issue(q, q % NT);
-        sctrl = *P.ctrl;
-        stop_chain = 0;
+        sh.sctrl = *P.ctrl;
+        sh.stop_chain = 0;
     }
 
-    // ---- this CTA's copy of the state: x (= cur), x_prev, sum for its Cnp ket entries and its R bra entries
+    // ---- consumer copy of x for the Cnp ket entries and the R bra entries this CTA multiplies
     for (int f = tid; f < (Cnp + R) * 2; f += MID_THREADS) {
         const int side = f >= Cnp * 2;
         const int ff = side ? f - Cnp * 2 : f;
-        const int e = ff >> 1, p = ff & 1;
-        const int g = (side ? row0 : col0) + e;
+        const int g = (side ? row0 : col0) + (ff >> 1);
+        double2 cur = make_double2(0.0, 0.0);
+        if (g < N) cur = *reinterpret_cast<const double2*>((side ? P.x0b : P.x0k) + (size_t)g * NQ + 2 * (ff & 1));
+        *reinterpret_cast<double2*>((side ? sxb : sxk) + (size_t)ff * 2) = cur;
+    }
+    // ---- owner copy of the state of the E indices this CTA owns
+    for (int f = tid; f < 2 * E * 2; f += MID_THREADS) {
+        const int side = f >= E * 2;
+        const int ff = side ? f - E * 2 : f;
+        const int g = o0 + (ff >> 1);
         double2 cur = make_double2(0.0, 0.0), sum = cur;
         if (g < N) {
-            cur = *reinterpret_cast<const double2*>((side ? P.x0b : P.x0k) + (size_t)g * NQ + 2 * p);
-            sum = *reinterpret_cast<const double2*>((side ? P.sum_b : P.sum_k) + (size_t)g * NQ + 2 * p);
-            if (g >= i0 && g < i1) __stcg(reinterpret_cast<double2*>(P.psi_store + ((size_t)side * N + g) * NQ + 2 * p), cur);
+            cur = *reinterpret_cast<const double2*>((side ? P.x0b : P.x0k) + (size_t)g * NQ + 2 * (ff & 1));
+            sum = *reinterpret_cast<const double2*>((side ? P.sum_b : P.sum_k) + (size_t)g * NQ + 2 * (ff & 1));
         }
-        double* st = reinterpret_cast<double*>(msm + (side ? L.xb : L.xk)) + (size_t)e * NQ + 2 * p;
-        const int n_e = side ? R : Cnp;
-        *reinterpret_cast<double2*>(st) = cur;
-        *reinterpret_cast<double2*>(st + (size_t)n_e * NQ) = make_double2(0.0, 0.0);
-        *reinterpret_cast<double2*>(st + (size_t)2 * n_e * NQ) = sum;
+        const size_t o = (size_t)side * E * NQ + (size_t)ff * 2;
+        *reinterpret_cast<double2*>(ocur + o) = cur;
+        *reinterpret_cast<double2*>(oprv + o) = make_double2(0.0, 0.0);
+        *reinterpret_cast<double2*>(osum + o) = sum;
+        *reinterpret_cast<double2*>(opsi + o) = cur;
     }
 
-    unsigned long long bar_target = 0;
     bool decided_all = false;
     constexpr int PW = sizeof(PassParams) / 8;
     double pass_word = 0.0;
     if (tid < PW && P.n_steps > 0) pass_word = reinterpret_cast<const double*>(P.passes)[tid];
     __syncthreads();
-    const bool act0[2] = {!sctrl.part[0].latched, !sctrl.part[1].latched};      // particles that take part in this launch
+    const bool act0[2] = {!sh.sctrl.part[0].latched, !sh.sctrl.part[1].latched};      // particles that take part in this launch
 
     // ring cursors (uniform over the CTA): tile being computed / retired / issued at retirement
     int qc = 0, sc = 0, phc = 0;                 // computed:  index, stage, phase
@@ -194,12 +482,13 @@ mid_series_kernel_t(const __grid_constant__ CUtensorMap tmap, const MidParams P)
 
     int t = 0;
     for (; t < P.n_steps; ++t) {
-        if (sctrl.part[0].latched && sctrl.part[1].latched) { decided_all = true; break; }
+        if (sh.sctrl.part[0].latched && sh.sctrl.part[1].latched) { decided_all = true; break; }
         if (tid < PW) {                                          // this term's parameters were fetched one term ahead
-            reinterpret_cast<double*>(&spass[t & 1])[tid] = pass_word;
+            reinterpret_cast<double*>(&sh.spass[t & 1])[tid] = pass_word;
             if (t + 1 < P.n_steps) pass_word = reinterpret_cast<const double*>(P.passes + t + 1)[tid];
         }
         const int par = t & 1;
+        const unsigned ep = P.epoch0 + t + 1;
         DYB_MSTAMP(0);
 
         // ---------------------------------------------------------------- 1. both products of the block, streamed
@@ -216,32 +505,67 @@ mid_series_kernel_t(const __grid_constant__ CUtensorMap tmap, const MidParams P)
                     for (int q = 0; q < NQ; ++q) acc[m][e][q] = 0.0;
                 }
             }
+            double pvo[MID_CPW * NQ];                            // bra partials of the previous tile, reduced beside the FMAs of this one
+#pragma unroll
+            for (int i = 0; i < MID_CPW * NQ; ++i) pvo[i] = 0.0;
+            double* Uw = U + ((size_t)wr * Cnp + wc * MID_CPW + (lane >> 4)) * NQ + ((lane >> 2) & 3);
             for (int j = 0; j < NT; ++j) {
                 mbar_wait_or_trap(&bar_full[sc], uint32_t(phc));
                 const double* sH = reinterpret_cast<const double*>(msm + (size_t)sc * MID_STAGE_BYTES);
-                double pv[MID_CPW * NQ];
+                // The five butterfly levels of tile j-1 (transpose_reduce<8>, same order) are issued BETWEEN the four FMA blocks
+                // of tile j: a shuffle's latency is covered by the 32 independent FMAs that follow it in the instruction stream.
+                double2 h0[MID_MPT], h1[MID_MPT];
+                double xk0[NQ], xk1[NQ];
+                {
+                    const double2* xq = reinterpret_cast<const double2*>(sxk + (size_t)(j * TC + wc * MID_CPW) * NQ);
+                    const double2 a01 = xq[0], a23 = xq[1], b01 = xq[2], b23 = xq[3];
+                    xk0[0] = a01.x; xk0[1] = a01.y; xk0[2] = a23.x; xk0[3] = a23.y;
+                    xk1[0] = b01.x; xk1[1] = b01.y; xk1[2] = b23.x; xk1[3] = b23.y;
+                    const double2* hp = reinterpret_cast<const double2*>(sH + (size_t)((wc * MID_CPW) * WR + wr) * MID_SUB) + lane;
 #pragma unroll
-                for (int cc = 0; cc < MID_CPW; ++cc) {
-                    const int c = wc * MID_CPW + cc;
-                    const double2* xq = reinterpret_cast<const double2*>(sxk + (size_t)(j * TC + c) * NQ);
-                    const double2 x01 = xq[0], x23 = xq[1];
-                    const double xk[NQ] = {x01.x, x01.y, x23.x, x23.y};
-                    const double2* hp = reinterpret_cast<const double2*>(sH + (size_t)(c * WR + wr) * MID_SUB) + lane;
-                    double2 h[MID_MPT];
+                    for (int m = 0; m < MID_MPT; ++m) { h0[m] = hp[m * 32]; h1[m] = hp[(size_t)WR * (MID_SUB / 2) + m * 32]; }
+                }
+                double pa[NQ], pa1[NQ], pb_[NQ], pb1[NQ];
+                double ra[4], rb[2], rc;
+                {
+                    const bool hi = lane & 16;
 #pragma unroll
-                    for (int m = 0; m < MID_MPT; ++m) h[m] = hp[m * 32];
-                    mid_fma_column(acc, xb, h, xk, pv + cc * NQ);
+                    for (int i = 0; i < 4; ++i) {
+                        const double keep = hi ? pvo[4 + i] : pvo[i], send = hi ? pvo[i] : pvo[4 + i];
+                        ra[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
                 }
-                const double tot = transpose_reduce<MID_CPW * NQ>(pv, lane);       // lane holds value (lane >> 2)
-                if ((lane & 3) == 0) {
-                    const int v = lane >> 2;
-                    U[((size_t)wr * Cnp + j * TC + wc * MID_CPW + (v >> 2)) * NQ + (v & 3)] = tot;
+                mid_fma_half<0>(acc, xb, h0, xk0, pa, pa1);
+                {
+                    const bool hi = lane & 8;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const double keep = hi ? ra[2 + i] : ra[i], send = hi ? ra[i] : ra[2 + i];
+                        rb[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    }
                 }
+                mid_fma_half<2>(acc, xb, h0, xk0, pa, pa1);
+                {
+                    const bool hi = lane & 4;
+                    const double keep = hi ? rb[1] : rb[0], send = hi ? rb[0] : rb[1];
+                    rc = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                }
+                mid_fma_half<0>(acc, xb, h1, xk1, pb_, pb1);
+                rc += __shfl_xor_sync(0xffffffffu, rc, 2);
+                mid_fma_half<2>(acc, xb, h1, xk1, pb_, pb1);
+                rc += __shfl_xor_sync(0xffffffffu, rc, 1);                        // lane holds value (lane >> 2) of tile j-1
+                if ((lane & 3) == 0 && j > 0) Uw[(size_t)(j - 1) * TC * NQ] = rc;
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) { pvo[q] = pa[q] + pa1[q]; pvo[NQ + q] = pb_[q] + pb1[q]; }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_empty[sc]);      // release: stage reads are done
                 if (j > 0) retire(qc - 1);
                 ++qc;
                 if (++sc == ST) { sc = 0; phc ^= 1; }
+            }
+            {
+                const double tot = transpose_reduce<MID_CPW * NQ>(pvo, lane);
+                if ((lane & 3) == 0) Uw[(size_t)(NT - 1) * TC * NQ] = tot;
             }
             retire(qc - 1);
             DYB_MSTAMP(1);
@@ -249,15 +573,12 @@ mid_series_kernel_t(const __grid_constant__ CUtensorMap tmap, const MidParams P)
 
             // bra partial of block column bj from block row bi -> pb[par][bj][bi][.]
             {
-                double* dst = P.pb + (((size_t)par * Gc + bj) * Gr + bi) * Cnp * NQ;
-                for (int idx = tid; idx < Cnp * 2; idx += MID_THREADS) {
-                    double2 v = *reinterpret_cast<const double2*>(U + (size_t)idx * 2);
+                ulonglong2* dst = P.pb + (((size_t)par * Gc + bj) * Gr + bi) * Cnp * NQ;
+                for (int idx = tid; idx < Cnp * NQ; idx += MID_THREADS) {
+                    double v = U[idx];
 #pragma unroll
-                    for (int r2 = 1; r2 < WR; ++r2) {
-                        const double2 o = *reinterpret_cast<const double2*>(U + ((size_t)r2 * Cnp * NQ) + (size_t)idx * 2);
-                        v.x += o.x; v.y += o.y;
-                    }
-                    __stcg(reinterpret_cast<double2*>(dst + (size_t)idx * 2), v);
+                    for (int r2 = 1; r2 < WR; ++r2) v += U[(size_t)r2 * Cnp * NQ + idx];
+                    ll_store(dst + idx, v, ep);
                 }
             }
             __syncthreads();                                     // U is free for the ket reduction
@@ -288,213 +609,53 @@ mid_series_kernel_t(const __grid_constant__ CUtensorMap tmap, const MidParams P)
                 }
                 if (2 * s < WC) __syncthreads();
             }
-            // ket partial of block row bi from block column bj -> pk[par][bi][bj][.]
+            // ket partial of block row bi from block column bj -> pk[par][bi][bj][.]: rows through shared memory (the region of
+            // U a wc == 0 warp writes is its own or already consumed), then 512 contiguous bytes per store instruction
             if (wc == 0) {
-                double2* dst = reinterpret_cast<double2*>(P.pk + ((((size_t)par * Gr + bi) * Gc + bj) * R + wr * MID_SUB + 2 * lane) * NQ);
+                double2* st = reinterpret_cast<double2*>(U) + (size_t)(wr * MID_SUB + 2 * lane) * 2;
 #pragma unroll
                 for (int m = 0; m < MID_MPT; ++m)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        __stcg(dst + m * (64 * NQ / 2) + e * 2,     make_double2(acc[m][e][0], acc[m][e][1]));
-                        __stcg(dst + m * (64 * NQ / 2) + e * 2 + 1, make_double2(acc[m][e][2], acc[m][e][3]));
+                        st[(m * 64 + e) * 2 + 0] = make_double2(acc[m][e][0], acc[m][e][1]);
+                        st[(m * 64 + e) * 2 + 1] = make_double2(acc[m][e][2], acc[m][e][3]);
                     }
             }
+            __syncthreads();
+            {
+                ulonglong2* dst = P.pk + ((((size_t)par * Gr + bi) * Gc + bj) * R) * NQ;
+#pragma unroll
+                for (int i = 0; i < R * NQ / MID_THREADS; ++i) ll_store(dst + i * MID_THREADS + tid, U[i * MID_THREADS + tid], ep);
+            }
         }
-
-        // ---------------------------------------------------------------- 2. the one grid barrier of the term
         DYB_MSTAMP(2);
-        bar_target += G;
-        res_grid_barrier(P.gbar, bar_target);
-        DYB_MSTAMP(3);
 
-        // ---------------------------------------------------------------- 3. decision on term t-1 (identical in every CTA)
+        // ---------------------------------------------------------------- 2. decision on term t-1 (identical in every CTA)
+        // (its scalars were published a whole product ago: one round trip)
         if (t > 0) {
-            if (w == 0) {
-                double v[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-                for (int d = lane; d < P.nd; d += 32) {
-                    const double2* ds = reinterpret_cast<const double2*>(P.dscal + ((size_t)((t + 1) & 1) * G + P.diag[d]) * 8);
-                    const double2 a0 = __ldcg(ds), a1 = __ldcg(ds + 1), a2 = __ldcg(ds + 2), a3 = __ldcg(ds + 3);
-                    v[0] = fmax(v[0], a0.x); v[1] = fmax(v[1], a0.y); v[2] += a1.x; v[3] += a1.y;
-                    v[4] = fmax(v[4], a2.x); v[5] = fmax(v[5], a2.y); v[6] += a3.x; v[7] += a3.y;
-                }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const double o = __shfl_xor_sync(0xffffffffu, v[q], off);
-                        v[q] = ((q & 3) < 2) ? fmax(v[q], o) : v[q] + o;
-                    }
-                if (lane == 0) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) fin[q] = v[q];
-                }
-            }
-            __syncthreads();
-            if (tid == 0 || tid == 32) {
-                const int p = tid >> 5;                          // stop_chain as of the previous term: the same in every CTA
-                decide_particle(sctrl.part[p], spass[(t - 1) & 1].part[p], fin + 4 * p, !stop_chain);
-            }
-            __syncthreads();
-            if (sctrl.part[0].latched && sctrl.part[1].latched) { decided_all = true; break; }
-            if (tid == 0 && ((sctrl.part[0].latched && !sctrl.part[0].ok) || (sctrl.part[1].latched && !sctrl.part[1].ok))) stop_chain = 1;
+            mid_decide(P, &sh, t - 1, !sh.stop_chain);           // stop_chain as of the previous term: the same in every CTA
+            if (sh.sctrl.part[0].latched && sh.sctrl.part[1].latched) { decided_all = true; break; }
+            if (tid == 0 && ((sh.sctrl.part[0].latched && !sh.sctrl.part[0].ok) || (sh.sctrl.part[1].latched && !sh.sctrl.part[1].ok))) sh.stop_chain = 1;
         }
+        DYB_MSTAMP(3);
+        __syncthreads();                                         // the ket rows staged in U have been published (t = 0: no decision)
 
-        DYB_MSTAMP(4);
-        // ---------------------------------------------------------------- 4. gather + recurrence + series sum
-        // A gather task = (entry, particle) of one side; 2^lsl lanes split its partials (<= 8 each, fixed order), a lane
-        // butterfly adds them up, the first lane applies the update to this CTA's copy of the state.
-#pragma unroll 1
-        for (int side = 0; side < 2; ++side) {
-            const int n_e   = side ? R : Cnp;
-            const int gbase = side ? row0 : col0;
-            const int lsl   = side ? P.lslb : P.lslk;
-            const int SL    = 1 << lsl;
-            const int n_par = side ? Gr : Gc;                    // partials per entry
-            const int nslots = (n_e * 2) << lsl;
-            double* xs = side ? sxb : sxk;
-            double* ps = xs + (size_t)n_e * NQ;
-            double* ss = ps + (size_t)n_e * NQ;
-            double* mg = U + (side ? Cnp * 2 : 0);               // |new - old|^2 per (entry, particle)
-#pragma unroll 1
-            for (int f0 = 0; f0 < nslots; f0 += MID_THREADS * MID_GB) {
-                double2 v[MID_GB][8];
-                bool okv[MID_GB];
-#pragma unroll
-                for (int u = 0; u < MID_GB; ++u) {
-                    const int f = f0 + u * MID_THREADS + tid;
-                    const int sl = f & (SL - 1), p = (f >> lsl) & 1, e = f >> (lsl + 1);
-                    const int g = gbase + e;
-                    okv[u] = (f < nslots) && (g < N);
-                    const double* src;
-                    size_t stride;
-                    if (side == 0) {                             // ket entry g: block row g / R, partials of the Gc block columns
-                        const int br = g / R, rr = g - br * R;
-                        src = P.pk + ((((size_t)par * Gr + br) * Gc) * R + rr) * NQ + 2 * p;
-                        stride = (size_t)R * NQ;
-                    } else {                                     // bra entry g: block column g / Cnp, partials of the Gr block rows
-                        const int bc = g / Cnp, cc = g - bc * Cnp;
-                        src = P.pb + ((((size_t)par * Gc + bc) * Gr) * Cnp + cc) * NQ + 2 * p;
-                        stride = (size_t)Cnp * NQ;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int k = sl + (i << lsl);
-                        v[u][i] = (okv[u] && k < n_par) ? __ldcg(reinterpret_cast<const double2*>(src + (size_t)k * stride)) : make_double2(0.0, 0.0);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < MID_GB; ++u) {
-                    double2 hx = v[u][0];
-#pragma unroll
-                    for (int i = 1; i < 8; ++i) { hx.x += v[u][i].x; hx.y += v[u][i].y; }
-                    for (int off = 1; off < SL; off <<= 1) {
-                        hx.x += __shfl_xor_sync(0xffffffffu, hx.x, off); hx.y += __shfl_xor_sync(0xffffffffu, hx.y, off);
-                    }
-                    const int f = f0 + u * MID_THREADS + tid;
-                    const int sl = f & (SL - 1), p = (f >> lsl) & 1, e = f >> (lsl + 1);
-                    if (okv[u] && sl == 0) {
-                        const PartPass& pa = spass[par].part[p];
-                        double mag = 0.0;
-                        if (pa.active && !sctrl.part[p].latched) {
-                            const size_t o = (size_t)e * NQ + 2 * p;
-                            double2 cur = *reinterpret_cast<const double2*>(xs + o);
-                            double2 sum = *reinterpret_cast<const double2*>(ss + o);
-                            if (pa.begin) {                      // next steady sub-step: adopt the previous sum (Taylor.f:105,:83-86);
-                                const int g = gbase + e;         // hx was computed from it (x of the chain term)
-                                if (g >= i0 && g < i1) __stcg(reinterpret_cast<double2*>(P.psi_store + ((size_t)side * N + g) * NQ + 2 * p), sum);
-                                cur = sum;
-                                const Cx s0 = cmul({pa.s_re, pa.s_im}, {sum.x, sum.y});
-                                sum = make_double2(s0.re, s0.im);
-                            }
-                            Cx y = cmul({pa.alpha_re, pa.alpha_im}, {hx.x, hx.y});
-                            if (pa.three_term) {
-                                const Cx bc = cmul({pa.beta_re, pa.beta_im}, {cur.x, cur.y});
-                                y.re += bc.re; y.im += bc.im;
-                                if (pa.gamma != 0.0) {
-                                    const double2 prv = *reinterpret_cast<const double2*>(ps + o);
-                                    y.re += pa.gamma * prv.x; y.im += pa.gamma * prv.y;
-                                }
-                            }
-                            Cx tt = y;
-                            if (pa.scale_term) tt = cmul({pa.c_re, pa.c_im}, y);
-                            const double nw_re = sum.x + tt.re, nw_im = sum.y + tt.im;
-                            const double dx = nw_re - sum.x, dy = nw_im - sum.y;
-                            mag = dx * dx + dy * dy;             // |new - old|^2 (isConverged, Taylor.f:290-303); root after the max
-                            *reinterpret_cast<double2*>(ps + o) = cur;
-                            // what the next product multiplies: the new vector, or (speculatively) the sum the next sub-step starts from
-                            *reinterpret_cast<double2*>(xs + o) = pa.chain ? make_double2(nw_re, nw_im) : make_double2(y.re, y.im);
-                            *reinterpret_cast<double2*>(ss + o) = make_double2(nw_re, nw_im);
-                        }
-                        mg[e * 2 + p] = mag;
-                    }
-                }
-            }
-        }
+        // ---------------------------------------------------------------- 3. owner: collect, update, publish
+        mid_collect<R>(P, U, t);
+        DYB_MSTAMP(7);
         __syncthreads();
-        DYB_MSTAMP(5);
+        mid_update(P, &sh, U, ocur, t);
+        DYB_MSTAMP(4);
 
-        // ---------------------------------------------------------------- 5. scalars of the indices this CTA holds on both sides
-        if (diag) {
-            double v[4] = {0.0, 0.0, 0.0, 0.0};                  // max_b, max_k, dot_re, dot_im of particle (tid & 1)
-            for (int idx = tid; idx < (i1 - i0) * 2; idx += MID_THREADS) {
-                const int g = i0 + (idx >> 1), p = idx & 1;
-                const int ek = g - col0, eb = g - row0;
-                const double2 k = *reinterpret_cast<const double2*>(sxk + (size_t)2 * Cnp * NQ + (size_t)ek * NQ + 2 * p);
-                const double2 b = *reinterpret_cast<const double2*>(sxb + (size_t)2 * R * NQ + (size_t)eb * NQ + 2 * p);
-                v[0] = fmax(v[0], U[Cnp * 2 + eb * 2 + p]); v[1] = fmax(v[1], U[ek * 2 + p]);
-                v[2] += b.x * k.x + b.y * k.y;                   // conj(bra) * ket
-                v[3] += b.x * k.y - b.y * k.x;
-            }
-#pragma unroll
-            for (int off = 2; off < 32; off <<= 1) {             // lanes of equal particle (lane bit 0)
-                v[0] = fmax(v[0], __shfl_xor_sync(0xffffffffu, v[0], off)); v[1] = fmax(v[1], __shfl_xor_sync(0xffffffffu, v[1], off));
-                v[2] += __shfl_xor_sync(0xffffffffu, v[2], off);            v[3] += __shfl_xor_sync(0xffffffffu, v[3], off);
-            }
-            if (lane < 2) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) wred[w][lane * 4 + q] = v[q];
-            }
-            __syncthreads();
-            if (tid < 8) {
-                double f = wred[0][tid];
-#pragma unroll
-                for (int w2 = 1; w2 < MID_WARPS; ++w2) f = ((tid & 3) < 2) ? fmax(f, wred[w2][tid]) : f + wred[w2][tid];
-                if ((tid & 3) < 2) f = sqrt(f);
-                __stcg(P.dscal + ((size_t)par * G + blockIdx.x) * 8 + tid, f);
-            }
-            __syncthreads();                                     // the magnitudes in U have been read: the next product may reuse U
-        }
+        // ---------------------------------------------------------------- 4. consumer: the entries the next product multiplies
+        if (t + 1 < P.n_steps) mid_consume<R>(P, sxk, t);
+        DYB_MSTAMP(5);
+        __syncthreads();
         DYB_MSTAMP(6);
     }
 
-    // ---- decision on the last term (one more barrier), unless the series was decided on the way
-    if (!decided_all && t > 0) {
-        bar_target += G;
-        res_grid_barrier(P.gbar, bar_target);
-        if (w == 0) {
-            double v[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-            for (int d = lane; d < P.nd; d += 32) {
-                const double2* ds = reinterpret_cast<const double2*>(P.dscal + ((size_t)((t - 1) & 1) * G + P.diag[d]) * 8);
-                const double2 a0 = __ldcg(ds), a1 = __ldcg(ds + 1), a2 = __ldcg(ds + 2), a3 = __ldcg(ds + 3);
-                v[0] = fmax(v[0], a0.x); v[1] = fmax(v[1], a0.y); v[2] += a1.x; v[3] += a1.y;
-                v[4] = fmax(v[4], a2.x); v[5] = fmax(v[5], a2.y); v[6] += a3.x; v[7] += a3.y;
-            }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const double o = __shfl_xor_sync(0xffffffffu, v[q], off);
-                    v[q] = ((q & 3) < 2) ? fmax(v[q], o) : v[q] + o;
-                }
-            if (lane == 0) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) fin[q] = v[q];
-            }
-        }
-        __syncthreads();
-        if (tid == 0 || tid == 32) { const int p = tid >> 5; decide_particle(sctrl.part[p], spass[(t - 1) & 1].part[p], fin + 4 * p); }
-        __syncthreads();
-    }
+    // ---- decision on the last term, unless the series was decided on the way
+    if (!decided_all && t > 0) mid_decide(P, &sh, t - 1, true);
 
     // ---- never exit with bulk copies in flight to our shared memory: tiles qc .. min(total, qc + ST) - 1 were issued
     if (tid == 0) {
@@ -502,26 +663,22 @@ mid_series_kernel_t(const __grid_constant__ CUtensorMap tmap, const MidParams P)
         for (int q = qc; q < issued; ++q) mbar_wait_or_trap(&bar_full[q % ST], uint32_t((q / ST) & 1));
     }
 
-    // ---- results: every index has exactly one CTA that holds both of its sums
+    // ---- results of the owned indices
     // a particle that failed a steady sub-step hands back the start vector of that sub-step (= the last accepted sum)
-    if (diag) {
-        for (int idx = tid; idx < (i1 - i0) * 2; idx += MID_THREADS) {
-            const int g = i0 + (idx >> 1), p = idx & 1;
-            if (!act0[p]) continue;
-            const bool failed = sctrl.part[p].latched && !sctrl.part[p].ok;
-            const size_t og = (size_t)g * NQ + 2 * p;
-            const double2 k = failed ? __ldcg(reinterpret_cast<const double2*>(P.psi_store + og))
-                                     : *reinterpret_cast<const double2*>(sxk + (size_t)2 * Cnp * NQ + (size_t)(g - col0) * NQ + 2 * p);
-            const double2 b = failed ? __ldcg(reinterpret_cast<const double2*>(P.psi_store + (size_t)N * NQ + og))
-                                     : *reinterpret_cast<const double2*>(sxb + (size_t)2 * R * NQ + (size_t)(g - row0) * NQ + 2 * p);
-            *reinterpret_cast<double2*>(P.sum_k + og) = k;
-            *reinterpret_cast<double2*>(P.sum_b + og) = b;
-        }
+    for (int f = tid; f < 2 * E * 2; f += MID_THREADS) {
+        const int side = f >= E * 2;
+        const int ff = side ? f - E * 2 : f;
+        const int e = ff >> 1, p = ff & 1, g = o0 + e;
+        if (g >= N || !act0[p]) continue;
+        const bool failed = sh.sctrl.part[p].latched && !sh.sctrl.part[p].ok;
+        const size_t o = ((size_t)side * E + e) * NQ + 2 * p;
+        const double2 v = *reinterpret_cast<const double2*>((failed ? opsi : osum) + o);
+        *reinterpret_cast<double2*>((side ? P.sum_b : P.sum_k) + (size_t)g * NQ + 2 * p) = v;
     }
     if (blockIdx.x == 0 && tid == 0) {
-        sctrl.all_latched = (sctrl.part[0].latched && sctrl.part[1].latched) ? 1 : 0;
-        sctrl.block_counter = 0u;
-        *P.ctrl = sctrl;
+        sh.sctrl.all_latched = (sh.sctrl.part[0].latched && sh.sctrl.part[1].latched) ? 1 : 0;
+        sh.sctrl.block_counter = 0u;
+        *P.ctrl = sh.sctrl;
     }
 }
 

@@ -104,7 +104,9 @@ struct dyb_ctx {
     MidParams mid_P;                     // constant part of the launch parameters
     size_t mid_smem = 0;
     CUtensorMap tmap_mid;
-    double *mid_pk = nullptr, *mid_pb = nullptr, *mid_dscal = nullptr, *mid_psi = nullptr;
+    double *mid_pk = nullptr, *mid_pb = nullptr, *mid_xx = nullptr, *mid_sc = nullptr;   // epoch-tagged exchange buffers (16 B per double)
+    size_t mid_bytes[4] = {0, 0, 0, 0};
+    unsigned mid_epoch = 1;              // next unused epoch of the tagged words
     PassParams* d_passes = nullptr;      // per-term parameters of the series in flight
     unsigned long long* gbar = nullptr;  // grid barrier counter
     cudaStream_t stream = nullptr;
@@ -452,30 +454,29 @@ static int run_series_resident(dyb_ctx* c, const std::vector<PassParams>& passes
 
 // Mid-size operators streamed by ONE launch per series (mid.cuh): single GPU; not for the reference-GPU term test.
 // Blocking (pure host arithmetic, exported as dyb_mid_plan for the CPU tests): R = 512 rows per CTA, Gr = ceil(N / R) block
-// rows, Gc = sm_count / Gr block columns of Cnp = roundup(ceil(N / Gc), 8) columns, Gc = ceil(N / Cnp).
-struct MidPlan { int WR, R, TC, Gr, Gc, Cnp, NT, ST, lslk, lslb, nd; int diag[MID_MAX_DIAG]; size_t smem; bool fits; };
-static int ceil_log2_lanes(int n_partials) { int l = 0; while (((n_partials + (1 << l) - 1) >> l) > 8) ++l; return l; }
+// rows, Gc = min(64, sm_count / Gr) block columns of Cnp = roundup(ceil(N / Gc), 8) columns, Gc = ceil(N / Cnp); every CTA
+// owns E = ceil(N / (Gr Gc)) consecutive indices of the vectors (n_own = ceil(N / E) CTAs own at least one).
+struct MidPlan { int WR, R, TC, Gr, Gc, Cnp, NT, ST, E, n_own; size_t smem; bool fits; };
 static MidPlan make_mid_plan(int N, int sm_count, size_t smem_optin, size_t static_smem) {
     MidPlan m;
     memset(&m, 0, sizeof m);
     m.WR = 2; m.R = m.WR * MID_SUB; m.TC = (MID_WARPS / m.WR) * MID_CPW;
     m.Gr = (N + m.R - 1) / m.R;
-    const int gc0 = sm_count / std::max(1, m.Gr);
+    const int gc0 = std::min(64, sm_count / std::max(1, m.Gr));        // <= 64 partials per ket entry (summed by one thread)
     if (gc0 < 1) return m;
     const int cn = (N + gc0 - 1) / gc0;
     m.Cnp = (cn + m.TC - 1) / m.TC * m.TC;
     m.Gc = (N + m.Cnp - 1) / m.Cnp;
     m.NT = m.Cnp / m.TC;
-    m.lslk = ceil_log2_lanes(m.Gc); m.lslb = ceil_log2_lanes(m.Gr);
-    for (int b = 0; b < m.Gr * m.Gc; ++b) {                   // CTAs that hold bra AND ket entries of some index
-        const int bi = b / m.Gc, bj = b % m.Gc;
-        const int i0 = std::max(bi * m.R, bj * m.Cnp), i1 = std::min(std::min(bi * m.R + m.R, bj * m.Cnp + m.Cnp), N);
-        if (i0 < i1) { if (m.nd < MID_MAX_DIAG) m.diag[m.nd] = b; m.nd++; }
-    }
+    const int G = m.Gr * m.Gc;
+    m.E = (N + G - 1) / G;
+    m.n_own = (N + m.E - 1) / m.E;
     const size_t budget = std::min((size_t)MID_SMEM_MAX, smem_optin > static_smem ? smem_optin - static_smem : 0);
-    for (m.ST = MID_MAX_ST; m.ST >= 2; --m.ST) { m.smem = (size_t)MidSmem(m.ST, m.R, m.Cnp).total; if (m.smem <= budget) break; }
-    m.fits = m.ST >= 2 && m.nd <= MID_MAX_DIAG && m.lslk <= 5 && m.lslb <= 5 && m.Gr * m.Gc <= sm_count
-             && (size_t)m.WR * m.Cnp * NQ * 8 <= (size_t)MID_U_BYTES && (size_t)(m.Cnp + m.R) * 2 * 8 <= (size_t)MID_U_BYTES;
+    for (m.ST = MID_MAX_ST; m.ST >= 2; --m.ST) { m.smem = (size_t)MidSmem(m.ST, m.R, m.Cnp, m.E, m.Gr + m.Gc).total; if (m.smem <= budget) break; }
+    // an owner's indices span at most two block columns (E <= Cnp); the 8 scalar slots of <= 16 * MID_SCU owners; a consumer's
+    // R + Cnp entries in MID_XU words per thread; the bra partials of the WR row groups in the union region
+    m.fits = m.ST >= 2 && G <= sm_count && m.E <= MID_MAX_E && m.E <= m.Cnp && m.n_own <= 16 * MID_SCU
+             && (m.Cnp + m.R) * NQ <= MID_THREADS * MID_XU && (size_t)m.WR * m.Cnp * NQ * 8 <= (size_t)MID_U_BYTES;
     return m;
 }
 static bool mid_ok(const dyb_ctx* c, bool refgpu) {
@@ -488,16 +489,23 @@ static int run_series_mid(dyb_ctx* c, const std::vector<PassParams>& passes) {
     const int n = (int)passes.size();
     if (n < 1 || n > MAX_CHAIN_PASSES) return fail(DYB_EINVAL, "series length %d out of range", n);
     CK(cudaMemcpyAsync(c->d_passes, passes.data(), sizeof(PassParams) * n, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemsetAsync(c->gbar, 0, sizeof(unsigned long long), c->stream));
     MidParams P = c->mid_P;
+    if (c->mid_epoch > 0xfff00000u) {          // the 32-bit epochs are about to wrap: forget every tagged word (stream-ordered)
+        CK(cudaMemsetAsync(c->mid_pk, 0, c->mid_bytes[0], c->stream)); CK(cudaMemsetAsync(c->mid_pb, 0, c->mid_bytes[1], c->stream));
+        CK(cudaMemsetAsync(c->mid_xx, 0, c->mid_bytes[2], c->stream)); CK(cudaMemsetAsync(c->mid_sc, 0, c->mid_bytes[3], c->stream));
+        c->mid_epoch = 1;
+    }
+    P.epoch0 = c->mid_epoch;
+    c->mid_epoch += (unsigned)n + 4u;
     P.x0k = c->vk[0]; P.x0b = c->vb[0]; P.sum_b = c->sum_b; P.sum_k = c->sum_k;
-    P.pk = c->mid_pk; P.pb = c->mid_pb; P.dscal = c->mid_dscal; P.psi_store = c->mid_psi;
-    P.ctrl = c->ctrl; P.passes = c->d_passes; P.n_steps = n; P.gbar = c->gbar;
+    P.pk = reinterpret_cast<ulonglong2*>(c->mid_pk); P.pb = reinterpret_cast<ulonglong2*>(c->mid_pb);
+    P.xx = reinterpret_cast<ulonglong2*>(c->mid_xx); P.sc = reinterpret_cast<ulonglong2*>(c->mid_sc);
+    P.ctrl = c->ctrl; P.passes = c->d_passes; P.n_steps = n;
 #ifdef DYB_SERIES_PROF
     static long long* d_mprof = nullptr;
     const int mgrid = P.Gr * P.Gc;
-    const size_t n_mprof = (size_t)MAX_SERIES_TERMS * mgrid * 8;
-    if (!d_mprof) CK(cudaMalloc(&d_mprof, (size_t)MAX_SERIES_TERMS * 512 * 8 * 8));
+    const size_t n_mprof = (size_t)MAX_SERIES_TERMS * mgrid * 16;
+    if (!d_mprof) CK(cudaMalloc(&d_mprof, (size_t)MAX_SERIES_TERMS * 512 * 16 * 8));
     CK(cudaMemsetAsync(d_mprof, 0, n_mprof * 8, c->stream));
     P.prof = d_mprof;
 #else
@@ -513,20 +521,23 @@ static int run_series_mid(dyb_ctx* c, const std::vector<PassParams>& passes) {
             std::vector<long long> h(n_mprof);
             CK(cudaStreamSynchronize(c->stream));
             CK(cudaMemcpy(h.data(), d_mprof, n_mprof * 8, cudaMemcpyDeviceToHost));
-            const char* name[7] = {"product", "reduce+store", "barrier", "decide", "gather", "scalars", "loop-gap"};
-            double mean[7] = {0}, mx[7] = {0};
+            const char* name[8] = {"product", "reduce+publish", "decide", "collect", "update+publish-x", "sync+scalars+consume-wait", "sync2", "loop-gap"};
+            const int order[9] = {0, 1, 2, 3, 7, 4, 5, 6, 0};      // stamp order inside a term; the last one is stamp 0 of the next term
+            double mean[8] = {0}, mx[8] = {0}, extra[2] = {0, 0};
             const int nt = std::min(n, MAX_SERIES_TERMS);
             for (int t = 1; t + 1 < nt; ++t) for (int b = 0; b < mgrid; ++b) {
-                const long long* q = &h[((size_t)t * mgrid + b) * 8];
-                for (int i = 0; i < 7; ++i) {
-                    const long long nx = (i < 6) ? q[i + 1] : h[((size_t)(t + 1) * mgrid + b) * 8];
-                    const double d = double(nx - q[i]);
+                const long long* q = &h[((size_t)t * mgrid + b) * 16];
+                extra[0] += double(q[9] - q[2]); extra[1] += double(q[10] - q[9]);
+                for (int i = 0; i < 8; ++i) {
+                    const long long nx = (i < 7) ? q[order[i + 1]] : h[((size_t)(t + 1) * mgrid + b) * 16];
+                    const double d = double(nx - q[order[i]]);
                     mean[i] += d; mx[i] = std::max(mx[i], d);
                 }
             }
             fprintf(stderr, "mid_prof N=%d grid=%dx%d Cnp=%d NT=%d ST=%d terms=%d:", c->N, P.Gr, P.Gc, P.Cnp, P.NT, P.ST, n);
-            for (int i = 0; i < 7; ++i) fprintf(stderr, "  %s mean %.0f max %.0f cyc;", name[i], mean[i] / ((double)std::max(1, nt - 2) * mgrid), mx[i]);
-            fprintf(stderr, "\n");
+            for (int i = 0; i < 8; ++i) fprintf(stderr, "  %s mean %.0f max %.0f cyc;", name[i], mean[i] / ((double)std::max(1, nt - 2) * mgrid), mx[i]);
+            const double dn = (double)std::max(1, nt - 2) * mgrid;
+            fprintf(stderr, "  [thread 128: reaches the decision %.0f after the publication, its scalar collect %.0f]\n", extra[0] / dn, extra[1] / dn);
         }
     }
 #endif
@@ -1050,14 +1061,14 @@ int dyb_resident_plan(int N, int sm_count, int64_t smem_optin, int64_t* out6) {
 }
 
 // Host-only: the blocking of the streamed one-launch series kernel (mid.cuh).  out12 = {block rows R, tile columns TC, grid rows
-// Gr, grid columns Gc, block columns Cnp, tiles per term, ring stages, log2 gather lanes (ket), log2 gather lanes (bra),
-// intersecting CTAs, dynamic smem bytes, fits (0/1)}; diag[out12[9]] (when non-NULL) receives their block indices.
-int dyb_mid_plan(int N, int sm_count, int64_t smem_optin, int64_t* out12, int32_t* diag) {
+// Gr, grid columns Gc, block columns Cnp, tiles per term, ring stages, indices per owner E, owner CTAs, words an owner collects
+// per term, dynamic smem bytes, fits (0/1)}.
+int dyb_mid_plan(int N, int sm_count, int64_t smem_optin, int64_t* out12) {
     if (N <= 0 || sm_count <= 0 || smem_optin <= 0 || !out12) return fail(DYB_EINVAL, "bad argument");
     const MidPlan m = make_mid_plan(N, sm_count, (size_t)smem_optin, 2048);
     out12[0] = m.R; out12[1] = m.TC; out12[2] = m.Gr; out12[3] = m.Gc; out12[4] = m.Cnp; out12[5] = m.NT; out12[6] = m.ST;
-    out12[7] = m.lslk; out12[8] = m.lslb; out12[9] = m.nd; out12[10] = (int64_t)m.smem; out12[11] = m.fits ? 1 : 0;
-    if (diag) for (int d = 0; d < std::min(m.nd, (int)MID_MAX_DIAG); ++d) diag[d] = m.diag[d];
+    out12[7] = m.E; out12[8] = m.n_own; out12[9] = (int64_t)(m.Gr + m.Gc) * m.E * NQ;
+    out12[10] = (int64_t)m.smem; out12[11] = m.fits ? 1 : 0;
     return DYB_OK;
 }
 
@@ -1122,7 +1133,7 @@ int dyb_destroy(dyb_ctx* c) {
     if (c->res_pb) cudaFree(c->res_pb);
     if (c->res_dscal) cudaFree(c->res_dscal);
     if (c->res_psi) cudaFree(c->res_psi);
-    for (double* b : {c->mid_pk, c->mid_pb, c->mid_dscal, c->mid_psi}) if (b) cudaFree(b);
+    for (double* b : {c->mid_pk, c->mid_pb, c->mid_xx, c->mid_sc}) if (b) cudaFree(b);
     if (c->h_ctrl) cudaFreeHost(c->h_ctrl);
     if (c->h_scal) cudaFreeHost(c->h_scal);
     for (auto e : c->ev) cudaEventDestroy(e);
@@ -1215,16 +1226,18 @@ int dyb_create(dyb_ctx** out, int device, int N, int row0, int n_rows) {
             if (const char* e = getenv("DYNEMOL_B200_MID_L2MB")) c->mid_l2_mb = atof(e);
             MidParams& P = c->mid_P;
             memset(&P, 0, sizeof P);
-            P.N = N; P.Gr = mp.Gr; P.Gc = mp.Gc; P.Cnp = mp.Cnp; P.NT = mp.NT; P.ST = mp.ST; P.lslk = mp.lslk; P.lslb = mp.lslb; P.nd = mp.nd;
-            for (int d = 0; d < mp.nd; ++d) P.diag[d] = mp.diag[d];
+            P.N = N; P.Gr = mp.Gr; P.Gc = mp.Gc; P.Cnp = mp.Cnp; P.NT = mp.NT; P.ST = mp.ST;
+            P.E = mp.E; P.n_own = mp.n_own;
             const double bytes = 8.0 * (double)c->ld * N;
             P.l2_frac = c->mid_l2_mb <= 0.0 ? 0.f : (float)std::min(1.0, c->mid_l2_mb * 1.0e6 / bytes);
             c->mid_smem = mp.smem;
             CKC(build_tensor_map_mid(c, mp.WR, mp.TC));
             const size_t G = (size_t)mp.Gr * mp.Gc;
-            CKC(alloc_zero(&c->mid_pk, 2 * G * mp.R * NQ)); CKC(alloc_zero(&c->mid_pb, 2 * G * mp.Cnp * NQ));
-            CKC(alloc_zero(&c->mid_dscal, 2 * G * 8));
-            CKC(alloc_zero(&c->mid_psi, (size_t)2 * N * NQ));
+            // two doubles of storage per published double (epoch-tagged 16-byte words); zero = epoch 0 = never valid
+            const size_t nd[4] = {2 * 2 * G * mp.R * NQ, 2 * 2 * G * mp.Cnp * NQ, 2 * (size_t)2 * 2 * N * NQ, 2 * 4 * G * 8};
+            CKC(alloc_zero(&c->mid_pk, nd[0])); CKC(alloc_zero(&c->mid_pb, nd[1]));
+            CKC(alloc_zero(&c->mid_xx, nd[2])); CKC(alloc_zero(&c->mid_sc, nd[3]));
+            for (int i = 0; i < 4; ++i) c->mid_bytes[i] = nd[i] * 8;
             c->mid_fits = true;
         }
     }
