@@ -154,8 +154,11 @@ def mid_plan(N: int, sm_count: int = 148, smem_optin: int = 232448) -> dict:
     """Blocking of the streamed one-launch series kernel for mid-size operators (csrc/mid.cuh); host arithmetic only."""
     out = (C.c_int64 * 12)()
     _check(lib.dyb_mid_plan(C.c_int(N), C.c_int(sm_count), C.c_int64(smem_optin), out))
-    return dict(zip(["block_rows", "tile_cols", "grid_rows", "grid_cols", "block_cols", "tiles_per_term", "stages",
-                     "owned", "owners", "collect_words", "smem_bytes", "fits"], [int(v) for v in out]))
+    d = dict(zip(["block_rows", "tile_cols", "grid_rows", "grid_cols", "block_cols", "tiles_per_term", "stages",
+                  "owned", "owners", "collect_words", "smem_bytes", "fits"], [int(v) for v in out]))
+    d["table16"] = 1 if d["collect_words"] < 0 else 0
+    d["collect_words"] = abs(d["collect_words"])
+    return d
 
 
 def steady_schedule(t: float, t_max: float, tau: float, max_sub: int = 4096) -> np.ndarray:

@@ -50,10 +50,13 @@ constexpr int MID_STAGE_BYTES = 32768;      // R x TC x 8 B with R*TC = 4096 for
 constexpr int MID_MAX_ST      = 5;
 constexpr int MID_U_BYTES     = 32768;      // union region: bra partials of the row groups / ket tree reduction
 constexpr int MID_MAX_E       = 64;         // indices an owner may hold
-constexpr int MID_CW          = 12;         // owner: words a thread has in flight per collect pass
-constexpr int MID_XU          = 16;         // consumer: words per thread ((R + Cn) * 4 <= 256 * 16)
+constexpr int MID_CW          = 21;         // owner: words a thread has in flight per collect pass
+constexpr int MID_XT          = 224;        // consumer threads: warps 1..7 (warp 0 publishes the scalars meanwhile)
+constexpr int MID_XU          = 19;         // consumer: words per thread ((R + Cn) * 4 <= 224 * 19)
 constexpr int MID_SCU         = 10;         // decision: owners per thread (16 * 10 >= owner CTAs)
 constexpr int MID_SMEM_MAX    = 227 * 1024 - 2048;
+constexpr int MID_NO_WORD     = 0xffff;     // table entries of a word that does not exist (index >= N): 16-bit / 32-bit table
+constexpr int MID_NO_WORD32   = INT_MIN;
 #ifndef DYB_LL_SLEEP
 #define DYB_LL_SLEEP 300                    // ns between two polling rounds of a thread
 #endif
@@ -63,6 +66,7 @@ constexpr long long MID_SPIN_LIMIT = 1ll << 22;     // polls before a reader giv
 struct MidParams {
     int N, Gr, Gc, Cnp, NT, ST;             // grid, block width (multiple of TC), tiles per term, ring depth
     int E, n_own;                           // indices per owner CTA (ceil(N / grid)), CTAs that own at least one index
+    int tab16;                              // the collect table holds 16-bit (source, word) pairs instead of 32-bit offsets (large blocks)
     unsigned epoch0;                        // the epoch of this launch's term t is epoch0 + t + 1
     float l2_frac;                          // fraction of the H' lines loaded with L2::evict_last (0: plain evict_first stream)
     const double* x0k; const double* x0b;   // starting vectors (quads), written by series_init_kernel
@@ -78,21 +82,27 @@ struct MidParams {
 #ifdef DYB_SERIES_PROF
 #define DYB_MSTAMP(i) do { if (threadIdx.x == 0 && t < 32) P.prof[((size_t)t * G + blockIdx.x) * 16 + (i)] = clock64(); } while (0)
 #define DYB_MSTAMP_T(i, thr, tt) do { if (threadIdx.x == (thr) && (tt) < 32 && (tt) >= 0) P.prof[((size_t)(tt) * G + blockIdx.x) * 16 + (i)] = clock64(); } while (0)
+#define DYB_MROUNDS(i, v) do { if (threadIdx.x == 0 && t < 32) P.prof[((size_t)t * G + blockIdx.x) * 16 + (i)] = (v); } while (0)
 #else
 #define DYB_MSTAMP(i) do { } while (0)
 #define DYB_MSTAMP_T(i, thr, tt) do { } while (0)
+#define DYB_MROUNDS(i, v) do { } while (0)
 #endif
 
 struct MidSmem {                            // dynamic shared memory carve-up (byte offsets)
-    int bars, U, xk, xb, own, total;
-    __host__ __device__ MidSmem(int ST, int R, int Cnp, int E, int Gsum) {     // Gsum = Gr + Gc
+    int bars, U, xk, xb, own, tab, total;
+    __host__ __device__ MidSmem(int ST, int R, int Cnp, int E, int Gsum, int n_own, int tab16) {     // Gsum = Gr + Gc
         bars = ST * MID_STAGE_BYTES;
-        U    = bars + 128;                  // union region; also holds the (Gr + Gc) * E * 4 partials an owner collects
-        const int ub = Gsum * E * NQ * 8;
+        U    = bars + 128;                  // union region; also holds what an owner collects per term: (Gr + Gc) * E * 4
+        const int ub = (Gsum * E * NQ + n_own * 8) * 8;        // partials and the 8 scalars of every owner
         xk   = U + (ub > MID_U_BYTES ? (ub + 127) & ~127 : MID_U_BYTES);
         xb   = xk + Cnp * 32;               // [Cnp][NQ] then [R][NQ]: contiguous (the consumer fills both as one array)
         own  = xb + R * 32;                 // owner state: cur, prev, sum, start [2 sides][E][NQ] + magnitudes [2][E][2]
-        total = own + E * (4 * 2 * NQ * 8 + 2 * 2 * 8);
+        tab  = own + E * (4 * 2 * NQ * 8 + 2 * 2 * 8);
+        // the owner's collect table, [slot][thread]: the 32-bit offset of every word, or (when that would cost a ring stage)
+        // 16-bit (source, e * 4 + q) pairs behind the offsets per source [Gsum] and per (side, e, q) [2][E * 4]
+        const int slots = (Gsum * E * NQ + MID_THREADS - 1) / MID_THREADS;
+        total = tab + (tab16 ? ((Gsum + 2 * E * NQ) * 4 + 127) / 128 * 128 + slots * MID_THREADS * 2 : slots * MID_THREADS * 4);
     }
 };
 
@@ -119,7 +129,7 @@ __device__ __forceinline__ double ll_value(const ulonglong2& r) {
 // missing ones requested again together -- a round costs one L2 round trip whatever the number of words; OUT(i, value) consumes
 // word i as soon as it is valid.  A macro on purpose: the 16-byte words must live in REGISTERS (an array that ends up in local
 // memory -- lambdas / references did that -- puts a store behind every load and serialises them, one round trip each).
-#define DYB_LL_POLL(NW, pend, ep_, ADDR, OUT)                                                                     \
+#define DYB_LL_POLL(NW, pend, EP, ADDR, OUT, AFTER_REQ)                                                                    \
     do {                                                                                                          \
         for (long long it_ = 0;; ++it_) {                                                                         \
             unsigned long long rx_[NW], ry_[NW];                                                                  \
@@ -127,12 +137,13 @@ __device__ __forceinline__ double ll_value(const ulonglong2& r) {
                 rx_[i] = 0ull; ry_[i] = 0ull;                                                                     \
                 if (((pend) >> i) & 1u) ll_load2(ADDR(i), rx_[i], ry_[i]);                                        \
             }                                                                                                     \
+            if (it_ == 0) { AFTER_REQ; }                                                                          \
             _Pragma("unroll") for (int i = 0; i < (NW); ++i)                                                      \
-                if ((((pend) >> i) & 1u) && (unsigned)(rx_[i] >> 32) == (ep_) && (unsigned)(ry_[i] >> 32) == (ep_)) { \
+                if ((((pend) >> i) & 1u) && (unsigned)(rx_[i] >> 32) == EP(i) && (unsigned)(ry_[i] >> 32) == EP(i)) {   \
                     OUT(i, __longlong_as_double((long long)((rx_[i] & 0xffffffffull) | (ry_[i] << 32))));         \
                     (pend) &= ~(1u << i);                                                                         \
                 }                                                                                                 \
-            if (!(pend)) break;                                                                                   \
+            if (!(pend)) { ll_rounds = (int)it_ + 1; break; }                                                     \
             if (it_ > MID_SPIN_LIMIT) __trap();                                                                   \
             if (DYB_LL_SLEEP > 0) __nanosleep(DYB_LL_SLEEP);                                                      \
         }                                                                                                         \
@@ -156,6 +167,9 @@ __device__ __forceinline__ void mid_fma_half(double (&acc)[MID_MPT][2][NQ], cons
 
 // static shared state of a CTA (one instance in the kernel; the exchange functions get a pointer)
 struct MidShared {
+    MidParams  P;                           // copy of the launch parameters: the non-inlined functions read them from shared
+                                            // memory (through a reference to the kernel parameter every read was a generic
+                                            // load from parameter space: 4000 cycles before the first request of a term)
     Ctrl       sctrl;
     PassParams spass[2];
     double     wsc[4][8];
@@ -169,7 +183,8 @@ struct MidShared {
 
 // Decision on term td: scalars of all owners, fixed combination order, identical in every CTA (decide_particle = the code
 // of the two other paths, Taylor.f:194-207 / :102-105).
-__device__ __noinline__ void mid_decide(const MidParams& P, MidShared* sh, int td, bool allow_chain) {
+__device__ __noinline__ void mid_decide(MidShared* sh, int td, bool allow_chain) {
+    const MidParams& P = sh->P;
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int G = P.Gr * P.Gc;
     if (tid >= 128) {
@@ -180,10 +195,13 @@ __device__ __noinline__ void mid_decide(const MidParams& P, MidShared* sh, int t
 #pragma unroll
         for (int i = 0; i < MID_SCU; ++i) if (ob + 16 * i < P.n_own) need |= 1u << i;
         double sv[MID_SCU];
+        int ll_rounds = 0; (void)ll_rounds;
 #define DYB_SC_ADDR(i) (src + (size_t)(ob + 16 * (i)) * 8)
 #define DYB_SC_OUT(i, v) sv[i] = (v)
         unsigned pend = need;
-        DYB_LL_POLL(MID_SCU, pend, epd, DYB_SC_ADDR, DYB_SC_OUT);
+#define DYB_SC_EP(i) epd
+        DYB_LL_POLL(MID_SCU, pend, DYB_SC_EP, DYB_SC_ADDR, DYB_SC_OUT, (void)0);
+#undef DYB_SC_EP
 #undef DYB_SC_ADDR
 #undef DYB_SC_OUT
         double a = 0.0;
@@ -212,129 +230,195 @@ __device__ __noinline__ void mid_decide(const MidParams& P, MidShared* sh, int t
     __syncthreads();
 }
 
-// Owner: collect the partials of the owned indices into val[] (shared memory).
-// Word w = k * E4 + e * 4 + q: source k (0 .. Gc-1: ket partial of block column k; Gc .. Gc+Gr-1: bra partial of block row
-// k - Gc), owned index e, real q.  Thread tid takes the words tid + 256 j, MID_CW per pass, all in flight at once.
+// Owner side of a term, one function:
+//   1. ONE polling batch collects the partials of the owned indices (term t) AND the 8 scalars of every owner (term t-1)
+//      into val[] (shared memory).  Word w < W: w = k * E4 + e * 4 + q -- source k (0 .. Gc-1: ket partial of block column k;
+//      Gc .. Gc+Gr-1: bra partial of block row k - Gc), owned index e, real q; word W + o * 8 + s: scalar s of owner o.
+//      Thread tid takes the words tid + 256 j, MID_CW per pass, all in flight at once.
+//   2. warp 0 takes the decision on term t-1 (decide_particle = the code of the two other paths, Taylor.f:194-207 / :102-105;
+//      fixed combination order, identical in every CTA) while warps 1..7 add up the partials (fixed order);
+//   3. warps 1..7 apply the recurrence and the series sum to the owner state (own: cur, prev, sum, start [2 sides][E][NQ] +
+//      magnitudes [2][E][2]) and publish the new entries; a latched particle skips the update;
+//   4. warp 0 publishes the convergence scalars of the owned indices while warps 1..7 already collect their next input.
+// Returns true when both particles are latched (the series is over; nothing of term t was applied).
 template <int R>
-__device__ __noinline__ void mid_collect(const MidParams& P, double* val, int t) {
-    const int tid = threadIdx.x;
-    const int Gr = P.Gr, Gc = P.Gc, Cnp = P.Cnp, N = P.N;
-    const int E4 = P.E * NQ, W = (Gc + Gr) * E4, o0 = blockIdx.x * P.E;
+__device__ __noinline__ bool mid_owner(MidShared* sh, double* val, double* own, int t) {
+    const MidParams& P = sh->P;
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int Gr = P.Gr, Gc = P.Gc, Cnp = P.Cnp, N = P.N, E = P.E, G = Gr * Gc;
+    const int E4 = E * NQ, W = (Gc + Gr) * E4, o0 = blockIdx.x * E;
+    const int Wt = W + (t > 0 ? P.n_own * 8 : 0);
     const int par = t & 1;
     const unsigned ep = P.epoch0 + t + 1;
-    const int ckstep = MID_THREADS / E4, cremstep = MID_THREADS - ckstep * E4;
-    const int obc0 = o0 / Cnp, obc_next = (obc0 + 1) * Cnp;     // block column of the first owned index, first index of the next one
-    const ulonglong2* pkb = P.pk + (size_t)par * Gr * Gc * R * NQ;
-    const ulonglong2* pbb = P.pb + (size_t)par * Gc * Gr * Cnp * NQ;
-    int k = tid / E4, rem = tid - k * E4;                       // source and (e, q) of the thread's next word
-    for (int w0 = 0; w0 < W; w0 += MID_THREADS * MID_CW) {
-        int off[MID_CW];                                         // word offset from pkb (ket, >= 0) or pbb (bra, stored as ~offset)
-        unsigned pend = 0;
+    {
+        // tables built once per launch: wtab[slot][thread] = 32-bit offset of the thread's word, or (tab16) its
+        // (k << 8 | e * 4 + q) with kt[k] = offset of source k, rt[side][e * 4 + q] = offset of the word inside a source
+        const int* kt = reinterpret_cast<const int*>(own + 4 * 2 * E * NQ + 2 * E * 2);
+        const int* rt = kt + (Gc + Gr);
+        const unsigned short* wtab16 = reinterpret_cast<const unsigned short*>(reinterpret_cast<const char*>(kt) + ((Gc + Gr + 2 * E4) * 4 + 127) / 128 * 128) + tid;
+        const int* wtab32 = kt + tid;
+        const bool tab16 = P.tab16 != 0;
+        const ulonglong2* pkb = P.pk + (size_t)par * Gr * Gc * R * NQ;
+        const ulonglong2* pbb = P.pb + (size_t)par * Gc * Gr * Cnp * NQ;
+        const ulonglong2* scb = P.sc + (size_t)((t + 3) & 3) * G * 8 - W;      // scalars of term t-1, indexed by the word number
+        for (int w0 = 0; w0 < Wt; w0 += MID_THREADS * MID_CW) {
+            int ll_rounds = 0;
+            int off[MID_CW];                                     // word offset from pkb (ket, >= 0) or pbb (bra, stored as ~offset) or scb
+            unsigned pend = 0, scm = 0;                          // scm: the word is a scalar of term t-1
 #pragma unroll
-        for (int j = 0; j < MID_CW; ++j) {
-            const int wj = w0 + j * MID_THREADS + tid;
-            const int g = o0 + (rem >> 2), q = rem & 3;
-            off[j] = 0;
-            if (wj < W && g < N) {
-                pend |= 1u << j;
-                if (k < Gc) {                                    // ket entry g: block row g / R, partial of block column k
-                    const int br = g / R, rr = g - br * R;
-                    off[j] = ((br * Gc + k) * R + rr) * NQ + q;
-                } else {                                         // bra entry g: block column bc (at most two per owner), partial of block row k - Gc
-                    const int bc = obc0 + (g >= obc_next ? 1 : 0), cc = g - bc * Cnp;
-                    off[j] = ~(((bc * Gr + (k - Gc)) * Cnp + cc) * NQ + q);
-                }
+            for (int j = 0; j < MID_CW; ++j) {
+                const int wb = w0 + j * MID_THREADS, wj = wb + tid;
+                off[j] = 0;
+                if (wb >= Wt) continue;                          // uniform: no thread has a word in this slot
+                if (wj < W) {
+                    if (tab16) {
+                        const int kr = wtab16[wb];
+                        if (kr != MID_NO_WORD) {
+                            pend |= 1u << j;
+                            const int k = kr >> 8, isb = k >= Gc;
+                            const int o = kt[k] + rt[(isb ? E4 : 0) + (kr & 255)];
+                            off[j] = isb ? ~o : o;
+                        }
+                    } else {
+                        off[j] = wtab32[wb];
+                        if (off[j] != MID_NO_WORD32) pend |= 1u << j;
+                    }
+                } else if (wj < Wt) { pend |= 1u << j; scm |= 1u << j; off[j] = wj; }
             }
-            k += ckstep; rem += cremstep;
-            if (rem >= E4) { rem -= E4; ++k; }
-        }
-#define DYB_CO_ADDR(j) (off[j] >= 0 ? pkb + off[j] : pbb + ~off[j])
+#define DYB_CO_ADDR(j) (((scm >> (j)) & 1u) ? scb + off[j] : (off[j] >= 0 ? pkb + off[j] : pbb + ~off[j]))
+#define DYB_CO_EP(j) (ep - ((scm >> (j)) & 1u))
 #define DYB_CO_OUT(j, v) val[w0 + (j) * MID_THREADS + tid] = (v)
-        DYB_LL_POLL(MID_CW, pend, ep, DYB_CO_ADDR, DYB_CO_OUT);
+            DYB_MSTAMP(9);
+            DYB_LL_POLL(MID_CW, pend, DYB_CO_EP, DYB_CO_ADDR, DYB_CO_OUT, if (w0 == 0) __syncthreads());
+            DYB_MROUNDS(8, ll_rounds);
 #undef DYB_CO_ADDR
+#undef DYB_CO_EP
 #undef DYB_CO_OUT
+        }
     }
-}
+    DYB_MSTAMP(7);
+    __syncthreads();
 
-// Owner: sums of the collected partials (fixed order), recurrence, series sum, publication of the new entries and of the
-// convergence scalars.  own = owner state in shared memory: cur, prev, sum, start [2 sides][E][NQ] + magnitudes [2][E][2].
-__device__ __noinline__ void mid_update(const MidParams& P, MidShared* sh, const double* val, double* own, int t) {
-    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-    const int Gr = P.Gr, Gc = P.Gc, N = P.N, E = P.E, G = Gr * Gc;
-    const int E4 = E * NQ, o0 = blockIdx.x * E, par = t & 1;
-    const unsigned ep = P.epoch0 + t + 1;
+    // ---- warp 0: decision on term t-1; warps 1..7: sums of the partials.  task = (side, e, q), MID_XT threads, <= 3 each;
+    // the two reals of a complex value sit in neighbouring lanes
+    double hx[3] = {0.0, 0.0, 0.0};
+    if (w == 0) {
+        if (t > 0) {
+            const int s = lane & 7;
+            const double* sv = val + W + s;
+            double a = 0.0;
+            for (int o = lane >> 3; o < P.n_own; o += 4) { const double v = sv[(size_t)o * 8]; a = ((s & 3) < 2) ? fmax(a, v) : a + v; }
+#pragma unroll
+            for (int off = 8; off < 32; off <<= 1) {
+                const double o = __shfl_xor_sync(0xffffffffu, a, off);
+                a = ((s & 3) < 2) ? fmax(a, o) : a + o;
+            }
+            double fin[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) fin[q] = __shfl_sync(0xffffffffu, a, 4 * (lane & 1) + q);
+            // stop_chain as of the previous term: the same in every CTA
+            if (lane < 2) decide_particle(sh->sctrl.part[lane], sh->spass[(t - 1) & 1].part[lane], fin, !sh->stop_chain);
+            __syncwarp();
+            if (lane == 0 && ((sh->sctrl.part[0].latched && !sh->sctrl.part[0].ok) || (sh->sctrl.part[1].latched && !sh->sctrl.part[1].ok))) sh->stop_chain = 1;
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int task = (tid - 32) + u * MID_XT;
+            const int side = task >= E4 ? 1 : 0;
+            const int eq = task - side * E4;
+            if (task < 2 * E4 && o0 + (eq >> 2) < N) {
+                const double* vp = val + (side ? Gc * E4 : 0) + eq;
+                const int np = side ? Gr : Gc;
+                double a = 0.0;
+                int kk = 0;
+                for (; kk + 8 <= np; kk += 8) {                  // eight loads in flight, added in the fixed order
+                    double v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = vp[(size_t)(kk + i) * E4];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) a += v[i];
+                }
+                for (; kk < np; ++kk) a += vp[(size_t)kk * E4];
+                hx[u] = a;
+            }
+        }
+    }
+    __syncthreads();
+    if (sh->sctrl.part[0].latched && sh->sctrl.part[1].latched) return true;
+    DYB_MSTAMP(3);
+
     double* ocur = own;
     double* oprv = ocur + 2 * E * NQ;
     double* osum = oprv + 2 * E * NQ;
     double* opsi = osum + 2 * E * NQ;
     double* omag = opsi + 2 * E * NQ;
-    // task = (side, e, q); the two reals of a complex value sit in neighbouring lanes
-#pragma unroll 1
-    for (int task = tid; task < ((2 * E4 + 31) & ~31); task += MID_THREADS) {
-        const int side = task >= E4 ? 1 : 0;
-        const int eq = task - side * E4, e = eq >> 2, q = eq & 3;
-        const bool ok = task < 2 * E4 && o0 + e < N;
-        double hx = 0.0;
-        if (ok) {
-            const double* vp = val + (side ? Gc * E4 : 0) + eq;
-            const int np = side ? Gr : Gc;
-            for (int kk = 0; kk < np; ++kk) hx += vp[(size_t)kk * E4];          // fixed order
-        }
-        const double ho = __shfl_xor_sync(0xffffffffu, hx, 1);  // the other real of the complex value
-        const int p = q >> 1, cmp = q & 1;
-        const Cx hc = cmp ? Cx{ho, hx} : Cx{hx, ho};
-        const size_t o = ((size_t)side * E + e) * NQ + 2 * p;
-        double xnew = 0.0, n_cur = 0.0, n_prv = 0.0, n_sum = 0.0, n_psi = 0.0, mag = 0.0;
-        bool upd = false, beg = false;
-        if (ok) {
-            const PartPass& pa = sh->spass[par].part[p];
-            double2 cur = *reinterpret_cast<const double2*>(ocur + o);
-            xnew = cmp ? cur.y : cur.x;
-            if (pa.active && !sh->sctrl.part[p].latched) {
-                double2 sum = *reinterpret_cast<const double2*>(osum + o);
-                if (pa.begin) {                                  // next steady sub-step: adopt the previous sum (Taylor.f:105,:83-86);
-                    beg = true;                                  // hx was computed from it (x of the chain term)
-                    n_psi = cmp ? sum.y : sum.x;
-                    cur = sum;
-                    const Cx s0 = cmul({pa.s_re, pa.s_im}, {sum.x, sum.y});
-                    sum = make_double2(s0.re, s0.im);
-                }
-                Cx y = cmul({pa.alpha_re, pa.alpha_im}, hc);
-                if (pa.three_term) {
-                    const Cx bc = cmul({pa.beta_re, pa.beta_im}, {cur.x, cur.y});
-                    y.re += bc.re; y.im += bc.im;
-                    if (pa.gamma != 0.0) {
-                        const double2 prv = *reinterpret_cast<const double2*>(oprv + o);
-                        y.re += pa.gamma * prv.x; y.im += pa.gamma * prv.y;
+    if (w > 0) {
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int task = (tid - 32) + u * MID_XT;
+            if (task - lane >= 2 * E4) continue;                 // warp-uniform: no task of this warp in this round
+            const int side = task >= E4 ? 1 : 0;
+            const int eq = task - side * E4, e = eq >> 2, q = eq & 3;
+            const bool ok = task < 2 * E4 && o0 + e < N;
+            const double ho = __shfl_xor_sync(0xffffffffu, hx[u], 1);           // the other real of the complex value
+            const int p = q >> 1, cmp = q & 1;
+            const Cx hc = cmp ? Cx{ho, hx[u]} : Cx{hx[u], ho};
+            const size_t o = ((size_t)side * E + e) * NQ + 2 * p;
+            double xnew = 0.0, n_cur = 0.0, n_prv = 0.0, n_sum = 0.0, n_psi = 0.0, mag = 0.0;
+            bool upd = false, beg = false;
+            if (ok) {
+                const PartPass& pa = sh->spass[par].part[p];
+                double2 cur = *reinterpret_cast<const double2*>(ocur + o);
+                xnew = cmp ? cur.y : cur.x;
+                if (pa.active && !sh->sctrl.part[p].latched) {
+                    double2 sum = *reinterpret_cast<const double2*>(osum + o);
+                    if (pa.begin) {                              // next steady sub-step: adopt the previous sum (Taylor.f:105,:83-86);
+                        beg = true;                              // hx was computed from it (x of the chain term)
+                        n_psi = cmp ? sum.y : sum.x;
+                        cur = sum;
+                        const Cx s0 = cmul({pa.s_re, pa.s_im}, {sum.x, sum.y});
+                        sum = make_double2(s0.re, s0.im);
                     }
+                    Cx y = cmul({pa.alpha_re, pa.alpha_im}, hc);
+                    if (pa.three_term) {
+                        const Cx bc = cmul({pa.beta_re, pa.beta_im}, {cur.x, cur.y});
+                        y.re += bc.re; y.im += bc.im;
+                        if (pa.gamma != 0.0) {
+                            const double2 prv = *reinterpret_cast<const double2*>(oprv + o);
+                            y.re += pa.gamma * prv.x; y.im += pa.gamma * prv.y;
+                        }
+                    }
+                    Cx tt = y;
+                    if (pa.scale_term) tt = cmul({pa.c_re, pa.c_im}, y);
+                    const double nw_re = sum.x + tt.re, nw_im = sum.y + tt.im;
+                    const double dx = nw_re - sum.x, dy = nw_im - sum.y;
+                    mag = dx * dx + dy * dy;                     // |new - old|^2 (isConverged, Taylor.f:290-303); root after the max
+                    upd = true;
+                    n_prv = cmp ? cur.y : cur.x;
+                    // what the next product multiplies: the new vector, or (speculatively) the sum the next sub-step starts from
+                    n_cur = pa.chain ? (cmp ? nw_im : nw_re) : (cmp ? y.im : y.re);
+                    n_sum = cmp ? nw_im : nw_re;
+                    xnew = n_cur;
                 }
-                Cx tt = y;
-                if (pa.scale_term) tt = cmul({pa.c_re, pa.c_im}, y);
-                const double nw_re = sum.x + tt.re, nw_im = sum.y + tt.im;
-                const double dx = nw_re - sum.x, dy = nw_im - sum.y;
-                mag = dx * dx + dy * dy;                         // |new - old|^2 (isConverged, Taylor.f:290-303); root after the max
-                upd = true;
-                n_prv = cmp ? cur.y : cur.x;
-                // what the next product multiplies: the new vector, or (speculatively) the sum the next sub-step starts from
-                n_cur = pa.chain ? (cmp ? nw_im : nw_re) : (cmp ? y.im : y.re);
-                n_sum = cmp ? nw_im : nw_re;
-                xnew = n_cur;
+            }
+            __syncwarp();                                        // both lanes of a complex value have read the old state
+            if (ok) {
+                if (upd) {
+                    oprv[o + cmp] = n_prv; ocur[o + cmp] = n_cur; osum[o + cmp] = n_sum;
+                    if (beg) opsi[o + cmp] = n_psi;
+                }
+                if (cmp == 0) omag[((size_t)side * E + e) * 2 + p] = mag;
+                ll_store(P.xx + (((size_t)((t + 1) & 1) * 2 + side) * N + (o0 + e)) * NQ + q, xnew, ep);
             }
         }
-        __syncwarp();                                            // both lanes of a complex value have read the old state
-        if (ok) {
-            if (upd) {
-                oprv[o + cmp] = n_prv; ocur[o + cmp] = n_cur; osum[o + cmp] = n_sum;
-                if (beg) opsi[o + cmp] = n_psi;
-            }
-            if (cmp == 0) omag[((size_t)side * E + e) * 2 + p] = mag;
-            ll_store(P.xx + (((size_t)((t + 1) & 1) * 2 + side) * N + (o0 + e)) * NQ + q, xnew, ep);
-        }
+        asm volatile("bar.arrive 1, 256;" ::: "memory");         // the owner state of term t is complete (warp 0 waits for it)
+        return false;
     }
-    __syncthreads();
 
-    // scalars of the owned indices
-    if (w == 0 && blockIdx.x < P.n_own) {
+    // ---- warp 0: scalars of the owned indices
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (blockIdx.x < P.n_own) {
         double v[4] = {0.0, 0.0, 0.0, 0.0};                      // max_b, max_k, dot_re, dot_im of particle (lane & 1)
         for (int idx = lane; idx < E * 2; idx += 32) {
             const int e = idx >> 1, p = idx & 1;
@@ -357,13 +441,15 @@ __device__ __noinline__ void mid_update(const MidParams& P, MidShared* sh, const
             ll_store(dst + 2, v[2], ep);       ll_store(dst + 3, v[3], ep);
         }
     }
+    return false;
 }
 
-// Consumer: the Cnp ket entries and the R bra entries the next product multiplies -> sx (sxk [Cnp][NQ] then sxb [R][NQ],
-// contiguous: word wi of the list is double wi of that array)
+// Consumer (warps 1..7): the Cnp ket entries and the R bra entries the next product multiplies -> sx (sxk [Cnp][NQ] then
+// sxb [R][NQ], contiguous: word wi of the list is double wi of that array)
 template <int R>
-__device__ __noinline__ void mid_consume(const MidParams& P, double* sx, int t) {
-    const int tid = threadIdx.x;
+__device__ __noinline__ void mid_consume(MidShared* sh, double* sx, int t) {
+    const MidParams& P = sh->P;
+    const int ct = threadIdx.x - 32;
     const int Cnp = P.Cnp, N = P.N;
     const int bi = blockIdx.x / P.Gc, bj = blockIdx.x % P.Gc;
     const int row0 = bi * R, col0 = bj * Cnp;
@@ -372,15 +458,18 @@ __device__ __noinline__ void mid_consume(const MidParams& P, double* sx, int t) 
     const ulonglong2* xb_src = P.xx + (((size_t)((t + 1) & 1) * 2 + 1) * N + row0) * NQ - (size_t)Cnp * NQ;    // indexed by wi
     const int nwk = min(Cnp, max(0, N - col0)) * NQ, nwb = min(R, max(0, N - row0)) * NQ;
     unsigned pend = 0;
+    int ll_rounds = 0; (void)ll_rounds;
 #pragma unroll
     for (int u = 0; u < MID_XU; ++u) {
-        const int wi = tid + u * MID_THREADS;
+        const int wi = ct + u * MID_XT;
         if (wi < Cnp * NQ ? wi < nwk : wi - Cnp * NQ < nwb) pend |= 1u << u;
     }
-#define DYB_X_ADDR(u) (((tid + (u) * MID_THREADS) < Cnp * NQ ? xk_src : xb_src) + (tid + (u) * MID_THREADS))
-#define DYB_X_OUT(u, v) sx[tid + (u) * MID_THREADS] = (v)
-    DYB_LL_POLL(MID_XU, pend, ep, DYB_X_ADDR, DYB_X_OUT);
+#define DYB_X_ADDR(u) (((ct + (u) * MID_XT) < Cnp * NQ ? xk_src : xb_src) + (ct + (u) * MID_XT))
+#define DYB_X_EP(u) ep
+#define DYB_X_OUT(u, v) sx[ct + (u) * MID_XT] = (v)
+    DYB_LL_POLL(MID_XU, pend, DYB_X_EP, DYB_X_ADDR, DYB_X_OUT, (void)0);
 #undef DYB_X_ADDR
+#undef DYB_X_EP
 #undef DYB_X_OUT
 }
 
@@ -391,7 +480,7 @@ mid_series_kernel_t(const __grid_constant__ CUtensorMap tmap, const __grid_const
     constexpr int WC = MID_WARPS / WR, TC = WC * MID_CPW, R = WR * MID_SUB;
     static_assert(R * TC * 8 == MID_STAGE_BYTES, "stage size");
     extern __shared__ __align__(128) uint8_t msm[];
-    const MidSmem L(P.ST, R, P.Cnp, P.E, P.Gr + P.Gc);
+    const MidSmem L(P.ST, R, P.Cnp, P.E, P.Gr + P.Gc, P.n_own, P.tab16);
     uint64_t* bar_full  = reinterpret_cast<uint64_t*>(msm + L.bars);
     uint64_t* bar_empty = bar_full + 8;
     double* U    = reinterpret_cast<double*>(msm + L.U);
@@ -427,6 +516,7 @@ mid_series_kernel_t(const __grid_constant__ CUtensorMap tmap, const __grid_const
         for (int s = 0; s < ST; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], MID_WARPS); }
         fence_barrier_init();
         for (int q = 0; q < ST && q < total_tiles; ++q) issue(q, q % NT);
+        sh.P = P;
         sh.sctrl = *P.ctrl;
         sh.stop_chain = 0;
     }
@@ -455,6 +545,45 @@ mid_series_kernel_t(const __grid_constant__ CUtensorMap tmap, const __grid_const
         *reinterpret_cast<double2*>(oprv + o) = make_double2(0.0, 0.0);
         *reinterpret_cast<double2*>(osum + o) = sum;
         *reinterpret_cast<double2*>(opsi + o) = cur;
+    }
+
+    // ---- tables of the owner's collect (word w = k * E4 + e * 4 + q; source k: ket partial of block column k < Gc, bra partial
+    // of block row k - Gc; thread tid takes the words tid + 256 j), built once per launch: the per-term address arithmetic
+    // was 1300 instructions per thread (3400 cycles per term).  Offsets are inside one parity of pk / pb.
+    {
+        const int E4 = E * NQ, W = (Gc + Gr) * E4, Wr = (W + MID_THREADS - 1) / MID_THREADS * MID_THREADS;
+        int* kt = reinterpret_cast<int*>(msm + L.tab);
+        if (P.tab16) {
+            int* rt = kt + (Gc + Gr);
+            unsigned short* wtab = reinterpret_cast<unsigned short*>(reinterpret_cast<char*>(kt) + ((Gc + Gr + 2 * E4) * 4 + 127) / 128 * 128);
+            for (int k = tid; k < Gc + Gr; k += MID_THREADS) kt[k] = k < Gc ? k * R * NQ : (k - Gc) * Cnp * NQ;
+            for (int f = tid; f < 2 * E4; f += MID_THREADS) {
+                const int side = f >= E4, rem = f - side * E4, g = o0 + (rem >> 2), q = rem & 3;
+                int v = 0;
+                if (g < N) {
+                    if (!side) { const int br = g / R; v = (br * Gc * R + (g - br * R)) * NQ + q; }           // pk[par][br][k][rr][q]
+                    else       { const int bc = g / Cnp; v = (bc * Gr * Cnp + (g - bc * Cnp)) * NQ + q; }     // pb[par][bc][k - Gc][cc][q]
+                }
+                rt[f] = v;
+            }
+            for (int wj = tid; wj < Wr; wj += MID_THREADS) {
+                int v = MID_NO_WORD;
+                if (wj < W) { const int k = wj / E4, rem = wj - k * E4; if (o0 + (rem >> 2) < N) v = (k << 8) | rem; }
+                wtab[wj] = (unsigned short)v;
+            }
+        } else {
+            for (int wj = tid; wj < Wr; wj += MID_THREADS) {
+                int v = MID_NO_WORD32;
+                if (wj < W) {
+                    const int k = wj / E4, rem = wj - k * E4, g = o0 + (rem >> 2), q = rem & 3;
+                    if (g < N) {
+                        if (k < Gc) { const int br = g / R; v = ((br * Gc + k) * R + (g - br * R)) * NQ + q; }
+                        else        { const int bc = g / Cnp; v = ~(((bc * Gr + (k - Gc)) * Cnp + (g - bc * Cnp)) * NQ + q); }
+                    }
+                }
+                kt[wj] = v;
+            }
+        }
     }
 
     bool decided_all = false;
@@ -630,32 +759,21 @@ mid_series_kernel_t(const __grid_constant__ CUtensorMap tmap, const __grid_const
         }
         DYB_MSTAMP(2);
 
-        // ---------------------------------------------------------------- 2. decision on term t-1 (identical in every CTA)
-        // (its scalars were published a whole product ago: one round trip)
-        if (t > 0) {
-            mid_decide(P, &sh, t - 1, !sh.stop_chain);           // stop_chain as of the previous term: the same in every CTA
-            if (sh.sctrl.part[0].latched && sh.sctrl.part[1].latched) { decided_all = true; break; }
-            if (tid == 0 && ((sh.sctrl.part[0].latched && !sh.sctrl.part[0].ok) || (sh.sctrl.part[1].latched && !sh.sctrl.part[1].ok))) sh.stop_chain = 1;
-        }
-        DYB_MSTAMP(3);
-        __syncthreads();                                         // the ket rows staged in U have been published (t = 0: no decision)
+        // (the ket rows staged in U are overwritten by what the owner collects: mid_owner synchronises after its first request)
 
-        // ---------------------------------------------------------------- 3. owner: collect, update, publish
-        mid_collect<R>(P, U, t);
-        DYB_MSTAMP(7);
-        __syncthreads();
-        mid_update(P, &sh, U, ocur, t);
+        // ---------------------------------------------------------------- 2. owner: collect, decide on term t-1, update, publish
+        if (mid_owner<R>(&sh, U, ocur, t)) { decided_all = true; break; }
         DYB_MSTAMP(4);
 
-        // ---------------------------------------------------------------- 4. consumer: the entries the next product multiplies
-        if (t + 1 < P.n_steps) mid_consume<R>(P, sxk, t);
+        // ---------------------------------------------------------------- 3. consumer: the entries the next product multiplies
+        if (w > 0 && t + 1 < P.n_steps) mid_consume<R>(&sh, sxk, t);
         DYB_MSTAMP(5);
         __syncthreads();
         DYB_MSTAMP(6);
     }
 
     // ---- decision on the last term, unless the series was decided on the way
-    if (!decided_all && t > 0) mid_decide(P, &sh, t - 1, true);
+    if (!decided_all && t > 0) mid_decide(&sh, t - 1, true);
 
     // ---- never exit with bulk copies in flight to our shared memory: tiles qc .. min(total, qc + ST) - 1 were issued
     if (tid == 0) {

@@ -456,7 +456,7 @@ static int run_series_resident(dyb_ctx* c, const std::vector<PassParams>& passes
 // Blocking (pure host arithmetic, exported as dyb_mid_plan for the CPU tests): R = 512 rows per CTA, Gr = ceil(N / R) block
 // rows, Gc = min(64, sm_count / Gr) block columns of Cnp = roundup(ceil(N / Gc), 8) columns, Gc = ceil(N / Cnp); every CTA
 // owns E = ceil(N / (Gr Gc)) consecutive indices of the vectors (n_own = ceil(N / E) CTAs own at least one).
-struct MidPlan { int WR, R, TC, Gr, Gc, Cnp, NT, ST, E, n_own; size_t smem; bool fits; };
+struct MidPlan { int WR, R, TC, Gr, Gc, Cnp, NT, ST, E, n_own, tab16; size_t smem; bool fits; };
 static MidPlan make_mid_plan(int N, int sm_count, size_t smem_optin, size_t static_smem) {
     MidPlan m;
     memset(&m, 0, sizeof m);
@@ -472,11 +472,17 @@ static MidPlan make_mid_plan(int N, int sm_count, size_t smem_optin, size_t stat
     m.E = (N + G - 1) / G;
     m.n_own = (N + m.E - 1) / m.E;
     const size_t budget = std::min((size_t)MID_SMEM_MAX, smem_optin > static_smem ? smem_optin - static_smem : 0);
-    for (m.ST = MID_MAX_ST; m.ST >= 2; --m.ST) { m.smem = (size_t)MidSmem(m.ST, m.R, m.Cnp, m.E, m.Gr + m.Gc).total; if (m.smem <= budget) break; }
+    // the collect table with 32-bit offsets is the faster one; the 16-bit form takes over when it saves a ring stage below 5
+    int st32 = MID_MAX_ST, st16 = MID_MAX_ST;
+    while (st32 >= 2 && (size_t)MidSmem(st32, m.R, m.Cnp, m.E, m.Gr + m.Gc, m.n_own, 0).total > budget) --st32;
+    while (st16 >= 2 && (size_t)MidSmem(st16, m.R, m.Cnp, m.E, m.Gr + m.Gc, m.n_own, 1).total > budget) --st16;
+    m.tab16 = (st16 > st32 && st32 < 4) ? 1 : 0;
+    m.ST = m.tab16 ? st16 : st32;
+    m.smem = (size_t)MidSmem(std::max(m.ST, 1), m.R, m.Cnp, m.E, m.Gr + m.Gc, m.n_own, m.tab16).total;
     // an owner's indices span at most two block columns (E <= Cnp); the 8 scalar slots of <= 16 * MID_SCU owners; a consumer's
     // R + Cnp entries in MID_XU words per thread; the bra partials of the WR row groups in the union region
     m.fits = m.ST >= 2 && G <= sm_count && m.E <= MID_MAX_E && m.E <= m.Cnp && m.n_own <= 16 * MID_SCU
-             && (m.Cnp + m.R) * NQ <= MID_THREADS * MID_XU && (size_t)m.WR * m.Cnp * NQ * 8 <= (size_t)MID_U_BYTES;
+             && (m.Cnp + m.R) * NQ <= MID_XT * MID_XU && 2 * m.E * NQ <= 3 * MID_XT && (size_t)m.WR * m.Cnp * NQ * 8 <= (size_t)MID_U_BYTES;
     return m;
 }
 static bool mid_ok(const dyb_ctx* c, bool refgpu) {
@@ -521,13 +527,13 @@ static int run_series_mid(dyb_ctx* c, const std::vector<PassParams>& passes) {
             std::vector<long long> h(n_mprof);
             CK(cudaStreamSynchronize(c->stream));
             CK(cudaMemcpy(h.data(), d_mprof, n_mprof * 8, cudaMemcpyDeviceToHost));
-            const char* name[8] = {"product", "reduce+publish", "decide", "collect", "update+publish-x", "sync+scalars+consume-wait", "sync2", "loop-gap"};
-            const int order[9] = {0, 1, 2, 3, 7, 4, 5, 6, 0};      // stamp order inside a term; the last one is stamp 0 of the next term
-            double mean[8] = {0}, mx[8] = {0}, extra[2] = {0, 0};
+            const char* name[8] = {"product", "reduce+publish", "collect", "decision+sums", "update+scalars (thread 0 = scalar warp)", "-", "consume-wait", "loop-gap"};
+            const int order[9] = {0, 1, 2, 7, 3, 4, 5, 6, 0};      // stamp order inside a term; the last one is stamp 0 of the next term
+            double mean[8] = {0}, mx[8] = {0}, rounds = 0, setup = 0;
             const int nt = std::min(n, MAX_SERIES_TERMS);
             for (int t = 1; t + 1 < nt; ++t) for (int b = 0; b < mgrid; ++b) {
                 const long long* q = &h[((size_t)t * mgrid + b) * 16];
-                extra[0] += double(q[9] - q[2]); extra[1] += double(q[10] - q[9]);
+                rounds += double(q[8]); setup += double(q[9] - q[2]);
                 for (int i = 0; i < 8; ++i) {
                     const long long nx = (i < 7) ? q[order[i + 1]] : h[((size_t)(t + 1) * mgrid + b) * 16];
                     const double d = double(nx - q[order[i]]);
@@ -537,7 +543,7 @@ static int run_series_mid(dyb_ctx* c, const std::vector<PassParams>& passes) {
             fprintf(stderr, "mid_prof N=%d grid=%dx%d Cnp=%d NT=%d ST=%d terms=%d:", c->N, P.Gr, P.Gc, P.Cnp, P.NT, P.ST, n);
             for (int i = 0; i < 8; ++i) fprintf(stderr, "  %s mean %.0f max %.0f cyc;", name[i], mean[i] / ((double)std::max(1, nt - 2) * mgrid), mx[i]);
             const double dn = (double)std::max(1, nt - 2) * mgrid;
-            fprintf(stderr, "  [thread 128: reaches the decision %.0f after the publication, its scalar collect %.0f]\n", extra[0] / dn, extra[1] / dn);
+            fprintf(stderr, "  [thread 0 collect: %.2f polling rounds, %.0f cycles from the publication to the first request]\n", rounds / dn, setup / dn);
         }
     }
 #endif
@@ -1062,12 +1068,12 @@ int dyb_resident_plan(int N, int sm_count, int64_t smem_optin, int64_t* out6) {
 
 // Host-only: the blocking of the streamed one-launch series kernel (mid.cuh).  out12 = {block rows R, tile columns TC, grid rows
 // Gr, grid columns Gc, block columns Cnp, tiles per term, ring stages, indices per owner E, owner CTAs, words an owner collects
-// per term, dynamic smem bytes, fits (0/1)}.
+// per term (negative: the collect table is the 16-bit one), dynamic smem bytes, fits (0/1)}.
 int dyb_mid_plan(int N, int sm_count, int64_t smem_optin, int64_t* out12) {
     if (N <= 0 || sm_count <= 0 || smem_optin <= 0 || !out12) return fail(DYB_EINVAL, "bad argument");
     const MidPlan m = make_mid_plan(N, sm_count, (size_t)smem_optin, 2048);
     out12[0] = m.R; out12[1] = m.TC; out12[2] = m.Gr; out12[3] = m.Gc; out12[4] = m.Cnp; out12[5] = m.NT; out12[6] = m.ST;
-    out12[7] = m.E; out12[8] = m.n_own; out12[9] = (int64_t)(m.Gr + m.Gc) * m.E * NQ;
+    out12[7] = m.E; out12[8] = m.n_own; out12[9] = (int64_t)(m.Gr + m.Gc) * m.E * NQ * (m.tab16 ? -1 : 1);
     out12[10] = (int64_t)m.smem; out12[11] = m.fits ? 1 : 0;
     return DYB_OK;
 }
@@ -1227,7 +1233,7 @@ int dyb_create(dyb_ctx** out, int device, int N, int row0, int n_rows) {
             MidParams& P = c->mid_P;
             memset(&P, 0, sizeof P);
             P.N = N; P.Gr = mp.Gr; P.Gc = mp.Gc; P.Cnp = mp.Cnp; P.NT = mp.NT; P.ST = mp.ST;
-            P.E = mp.E; P.n_own = mp.n_own;
+            P.E = mp.E; P.n_own = mp.n_own; P.tab16 = mp.tab16;
             const double bytes = 8.0 * (double)c->ld * N;
             P.l2_frac = c->mid_l2_mb <= 0.0 ? 0.f : (float)std::min(1.0, c->mid_l2_mb * 1.0e6 / bytes);
             c->mid_smem = mp.smem;

@@ -163,7 +163,7 @@ int  dyb_resident_plan(int N, int sm_count, int64_t smem_optin_bytes, int64_t* o
 /* Host-only: blocking of the streamed one-launch series kernel (DYB_SERIES_MID) for an N x N operator: a Gr x Gc grid of
  * CTAs, CTA (bi, bj) owns rows [bi*R, bi*R+R) x columns [bj*Cnp, bj*Cnp+Cnp) of H' and the E consecutive vector indices
  * starting at (bi*Gc + bj)*E.  out12 = {R, tile columns, Gr, Gc, Cnp, tiles per term, ring stages, E, owner CTAs, words an
- * owner collects per term, dynamic smem bytes, fits (0/1)}. */
+ * owner collects per term (negative: its collect table holds 16-bit pairs), dynamic smem bytes, fits (0/1)}. */
 int  dyb_mid_plan(int N, int sm_count, int64_t smem_optin_bytes, int64_t* out12);
 
 /* Host-only: the tau of every remaining sub-step of the steady loop (Taylor.f:81-126: t += tau*h_bar, a last shorter

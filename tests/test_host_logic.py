@@ -95,8 +95,8 @@ def test_mid_plan_blocking():
     """Host arithmetic of the streamed one-launch series kernel (csrc/mid.cuh): the Gr x Gc blocking covers the operator with
     no empty block row or column and at most one CTA per SM; block columns are whole tiles; every vector index has exactly ONE
     owner CTA (E consecutive indices each, spanning at most two block columns); at most 64 ket partials per entry; a
-    consumer's R + Cnp entries fit 16 words per thread; the ring, the union region (bra partials of the row groups, the
-    staged ket rows, the words an owner collects), the consumer copy of x and the owner state fit the opt-in shared memory."""
+    consumer's R + Cnp entries fit 19 words per thread of warps 1..7; the ring, the union region (bra partials of the row groups, the
+    staged ket rows, the partials and scalars an owner collects), the consumer copy of x and the owner state fit the opt-in shared memory."""
     from dynemol_b200 import api
     for N in [257, 300, 512, 520, 600, 640, 700, 1825, 2000, 2048, 2304, 2592, 3000, 3333, 4096, 4608, 5000, 5632, 6144]:
         p = api.mid_plan(N)
@@ -108,13 +108,16 @@ def test_mid_plan_blocking():
         assert Gr * R >= N > (Gr - 1) * R and Gc * Cnp >= N > (Gc - 1) * Cnp
         assert E * Gr * Gc >= N and n_own == -(-N // E) and n_own <= Gr * Gc and (n_own - 1) * E < N and E <= min(64, Cnp)
         assert p["collect_words"] == (Gr + Gc) * E * 4
-        assert (Cnp + R) * 4 <= 16 * 256
-        union = max(32768, -(-p["collect_words"] * 8 // 128) * 128)
+        assert (Cnp + R) * 4 <= 19 * 224 and 2 * E * 4 <= 3 * 224
+        slots = -(-p["collect_words"] // 256)
+        table = (-(-(Gr + Gc + 8 * E) * 4 // 128) * 128 + slots * 512) if p["table16"] else slots * 1024
+        union = max(32768, -(-(p["collect_words"] + 8 * n_own) * 8 // 128) * 128)
         assert 2 * Cnp * 32 <= 32768 and R * 32 <= 32768
         assert 2 <= p["stages"] <= 5 and p["smem_bytes"] <= 227 * 1024 - 2048
-        assert p["smem_bytes"] == p["stages"] * 32768 + 128 + union + 32 * (R + Cnp) + E * (4 * 2 * 32 + 32)
+        assert p["smem_bytes"] == p["stages"] * 32768 + 128 + union + 32 * (R + Cnp) + E * (4 * 2 * 32 + 32) + table
     assert api.mid_plan(4096)["grid_rows"] == 8 and api.mid_plan(4096)["grid_cols"] == 18 and api.mid_plan(4096)["block_cols"] == 232
     assert api.mid_plan(2048)["grid_cols"] == 37 and api.mid_plan(2048)["stages"] == 5 and api.mid_plan(2048)["owned"] == 14
+    assert api.mid_plan(2048)["table16"] == 0 and api.mid_plan(6144)["table16"] == 1 and api.mid_plan(6144)["stages"] == 4
     for N in (7168, 8192, 16384):     # blocks wider than 512 columns: the consumer copy and the union region overflow;
         assert api.mid_plan(N)["fits"] == 0       # the two-launch path (>= 80 % of the HBM peak there) takes over
 
