@@ -2,8 +2,9 @@
 reach ("no trajectory-level parity on the streaming (TMA) path and none at config-2 size", "N=16384 has no
 oracle comparison for propagate").
 
-  * 100 nuclear steps with moving nuclei at N = 2304 (launch-per-term path: TMA dual product + fused epilogue) and at
-    N = 900 (BASELINE config 2 size, shared-memory-resident series kernel with the chained steady loop): per step the
+  * 100 nuclear steps with moving nuclei at N = 2304 (twice: the launch-per-term path -- TMA dual product + fused epilogue --
+    and the streamed one-launch series kernel of csrc/mid.cuh that DYB_SERIES_AUTO selects there, with the chained steady
+    loop) and at N = 900 (BASELINE config 2 size, shared-memory-resident series kernel with the chained steady loop): per step the
     product forms H' = S^-1 h on the device from the host-built S, h, propagates electron and hole with the carried-over
     tau of ElHl_Chebyshev.f:174-187 and reduces the fragment populations on the device; the oracle propagates the same
     packets with the same H' (Taylor.f:35-219) and reduces them on the host (data_output.f:242-263).
@@ -38,15 +39,18 @@ def events3(tr):
     return [(e[0], e[1], e[2]) for e in tr.events()]
 
 
-@pytest.mark.parametrize("N,dt,series", [(2304, 5e-7, 1), (900, 2e-6, 3)])
-def test_hundred_step_trajectory_against_oracle(api, oracle_mod, N, dt, series):
+@pytest.mark.parametrize("N,dt,force,series", [(2304, 5e-7, 1, 1), (2304, 5e-7, 0, 5), (900, 2e-6, 0, 3)])
+def test_hundred_step_trajectory_against_oracle(api, oracle_mod, N, dt, force, series):
     n_steps = 100
     pos, species = syn.lattice(N // 4, 1234 + N)
     S0, _ = syn.workload_at(pos, species)
     _, Psi_bra, Psi_ket = syn.packets(S0, N)
     frag = syn.fragments(N)
     P = api.Propagator(N)
-    assert P.info()["series_kernel"] == series            # 1: launch per term (TMA path), 3: resident series kernel
+    if force:
+        P.set_series_kernel(force)
+    # 1: launch per term (TMA path, forced), 5: streamed one-launch kernel (AUTO), 3: resident series kernel (AUTO)
+    assert P.info()["series_kernel"] == series
     P.set_packets(Psi_bra, Psi_ket)
     o_bra = Psi_bra.copy(order="F"); o_ket = Psi_ket.copy(order="F")
     tau_max = dt / H_BAR
