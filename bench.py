@@ -233,6 +233,10 @@ def run_ours_single(args):
     if N == 16384 and not args.skip_small:
         small = small_operator(args)
 
+    mid = None
+    if N == 16384 and not args.skip_small:
+        mid = mid_operator(args)
+
     n65536 = None
     if N == 16384 and not args.skip_65k:
         n65536 = single_gpu_65536(P, args)
@@ -244,7 +248,7 @@ def run_ours_single(args):
                        "terms_per_step": TERMS_PER_STEP, "l2": "inputs larger than L2 (H' = %.2f GB per pass)" % (alg_bytes / 1e9),
                        "kernel_variant": args.kernel, "grid": info["grid"], "tiles": info["tiles"], "build": build_info},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "n65536_single_gpu": n65536, "small_operator": small}
+            "n65536_single_gpu": n65536, "small_operator": small, "mid_operator": mid}
     print(json.dumps(line))
 
 
@@ -276,6 +280,40 @@ def small_operator(args, N=900):
             out[key]["taylor_step_ms"] = round((time.perf_counter() - t0) / 5 * 1e3, 3)
             out[key]["passes_per_step"] = P.info()["passes_last"]; out[key]["launches_per_step"] = (P.launch_count() - l0) // 5
         P.close()
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:      # the headline line must survive a failure of the side measurement
+        return {"error": repr(e)[:200]}
+
+
+def mid_operator(args, sizes=(2048, 4096)):
+    """Side measurement in the size range of real Dynemol QM regions (1824 < N <= 6144): the same 24-term series through
+    the two-launch path and through the streamed one-launch series kernel (csrc/mid.cuh: H' streamed per term by a TMA ring
+    that runs across the terms, barrier-free exchange through epoch-tagged words), which is what the library selects by
+    itself there.  H' is a dense surrogate operator generated on the device (only the time per term is measured)."""
+    import torch
+    from dynemol_b200 import api
+    out = {"unit": "us per el+hole term", "series_terms": TERMS_PER_STEP, "steps": 100}
+    try:
+        for N in sizes:
+            g = torch.Generator(device="cuda").manual_seed(N)
+            H = torch.randn((N, N), device="cuda", dtype=torch.float64, generator=g) / np.sqrt(N)
+            rng = np.random.default_rng(1)
+            x = (rng.standard_normal((N, 2)) + 1j * rng.standard_normal((N, 2))) / np.sqrt(N)
+            P = api.Propagator(N)
+            P.upload_hprime_device(H.data_ptr(), N)
+            P.set_packets(x, x.conj())
+            row = {"hbm_time_of_one_pass_us": round(8.0 * N * N / (measured_peak_gbs()[0] * 1e9) * 1e6, 2)}
+            for kind in ("term", "auto"):
+                P.set_series_kernel(kind)
+                for _ in range(3):
+                    P.run_terms(1e-4, TERMS_PER_STEP)
+                ms, _ = P.run_terms(1e-4, TERMS_PER_STEP * 100)
+                key = "two_launch" if kind == "term" else ("one_launch" if P.info()["series_kernel"] == 5 else "auto")
+                row[key] = round(ms * 1e3 / (TERMS_PER_STEP * 100), 2)
+            out["N%d" % N] = row
+            P.close()
+            del H
         torch.cuda.empty_cache()
         return out
     except Exception as e:      # the headline line must survive a failure of the side measurement

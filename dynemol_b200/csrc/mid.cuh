@@ -306,12 +306,21 @@ __device__ __noinline__ bool mid_owner(MidShared* sh, double* val, double* own, 
         if (t > 0) {
             const int s = lane & 7;
             const double* sv = val + W + s;
+            const bool is_max = (s & 3) < 2;
             double a = 0.0;
-            for (int o = lane >> 3; o < P.n_own; o += 4) { const double v = sv[(size_t)o * 8]; a = ((s & 3) < 2) ? fmax(a, v) : a + v; }
+            int o = lane >> 3;
+            for (; o + 28 < P.n_own; o += 32) {                  // eight loads in flight, combined in the fixed order
+                double v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = sv[(size_t)(o + 4 * i) * 8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a = is_max ? fmax(a, v[i]) : a + v[i];
+            }
+            for (; o < P.n_own; o += 4) { const double v = sv[(size_t)o * 8]; a = is_max ? fmax(a, v) : a + v; }
 #pragma unroll
             for (int off = 8; off < 32; off <<= 1) {
-                const double o = __shfl_xor_sync(0xffffffffu, a, off);
-                a = ((s & 3) < 2) ? fmax(a, o) : a + o;
+                const double ov = __shfl_xor_sync(0xffffffffu, a, off);
+                a = is_max ? fmax(a, ov) : a + ov;
             }
             double fin[4];
 #pragma unroll
