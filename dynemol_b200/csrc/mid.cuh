@@ -50,7 +50,11 @@ constexpr int MID_STAGE_BYTES = 32768;      // R x TC x 8 B with R*TC = 4096 for
 constexpr int MID_MAX_ST      = 5;
 constexpr int MID_U_BYTES     = 32768;      // union region: bra partials of the row groups / ket tree reduction
 constexpr int MID_MAX_E       = 64;         // indices an owner may hold
-constexpr int MID_CW          = 21;         // owner: words a thread has in flight per collect pass
+#ifndef DYB_MID_CWP
+#define DYB_MID_CWP 17
+#endif
+constexpr int MID_CWP         = DYB_MID_CWP; // owner: partial words per thread ((Gr + Gc) * E * 4 <= 256 * 17) ...
+constexpr int MID_CWS         = 5;          // ... and scalar words per thread (8 * owners <= 256 * 5), all in flight at once
 constexpr int MID_XT          = 224;        // consumer threads: warps 1..7 (warp 0 publishes the scalars meanwhile)
 constexpr int MID_XU          = 19;         // consumer: words per thread ((R + Cn) * 4 <= 224 * 19)
 constexpr int MID_SCU         = 10;         // decision: owners per thread (16 * 10 >= owner CTAs)
@@ -149,6 +153,36 @@ __device__ __forceinline__ double ll_value(const ulonglong2& r) {
         }                                                                                                         \
     } while (0)
 
+// The same for two word lists polled together (the owner's partials and the owners' scalars: different epochs and addressing).
+#define DYB_LL_POLL2(NA, pa, EPA, ADDRA, OUTA, NB, pb, EPB, ADDRB, OUTB, AFTER_REQ)                               \
+    do {                                                                                                          \
+        for (long long it_ = 0;; ++it_) {                                                                         \
+            unsigned long long ax_[NA], ay_[NA], bx_[NB], by_[NB];                                                \
+            _Pragma("unroll") for (int i = 0; i < (NA); ++i) {                                                    \
+                ax_[i] = 0ull; ay_[i] = 0ull;                                                                     \
+                if (((pa) >> i) & 1u) ll_load2(ADDRA(i), ax_[i], ay_[i]);                                         \
+            }                                                                                                     \
+            _Pragma("unroll") for (int i = 0; i < (NB); ++i) {                                                    \
+                bx_[i] = 0ull; by_[i] = 0ull;                                                                     \
+                if (((pb) >> i) & 1u) ll_load2(ADDRB(i), bx_[i], by_[i]);                                         \
+            }                                                                                                     \
+            if (it_ == 0) { AFTER_REQ; }                                                                          \
+            _Pragma("unroll") for (int i = 0; i < (NA); ++i)                                                      \
+                if ((((pa) >> i) & 1u) && (unsigned)(ax_[i] >> 32) == (EPA) && (unsigned)(ay_[i] >> 32) == (EPA)) { \
+                    OUTA(i, __longlong_as_double((long long)((ax_[i] & 0xffffffffull) | (ay_[i] << 32))));        \
+                    (pa) &= ~(1u << i);                                                                           \
+                }                                                                                                 \
+            _Pragma("unroll") for (int i = 0; i < (NB); ++i)                                                      \
+                if ((((pb) >> i) & 1u) && (unsigned)(bx_[i] >> 32) == (EPB) && (unsigned)(by_[i] >> 32) == (EPB)) { \
+                    OUTB(i, __longlong_as_double((long long)((bx_[i] & 0xffffffffull) | (by_[i] << 32))));        \
+                    (pb) &= ~(1u << i);                                                                           \
+                }                                                                                                 \
+            if (!((pa) | (pb))) { ll_rounds = (int)it_ + 1; break; }                                              \
+            if (it_ > MID_SPIN_LIMIT) __trap();                                                                   \
+            if (DYB_LL_SLEEP > 0) __nanosleep(DYB_LL_SLEEP);                                                      \
+        }                                                                                                         \
+    } while (0)
+
 // 32 FMAs of half a column: rows of m = M0, M0 + 1 against the 4 reals of x_ket (-> acc) and of x_bra (-> p, p1)
 template <int M0>
 __device__ __forceinline__ void mid_fma_half(double (&acc)[MID_MPT][2][NQ], const double (&xb)[MID_MPT][2][NQ],
@@ -234,7 +268,7 @@ __device__ __noinline__ void mid_decide(MidShared* sh, int td, bool allow_chain)
 //   1. ONE polling batch collects the partials of the owned indices (term t) AND the 8 scalars of every owner (term t-1)
 //      into val[] (shared memory).  Word w < W: w = k * E4 + e * 4 + q -- source k (0 .. Gc-1: ket partial of block column k;
 //      Gc .. Gc+Gr-1: bra partial of block row k - Gc), owned index e, real q; word W + o * 8 + s: scalar s of owner o.
-//      Thread tid takes the words tid + 256 j, MID_CW per pass, all in flight at once.
+//      Thread tid takes the words tid + 256 j (<= 17 partial words, <= 5 scalar words), all in flight at once.
 //   2. warp 0 takes the decision on term t-1 (decide_particle = the code of the two other paths, Taylor.f:194-207 / :102-105;
 //      fixed combination order, identical in every CTA) while warps 1..7 add up the partials (fixed order);
 //   3. warps 1..7 apply the recurrence and the series sum to the owner state (own: cur, prev, sum, start [2 sides][E][NQ] +
@@ -247,122 +281,116 @@ __device__ __noinline__ bool mid_owner(MidShared* sh, double* val, double* own, 
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int Gr = P.Gr, Gc = P.Gc, Cnp = P.Cnp, N = P.N, E = P.E, G = Gr * Gc;
     const int E4 = E * NQ, W = (Gc + Gr) * E4, o0 = blockIdx.x * E;
-    const int Wt = W + (t > 0 ? P.n_own * 8 : 0);
     const int par = t & 1;
     const unsigned ep = P.epoch0 + t + 1;
     {
-        // tables built once per launch: wtab[slot][thread] = 32-bit offset of the thread's word, or (tab16) its
-        // (k << 8 | e * 4 + q) with kt[k] = offset of source k, rt[side][e * 4 + q] = offset of the word inside a source
+        // offsets of the thread's partial words, from the tables built once per launch: wtab32[slot][thread] = offset (ket:
+        // >= 0 from pkb, bra: ~offset from pbb), or (tab16) wtab16 = (k << 8 | e * 4 + q) with kt[k] = offset of source k,
+        // rt[side][e * 4 + q] = offset of the word inside a source
         const int* kt = reinterpret_cast<const int*>(own + 4 * 2 * E * NQ + 2 * E * 2);
-        const int* rt = kt + (Gc + Gr);
-        const unsigned short* wtab16 = reinterpret_cast<const unsigned short*>(reinterpret_cast<const char*>(kt) + ((Gc + Gr + 2 * E4) * 4 + 127) / 128 * 128) + tid;
-        const int* wtab32 = kt + tid;
-        const bool tab16 = P.tab16 != 0;
+        int off[MID_CWP];
+        unsigned pp = 0, ps = 0;                                 // pending partial / scalar words
+        if (P.tab16) {
+            const int* rt = kt + (Gc + Gr);
+            const unsigned short* wtab16 = reinterpret_cast<const unsigned short*>(reinterpret_cast<const char*>(kt) + ((Gc + Gr + 2 * E4) * 4 + 127) / 128 * 128) + tid;
+#pragma unroll
+            for (int j = 0; j < MID_CWP; ++j) {
+                off[j] = 0;
+                if (j * MID_THREADS < W) {                       // uniform
+                    const int kr = wtab16[j * MID_THREADS];
+                    if (kr != MID_NO_WORD) {
+                        pp |= 1u << j;
+                        const int k = kr >> 8, isb = k >= Gc;
+                        const int o = kt[k] + rt[(isb ? E4 : 0) + (kr & 255)];
+                        off[j] = isb ? ~o : o;
+                    }
+                }
+            }
+        } else {
+            const int* wtab32 = kt + tid;
+#pragma unroll
+            for (int j = 0; j < MID_CWP; ++j) {
+                off[j] = MID_NO_WORD32;
+                if (j * MID_THREADS < W) off[j] = wtab32[j * MID_THREADS];          // uniform guard; the table is padded to whole slots
+                if (off[j] != MID_NO_WORD32) pp |= 1u << j;
+            }
+        }
+        const int nS = t > 0 ? P.n_own * 8 : 0;                  // scalars of term t-1: word o * 8 + s
+#pragma unroll
+        for (int j = 0; j < MID_CWS; ++j) if (j * MID_THREADS + tid < nS) ps |= 1u << j;
         const ulonglong2* pkb = P.pk + (size_t)par * Gr * Gc * R * NQ;
         const ulonglong2* pbb = P.pb + (size_t)par * Gc * Gr * Cnp * NQ;
-        const ulonglong2* scb = P.sc + (size_t)((t + 3) & 3) * G * 8 - W;      // scalars of term t-1, indexed by the word number
-        for (int w0 = 0; w0 < Wt; w0 += MID_THREADS * MID_CW) {
-            int ll_rounds = 0;
-            int off[MID_CW];                                     // word offset from pkb (ket, >= 0) or pbb (bra, stored as ~offset) or scb
-            unsigned pend = 0, scm = 0;                          // scm: the word is a scalar of term t-1
-#pragma unroll
-            for (int j = 0; j < MID_CW; ++j) {
-                const int wb = w0 + j * MID_THREADS, wj = wb + tid;
-                off[j] = 0;
-                if (wb >= Wt) continue;                          // uniform: no thread has a word in this slot
-                if (wj < W) {
-                    if (tab16) {
-                        const int kr = wtab16[wb];
-                        if (kr != MID_NO_WORD) {
-                            pend |= 1u << j;
-                            const int k = kr >> 8, isb = k >= Gc;
-                            const int o = kt[k] + rt[(isb ? E4 : 0) + (kr & 255)];
-                            off[j] = isb ? ~o : o;
-                        }
-                    } else {
-                        off[j] = wtab32[wb];
-                        if (off[j] != MID_NO_WORD32) pend |= 1u << j;
-                    }
-                } else if (wj < Wt) { pend |= 1u << j; scm |= 1u << j; off[j] = wj; }
-            }
-#define DYB_CO_ADDR(j) (((scm >> (j)) & 1u) ? scb + off[j] : (off[j] >= 0 ? pkb + off[j] : pbb + ~off[j]))
-#define DYB_CO_EP(j) (ep - ((scm >> (j)) & 1u))
-#define DYB_CO_OUT(j, v) val[w0 + (j) * MID_THREADS + tid] = (v)
-            DYB_MSTAMP(9);
-            DYB_LL_POLL(MID_CW, pend, DYB_CO_EP, DYB_CO_ADDR, DYB_CO_OUT, if (w0 == 0) __syncthreads());
-            DYB_MROUNDS(8, ll_rounds);
+        const ulonglong2* scb = P.sc + (size_t)((t + 3) & 3) * G * 8 + tid;
+        int ll_rounds = 0;
+#define DYB_CO_ADDR(j) (off[j] >= 0 ? pkb + off[j] : pbb + ~off[j])
+#define DYB_CO_OUT(j, v) val[(j) * MID_THREADS + tid] = (v)
+#define DYB_CS_ADDR(j) (scb + (j) * MID_THREADS)
+#define DYB_CS_OUT(j, v) val[W + (j) * MID_THREADS + tid] = (v)
+        DYB_MSTAMP(9);
+        // (the ket rows staged in U are overwritten by val: every thread must have published them -> barrier behind the request)
+        DYB_LL_POLL2(MID_CWP, pp, ep, DYB_CO_ADDR, DYB_CO_OUT, MID_CWS, ps, ep - 1u, DYB_CS_ADDR, DYB_CS_OUT, __syncthreads());
+        DYB_MROUNDS(8, ll_rounds);
 #undef DYB_CO_ADDR
-#undef DYB_CO_EP
 #undef DYB_CO_OUT
-        }
+#undef DYB_CS_ADDR
+#undef DYB_CS_OUT
     }
     DYB_MSTAMP(7);
     __syncthreads();
+    DYB_MSTAMP(10);
 
     // ---- warp 0: decision on term t-1; warps 1..7: sums of the partials.  task = (side, e, q), MID_XT threads, <= 3 each;
     // the two reals of a complex value sit in neighbouring lanes
-    double hx[3] = {0.0, 0.0, 0.0};
+    double* ocur = own;
+    double* oprv = ocur + 2 * E * NQ;
+    double* osum = oprv + 2 * E * NQ;
+    double* opsi = osum + 2 * E * NQ;
+    double* omag = opsi + 2 * E * NQ;
+    double s_old[3] = {0.0, 0.0, 0.0}, s_cur[3] = {0.0, 0.0, 0.0}, s_prv[3] = {0.0, 0.0, 0.0}, s_sum[3] = {0.0, 0.0, 0.0},
+           s_psi[3] = {0.0, 0.0, 0.0}, s_mag[3] = {0.0, 0.0, 0.0};
+    unsigned flags = 0;                                           // per round u: bit 2u = update computed, bit 2u+1 = sub-step begins
     if (w == 0) {
         if (t > 0) {
             const int s = lane & 7;
             const double* sv = val + W + s;
+            // lane (part, s) combines the owners part, part + 4, ... (<= 40 of them): all loads first (a loop of dependent
+            // load -> combine steps cost 50 cycles per owner: 2200 cycles per term), then eight interleaved accumulators -- a
+            // fixed order, the same in every CTA.  The maxima are non-negative and never NaN (the owners start from 0.0 and
+            // fmax drops NaNs), so their order is the order of their bit patterns: integer max, no DSETP / select chains.
             const bool is_max = (s & 3) < 2;
-            double a = 0.0;
-            int o = lane >> 3;
-            for (; o + 28 < P.n_own; o += 32) {                  // eight loads in flight, combined in the fixed order
-                double v[8];
+            const int part = lane >> 3, n_own = P.n_own;
+            double v[4 * MID_SCU];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = sv[(size_t)(o + 4 * i) * 8];
+            for (int i = 0; i < 4 * MID_SCU; ++i) v[i] = (part + 4 * i < n_own) ? sv[(size_t)(part + 4 * i) * 8] : 0.0;
+            double a;
+            if (is_max) {
+                long long m[8] = {0ll, 0ll, 0ll, 0ll, 0ll, 0ll, 0ll, 0ll};
 #pragma unroll
-                for (int i = 0; i < 8; ++i) a = is_max ? fmax(a, v[i]) : a + v[i];
+                for (int i = 0; i < 4 * MID_SCU; ++i) m[i & 7] = max(m[i & 7], __double_as_longlong(v[i]));
+                a = __longlong_as_double(max(max(max(m[0], m[1]), max(m[2], m[3])), max(max(m[4], m[5]), max(m[6], m[7]))));
+            } else {                                             // a dependent FP64 add costs ~40 cycles: eight chains of five
+                double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                for (int i = 0; i < 4 * MID_SCU; ++i) acc[i & 7] += v[i];
+                a = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
             }
-            for (; o < P.n_own; o += 4) { const double v = sv[(size_t)o * 8]; a = is_max ? fmax(a, v) : a + v; }
 #pragma unroll
-            for (int off = 8; off < 32; off <<= 1) {
+            for (int off = 8; off < 32; off <<= 1) {             // the four parts of a slot (lanes s, s + 8, s + 16, s + 24)
                 const double ov = __shfl_xor_sync(0xffffffffu, a, off);
-                a = is_max ? fmax(a, ov) : a + ov;
+                a = is_max ? __longlong_as_double(max(__double_as_longlong(a), __double_as_longlong(ov))) : a + ov;
             }
             double fin[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) fin[q] = __shfl_sync(0xffffffffu, a, 4 * (lane & 1) + q);
+            DYB_MSTAMP(12);
             // stop_chain as of the previous term: the same in every CTA
             if (lane < 2) decide_particle(sh->sctrl.part[lane], sh->spass[(t - 1) & 1].part[lane], fin, !sh->stop_chain);
             __syncwarp();
             if (lane == 0 && ((sh->sctrl.part[0].latched && !sh->sctrl.part[0].ok) || (sh->sctrl.part[1].latched && !sh->sctrl.part[1].ok))) sh->stop_chain = 1;
         }
     } else {
-#pragma unroll
-        for (int u = 0; u < 3; ++u) {
-            const int task = (tid - 32) + u * MID_XT;
-            const int side = task >= E4 ? 1 : 0;
-            const int eq = task - side * E4;
-            if (task < 2 * E4 && o0 + (eq >> 2) < N) {
-                const double* vp = val + (side ? Gc * E4 : 0) + eq;
-                const int np = side ? Gr : Gc;
-                double a = 0.0;
-                int kk = 0;
-                for (; kk + 8 <= np; kk += 8) {                  // eight loads in flight, added in the fixed order
-                    double v[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = vp[(size_t)(kk + i) * E4];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) a += v[i];
-                }
-                for (; kk < np; ++kk) a += vp[(size_t)kk * E4];
-                hx[u] = a;
-            }
-        }
-    }
-    __syncthreads();
-    if (sh->sctrl.part[0].latched && sh->sctrl.part[1].latched) return true;
-    DYB_MSTAMP(3);
-
-    double* ocur = own;
-    double* oprv = ocur + 2 * E * NQ;
-    double* osum = oprv + 2 * E * NQ;
-    double* opsi = osum + 2 * E * NQ;
-    double* omag = opsi + 2 * E * NQ;
-    if (w > 0) {
+        // the recurrence and the series sum are computed here, beside the decision, and committed after it: a particle the
+        // decision latches keeps its state (the update of term t is dropped)
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
             const int task = (tid - 32) + u * MID_XT;
@@ -370,21 +398,33 @@ __device__ __noinline__ bool mid_owner(MidShared* sh, double* val, double* own, 
             const int side = task >= E4 ? 1 : 0;
             const int eq = task - side * E4, e = eq >> 2, q = eq & 3;
             const bool ok = task < 2 * E4 && o0 + e < N;
-            const double ho = __shfl_xor_sync(0xffffffffu, hx[u], 1);           // the other real of the complex value
+            double hx = 0.0;
+            if (ok) {
+                const double* vp = val + (side ? Gc * E4 : 0) + eq;
+                const int np = side ? Gr : Gc;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;  // four interleaved accumulators: a fixed order, short dependent chains
+                int kk = 0;
+                for (; kk + 4 <= np; kk += 4) {
+                    a0 += vp[(size_t)kk * E4]; a1 += vp[(size_t)(kk + 1) * E4]; a2 += vp[(size_t)(kk + 2) * E4]; a3 += vp[(size_t)(kk + 3) * E4];
+                }
+                if (kk < np) a0 += vp[(size_t)kk * E4];
+                if (kk + 1 < np) a1 += vp[(size_t)(kk + 1) * E4];
+                if (kk + 2 < np) a2 += vp[(size_t)(kk + 2) * E4];
+                hx = (a0 + a1) + (a2 + a3);
+            }
+            const double ho = __shfl_xor_sync(0xffffffffu, hx, 1);              // the other real of the complex value
             const int p = q >> 1, cmp = q & 1;
-            const Cx hc = cmp ? Cx{ho, hx[u]} : Cx{hx[u], ho};
+            const Cx hc = cmp ? Cx{ho, hx} : Cx{hx, ho};
             const size_t o = ((size_t)side * E + e) * NQ + 2 * p;
-            double xnew = 0.0, n_cur = 0.0, n_prv = 0.0, n_sum = 0.0, n_psi = 0.0, mag = 0.0;
-            bool upd = false, beg = false;
             if (ok) {
                 const PartPass& pa = sh->spass[par].part[p];
                 double2 cur = *reinterpret_cast<const double2*>(ocur + o);
-                xnew = cmp ? cur.y : cur.x;
-                if (pa.active && !sh->sctrl.part[p].latched) {
+                s_old[u] = cmp ? cur.y : cur.x;
+                if (pa.active && !sh->sctrl.part[p].latched) {   // latched as of term t-2; the decision on t-1 is re-checked at the commit
                     double2 sum = *reinterpret_cast<const double2*>(osum + o);
                     if (pa.begin) {                              // next steady sub-step: adopt the previous sum (Taylor.f:105,:83-86);
-                        beg = true;                              // hx was computed from it (x of the chain term)
-                        n_psi = cmp ? sum.y : sum.x;
+                        flags |= 2u << (2 * u);                  // hx was computed from it (x of the chain term)
+                        s_psi[u] = cmp ? sum.y : sum.x;
                         cur = sum;
                         const Cx s0 = cmul({pa.s_re, pa.s_im}, {sum.x, sum.y});
                         sum = make_double2(s0.re, s0.im);
@@ -402,23 +442,37 @@ __device__ __noinline__ bool mid_owner(MidShared* sh, double* val, double* own, 
                     if (pa.scale_term) tt = cmul({pa.c_re, pa.c_im}, y);
                     const double nw_re = sum.x + tt.re, nw_im = sum.y + tt.im;
                     const double dx = nw_re - sum.x, dy = nw_im - sum.y;
-                    mag = dx * dx + dy * dy;                     // |new - old|^2 (isConverged, Taylor.f:290-303); root after the max
-                    upd = true;
-                    n_prv = cmp ? cur.y : cur.x;
+                    s_mag[u] = dx * dx + dy * dy;                // |new - old|^2 (isConverged, Taylor.f:290-303); root after the max
+                    flags |= 1u << (2 * u);
+                    s_prv[u] = cmp ? cur.y : cur.x;
                     // what the next product multiplies: the new vector, or (speculatively) the sum the next sub-step starts from
-                    n_cur = pa.chain ? (cmp ? nw_im : nw_re) : (cmp ? y.im : y.re);
-                    n_sum = cmp ? nw_im : nw_re;
-                    xnew = n_cur;
+                    s_cur[u] = pa.chain ? (cmp ? nw_im : nw_re) : (cmp ? y.im : y.re);
+                    s_sum[u] = cmp ? nw_im : nw_re;
                 }
             }
-            __syncwarp();                                        // both lanes of a complex value have read the old state
-            if (ok) {
+        }
+    }
+    DYB_MSTAMP(11);
+    __syncthreads();
+    if (sh->sctrl.part[0].latched && sh->sctrl.part[1].latched) return true;
+    DYB_MSTAMP(3);
+
+    if (w > 0) {
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int task = (tid - 32) + u * MID_XT;
+            const int side = task >= E4 ? 1 : 0;
+            const int eq = task - side * E4, e = eq >> 2, q = eq & 3;
+            if (task < 2 * E4 && o0 + e < N) {
+                const int p = q >> 1, cmp = q & 1;
+                const size_t o = ((size_t)side * E + e) * NQ + 2 * p;
+                const bool upd = ((flags >> (2 * u)) & 1u) && !sh->sctrl.part[p].latched;
                 if (upd) {
-                    oprv[o + cmp] = n_prv; ocur[o + cmp] = n_cur; osum[o + cmp] = n_sum;
-                    if (beg) opsi[o + cmp] = n_psi;
+                    oprv[o + cmp] = s_prv[u]; ocur[o + cmp] = s_cur[u]; osum[o + cmp] = s_sum[u];
+                    if ((flags >> (2 * u)) & 2u) opsi[o + cmp] = s_psi[u];
                 }
-                if (cmp == 0) omag[((size_t)side * E + e) * 2 + p] = mag;
-                ll_store(P.xx + (((size_t)((t + 1) & 1) * 2 + side) * N + (o0 + e)) * NQ + q, xnew, ep);
+                if (cmp == 0) omag[((size_t)side * E + e) * 2 + p] = upd ? s_mag[u] : 0.0;
+                ll_store(P.xx + (((size_t)((t + 1) & 1) * 2 + side) * N + (o0 + e)) * NQ + q, upd ? s_cur[u] : s_old[u], ep);
             }
         }
         asm volatile("bar.arrive 1, 256;" ::: "memory");         // the owner state of term t is complete (warp 0 waits for it)
@@ -465,15 +519,15 @@ __device__ __noinline__ void mid_consume(MidShared* sh, double* sx, int t) {
     const unsigned ep = P.epoch0 + t + 1;
     const ulonglong2* xk_src = P.xx + (((size_t)((t + 1) & 1) * 2 + 0) * N + col0) * NQ;
     const ulonglong2* xb_src = P.xx + (((size_t)((t + 1) & 1) * 2 + 1) * N + row0) * NQ - (size_t)Cnp * NQ;    // indexed by wi
-    const int nwk = min(Cnp, max(0, N - col0)) * NQ, nwb = min(R, max(0, N - row0)) * NQ;
+    const int nwk = min(Cnp, max(0, N - col0)) * NQ, nwb = min(R, max(0, N - row0)) * NQ, c4 = Cnp * NQ;
     unsigned pend = 0;
     int ll_rounds = 0; (void)ll_rounds;
 #pragma unroll
     for (int u = 0; u < MID_XU; ++u) {
         const int wi = ct + u * MID_XT;
-        if (wi < Cnp * NQ ? wi < nwk : wi - Cnp * NQ < nwb) pend |= 1u << u;
+        if (wi < nwk || (unsigned)(wi - c4) < (unsigned)nwb) pend |= 1u << u;
     }
-#define DYB_X_ADDR(u) (((ct + (u) * MID_XT) < Cnp * NQ ? xk_src : xb_src) + (ct + (u) * MID_XT))
+#define DYB_X_ADDR(u) (((ct + (u) * MID_XT) < c4 ? xk_src : xb_src) + (ct + (u) * MID_XT))
 #define DYB_X_EP(u) ep
 #define DYB_X_OUT(u, v) sx[ct + (u) * MID_XT] = (v)
     DYB_LL_POLL(MID_XU, pend, DYB_X_EP, DYB_X_ADDR, DYB_X_OUT, (void)0);

@@ -482,7 +482,8 @@ static MidPlan make_mid_plan(int N, int sm_count, size_t smem_optin, size_t stat
     // an owner's indices span at most two block columns (E <= Cnp); the 8 scalar slots of <= 16 * MID_SCU owners; a consumer's
     // R + Cnp entries in MID_XU words per thread; the bra partials of the WR row groups in the union region
     m.fits = m.ST >= 2 && G <= sm_count && m.E <= MID_MAX_E && m.E <= m.Cnp && m.n_own <= 16 * MID_SCU
-             && (m.Cnp + m.R) * NQ <= MID_XT * MID_XU && 2 * m.E * NQ <= 3 * MID_XT && (size_t)m.WR * m.Cnp * NQ * 8 <= (size_t)MID_U_BYTES;
+             && (m.Cnp + m.R) * NQ <= MID_XT * MID_XU && 2 * m.E * NQ <= 3 * MID_XT
+             && (m.Gr + m.Gc) * m.E * NQ <= MID_THREADS * MID_CWP && m.n_own * 8 <= MID_THREADS * MID_CWS && (size_t)m.WR * m.Cnp * NQ * 8 <= (size_t)MID_U_BYTES;
     return m;
 }
 static bool mid_ok(const dyb_ctx* c, bool refgpu) {
@@ -529,11 +530,11 @@ static int run_series_mid(dyb_ctx* c, const std::vector<PassParams>& passes) {
             CK(cudaMemcpy(h.data(), d_mprof, n_mprof * 8, cudaMemcpyDeviceToHost));
             const char* name[8] = {"product", "reduce+publish", "collect", "decision+sums", "update+scalars (thread 0 = scalar warp)", "-", "consume-wait", "loop-gap"};
             const int order[9] = {0, 1, 2, 7, 3, 4, 5, 6, 0};      // stamp order inside a term; the last one is stamp 0 of the next term
-            double mean[8] = {0}, mx[8] = {0}, rounds = 0, setup = 0;
+            double mean[8] = {0}, mx[8] = {0}, rounds = 0, setup = 0, wait_all = 0, dec = 0, red = 0;
             const int nt = std::min(n, MAX_SERIES_TERMS);
             for (int t = 1; t + 1 < nt; ++t) for (int b = 0; b < mgrid; ++b) {
                 const long long* q = &h[((size_t)t * mgrid + b) * 16];
-                rounds += double(q[8]); setup += double(q[9] - q[2]);
+                rounds += double(q[8]); setup += double(q[9] - q[2]); wait_all += double(q[10] - q[7]); dec += double(q[11] - q[10]); red += double(q[12] - q[10]);
                 for (int i = 0; i < 8; ++i) {
                     const long long nx = (i < 7) ? q[order[i + 1]] : h[((size_t)(t + 1) * mgrid + b) * 16];
                     const double d = double(nx - q[order[i]]);
@@ -543,7 +544,7 @@ static int run_series_mid(dyb_ctx* c, const std::vector<PassParams>& passes) {
             fprintf(stderr, "mid_prof N=%d grid=%dx%d Cnp=%d NT=%d ST=%d terms=%d:", c->N, P.Gr, P.Gc, P.Cnp, P.NT, P.ST, n);
             for (int i = 0; i < 8; ++i) fprintf(stderr, "  %s mean %.0f max %.0f cyc;", name[i], mean[i] / ((double)std::max(1, nt - 2) * mgrid), mx[i]);
             const double dn = (double)std::max(1, nt - 2) * mgrid;
-            fprintf(stderr, "  [thread 0 collect: %.2f polling rounds, %.0f cycles from the publication to the first request]\n", rounds / dn, setup / dn);
+            fprintf(stderr, "  [thread 0 collect: %.2f polling rounds, %.0f cycles from the publication to the first request; then %.0f waiting for the other threads' words, %.0f for the decision (warp 0), of which %.0f for the combination of the scalars]\n", rounds / dn, setup / dn, wait_all / dn, dec / dn, red / dn);
         }
     }
 #endif

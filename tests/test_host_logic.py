@@ -108,7 +108,7 @@ def test_mid_plan_blocking():
         assert Gr * R >= N > (Gr - 1) * R and Gc * Cnp >= N > (Gc - 1) * Cnp
         assert E * Gr * Gc >= N and n_own == -(-N // E) and n_own <= Gr * Gc and (n_own - 1) * E < N and E <= min(64, Cnp)
         assert p["collect_words"] == (Gr + Gc) * E * 4
-        assert (Cnp + R) * 4 <= 19 * 224 and 2 * E * 4 <= 3 * 224
+        assert (Cnp + R) * 4 <= 19 * 224 and 2 * E * 4 <= 3 * 224 and p["collect_words"] <= 17 * 256 and 8 * n_own <= 5 * 256
         slots = -(-p["collect_words"] // 256)
         table = (-(-(Gr + Gc + 8 * E) * 4 // 128) * 128 + slots * 512) if p["table16"] else slots * 1024
         union = max(32768, -(-(p["collect_words"] + 8 * n_own) * 8 // 128) * 128)
