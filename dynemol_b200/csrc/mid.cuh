@@ -206,7 +206,8 @@ struct MidShared {
                                             // load from parameter space: 4000 cycles before the first request of a term)
     Ctrl       sctrl;
     PassParams spass[2];
-    double     wsc[4][8];
+    double     wsc[4][8];                   // mid_decide (last term): per-warp combinations of the scalars
+    double     wsc8[8][8];                  // mid_owner: the same, all eight warps
     int        stop_chain;                  // a particle failed a chained sub-step: the other one stops at its next sub-step
 };                                          // boundary so that both resume together
 
@@ -339,6 +340,36 @@ __device__ __noinline__ bool mid_owner(MidShared* sh, double* val, double* own, 
     __syncthreads();
     DYB_MSTAMP(10);
 
+    // ---- decision on term t-1, first half (all warps): thread (warp w, lane) = (slot s = lane & 7, sub = lane >> 3) combines the
+    // owners w * 4 + sub + 32 i of its slot, the four lanes of a slot are joined by two shuffles: 8 values per warp.  Done by
+    // one warp alone this was 1700 cycles per term.  The maxima are non-negative and never NaN (the owners start from 0.0 and
+    // fmax drops NaNs), so their order is the order of their bit patterns: integer max.  Fixed order, the same in every CTA.
+    if (t > 0) {
+        const int s = lane & 7, ob = w * 4 + (lane >> 3), n_own = P.n_own;
+        const bool is_max = (s & 3) < 2;
+        const double* sv = val + W + s;
+        double v[MID_CWS];
+#pragma unroll
+        for (int i = 0; i < MID_CWS; ++i) v[i] = (ob + 32 * i < n_own) ? sv[(size_t)(ob + 32 * i) * 8] : 0.0;
+        double a;
+        if (is_max) {
+            long long m = __double_as_longlong(v[0]);
+#pragma unroll
+            for (int i = 1; i < MID_CWS; ++i) m = max(m, __double_as_longlong(v[i]));
+            a = __longlong_as_double(m);
+        } else {
+            a = ((v[0] + v[1]) + (v[2] + v[3])) + v[4];
+            static_assert(MID_CWS == 5, "combination order of the scalars");
+        }
+#pragma unroll
+        for (int off = 8; off < 32; off <<= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, a, off);
+            a = is_max ? __longlong_as_double(max(__double_as_longlong(a), __double_as_longlong(ov))) : a + ov;
+        }
+        if (lane < 8) sh->wsc8[w][lane] = a;
+    }
+    __syncthreads();
+
     // ---- warp 0: decision on term t-1; warps 1..7: sums of the partials.  task = (side, e, q), MID_XT threads, <= 3 each;
     // the two reals of a complex value sit in neighbouring lanes
     double* ocur = own;
@@ -351,34 +382,19 @@ __device__ __noinline__ bool mid_owner(MidShared* sh, double* val, double* own, 
     unsigned flags = 0;                                           // per round u: bit 2u = update computed, bit 2u+1 = sub-step begins
     if (w == 0) {
         if (t > 0) {
+            // second half: lane s < 8 joins the eight warps' values of slot s (a fixed tree)
             const int s = lane & 7;
-            const double* sv = val + W + s;
-            // lane (part, s) combines the owners part, part + 4, ... (<= 40 of them): all loads first (a loop of dependent
-            // load -> combine steps cost 50 cycles per owner: 2200 cycles per term), then eight interleaved accumulators -- a
-            // fixed order, the same in every CTA.  The maxima are non-negative and never NaN (the owners start from 0.0 and
-            // fmax drops NaNs), so their order is the order of their bit patterns: integer max, no DSETP / select chains.
             const bool is_max = (s & 3) < 2;
-            const int part = lane >> 3, n_own = P.n_own;
-            double v[4 * MID_SCU];
+            double c[8];
 #pragma unroll
-            for (int i = 0; i < 4 * MID_SCU; ++i) v[i] = (part + 4 * i < n_own) ? sv[(size_t)(part + 4 * i) * 8] : 0.0;
+            for (int ww = 0; ww < 8; ++ww) c[ww] = sh->wsc8[ww][s];
             double a;
             if (is_max) {
-                long long m[8] = {0ll, 0ll, 0ll, 0ll, 0ll, 0ll, 0ll, 0ll};
+                long long m = __double_as_longlong(c[0]);
 #pragma unroll
-                for (int i = 0; i < 4 * MID_SCU; ++i) m[i & 7] = max(m[i & 7], __double_as_longlong(v[i]));
-                a = __longlong_as_double(max(max(max(m[0], m[1]), max(m[2], m[3])), max(max(m[4], m[5]), max(m[6], m[7]))));
-            } else {                                             // a dependent FP64 add costs ~40 cycles: eight chains of five
-                double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-                for (int i = 0; i < 4 * MID_SCU; ++i) acc[i & 7] += v[i];
-                a = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
-            }
-#pragma unroll
-            for (int off = 8; off < 32; off <<= 1) {             // the four parts of a slot (lanes s, s + 8, s + 16, s + 24)
-                const double ov = __shfl_xor_sync(0xffffffffu, a, off);
-                a = is_max ? __longlong_as_double(max(__double_as_longlong(a), __double_as_longlong(ov))) : a + ov;
-            }
+                for (int ww = 1; ww < 8; ++ww) m = max(m, __double_as_longlong(c[ww]));
+                a = __longlong_as_double(m);
+            } else a = ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
             double fin[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) fin[q] = __shfl_sync(0xffffffffu, a, 4 * (lane & 1) + q);
