@@ -122,6 +122,44 @@ def test_mid_plan_blocking():
         assert api.mid_plan(N)["fits"] == 0       # the two-launch path (>= 80 % of the HBM peak there) takes over
 
 
+def test_mid_exchange_needs_no_barrier():
+    """The barrier-free exchange of csrc/mid.cuh reuses its tagged buffers after two terms (scalars: four).  That is safe
+    because of who waits for whom -- checked here on the blocking dyb_mid_plan returns, for the sizes the GPU tests run:
+      * CTA (i, j) overwrites its partials of term t when it publishes term t+2, i.e. after it consumed x(t+2) on rows(i) and
+        cols(j); the owners of those indices are exactly the readers of its partials of term t, and they published x(t+2)
+        after reading them;
+      * an owner overwrites x(t+1) when it publishes x(t+3), i.e. after it collected the partials of term t+2 of the block row
+        and block column of its indices -- exactly the CTAs that read its x(t+1);
+      * the product of a term depends on the products of EVERY CTA two terms earlier (two hops of "the producers of the
+        entries I consume"), which is what makes a four-deep ring enough for the scalars every CTA reads."""
+    from dynemol_b200 import api
+    for N in [257, 300, 700, 2048, 2304, 3000, 4096, 5000, 6144]:
+        p = api.mid_plan(N)
+        R, Gr, Gc, Cnp, E = p["block_rows"], p["grid_rows"], p["grid_cols"], p["block_cols"], p["owned"]
+        G = Gr * Gc
+        rows = lambda i: range(i * R, min((i + 1) * R, N))
+        cols = lambda j: range(j * Cnp, min((j + 1) * Cnp, N))
+        producers = {}
+        for b in range(G):
+            i, j = divmod(b, Gc)
+            readers = {g // E for g in rows(i)} | {g // E for g in cols(j)}       # owners that collect b's ket / bra partials
+            awaited = {g // E for g in rows(i)} | {g // E for g in cols(j)}       # owners of the entries b consumes next
+            assert readers <= awaited
+            d = set()                                                             # CTAs whose partials feed those entries
+            for bc in {g // Cnp for g in rows(i)}:
+                d |= {r * Gc + bc for r in range(Gr)}
+            for br in {g // R for g in cols(j)}:
+                d |= {br * Gc + c for c in range(Gc)}
+            producers[b] = d
+        for o in range(p["owners"]):
+            idx = range(o * E, min((o + 1) * E, N))
+            x_readers = {(g // R) * Gc + c for g in idx for c in range(Gc)} | {r * Gc + g // Cnp for g in idx for r in range(Gr)}
+            collected = {b for b in range(G) if o in ({g // E for g in rows(b // Gc)} | {g // E for g in cols(b % Gc)})}
+            assert x_readers <= collected, (N, o)
+        for b in range(G):
+            assert set().union(*[producers[d] for d in producers[b]]) == set(range(G)), (N, b)
+
+
 @pytest.mark.parametrize("name", ["prop_N64_dt5e-6", "prop_N128_dt2e-5", "cheb_N64_dt5e-4", "cheb_N128_dt5e-5"])
 def test_steady_schedule_matches_oracle_traces(golden_dir, name):
     """dyb_steady_schedule (the sub-step schedule the library predicts when it chains the steady loop of Taylor.f:81-126
