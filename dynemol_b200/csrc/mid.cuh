@@ -820,6 +820,7 @@ mid_series_kernel_t(const __grid_constant__ CUtensorMap tmap, const __grid_const
             // ket partial of block row bi from block column bj -> pk[par][bi][bj][.]: rows through shared memory (the region of
             // U a wc == 0 warp writes is its own or already consumed), then 512 contiguous bytes per store instruction
             if (wc == 0) {
+                __syncwarp();                                    // the lanes of this warp have read their part of the tree slot it overwrites
                 double2* st = reinterpret_cast<double2*>(U) + (size_t)(wr * MID_SUB + 2 * lane) * 2;
 #pragma unroll
                 for (int m = 0; m < MID_MPT; ++m)
