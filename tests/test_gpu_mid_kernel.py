@@ -3,9 +3,10 @@
 It must be interchangeable with the two-launch path (DYB_SERIES_PER_TERM), which the other GPU tests pin against the oracle
 at every size: identical decision traces (tau schedule, exit index of every Convergence call of Taylor.f:132-219, sub-step
 count of Taylor.f:81-126), wavepackets within 1e-10 of the oracle (the north_star tolerance) and within 1e-12 of the
-two-launch path (only the summation order differs).  Sizes: its natural range (2304, 3000, 4096, 5000: different grid
-shapes, ragged last block row / column) and small operators forced through it (300, 700: few block rows, many block
-columns, whole tiles out of bounds)."""
+two-launch path (only the summation order differs).  Sizes: its natural range (1828 = the first size (4 orbitals per atom) past the resident
+kernel, 2304, 3000, 4096, 5000, 6144 = the last one, with the 16-bit collect table: different grid shapes, ragged last block
+row / column) and small operators forced through it (300, 700: few block rows, many block columns, whole tiles out of
+bounds)."""
 import os
 
 import numpy as np
@@ -64,13 +65,13 @@ def hprime(oracle_mod, w):
 
 
 def test_mid_is_the_default_between_resident_and_streaming(api):
-    for N, want in ((900, SERIES_RESIDENT), (2304, SERIES_MID), (4096, SERIES_MID), (16384, SERIES_PER_TERM)):
+    for N, want in ((900, SERIES_RESIDENT), (1825, SERIES_MID), (2304, SERIES_MID), (4096, SERIES_MID), (6144, SERIES_MID), (6400, SERIES_PER_TERM), (16384, SERIES_PER_TERM)):
         P = api.Propagator(N)
         assert P.info()["series_kernel"] == want, (N, P.info())
         P.close()
 
 
-@pytest.mark.parametrize("N,dt", [(300, 1e-5), (700, 2e-6), (2304, 5e-7), (3000, 4e-7), (4096, 2e-7), (5000, 2e-7)])
+@pytest.mark.parametrize("N,dt", [(300, 1e-5), (700, 2e-6), (1828, 6e-7), (2304, 5e-7), (3000, 4e-7), (4096, 2e-7), (5000, 2e-7), (6144, 1.5e-7)])
 def test_mid_taylor_matches_per_term_and_oracle(api, oracle_mod, N, dt):
     w = syn.make_workload(N)
     Hp = hprime(oracle_mod, w)
