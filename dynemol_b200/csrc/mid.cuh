@@ -27,7 +27,8 @@
 //     itself until both tags carry the epoch of the term -- no fence, no flag, no counter.  Epochs grow across launches,
 //     buffers are double-buffered by term parity (scalars: four deep); the data dependencies of the recurrence guarantee
 //     that a slot is never overwritten before its readers are done (a CTA needs x(t+2) from exactly the owners that read
-//     its partials of term t);
+//     its partials of term t; checked on the host for the plans in use: tests/test_host_logic.py,
+//     test_mid_exchange_needs_no_barrier);
 //   * the decision on term t-1 (decide_particle, the code of the other two paths) is taken by every CTA, identically,
 //     from the owners' scalars before term t is applied: a latched particle skips the update.
 //
