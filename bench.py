@@ -281,9 +281,41 @@ def small_operator(args, N=900):
             out[key]["passes_per_step"] = P.info()["passes_last"]; out[key]["launches_per_step"] = (P.launch_count() - l0) // 5
         P.close()
         torch.cuda.empty_cache()
+        out["config2_100_steps"] = config2_trajectory(N)
         return out
     except Exception as e:      # the headline line must survive a failure of the side measurement
         return {"error": repr(e)[:200]}
+
+
+def config2_trajectory(N=900, n_steps=100, dt=2e-5):
+    """BASELINE config 2 (QM region of the heptazine-in-water example, N ~ 900), the propagator's share of it: 100
+    nuclear steps with MOVING nuclei through the PRIMARY symbol propagationelhl2_gpucaller_, called by reference like
+    ElHl_Chebyshev_GPU.f:269-272 -- every step uploads that frame's host-built S and h, forms H' = S^-1 h, propagates electron
+    and hole (Taylor.f semantics, carried-over tau of ElHl_Chebyshev.f:182-184) and returns H', the packets and AO_bra.
+    The frames (S, h of 10 perturbed geometries, reused cyclically) are built before the clock starts: assembling them is
+    the reference host's job (overlap_D.f, hamiltonians.f)."""
+    from dynemol_b200 import api, synthetic as syn
+    try:
+        pos, species = syn.lattice(N // 4, 1234 + N)
+        frames = [syn.workload_at(syn.perturb_positions(pos, s), species) for s in range(10)]
+        _, bra, ket = syn.packets(frames[0][0], N)
+        tau_max = dt / H_BAR
+        o = api.legacy_propagationelhl(frames[0][0], frames[0][1], bra, ket, 0.0, dt, tau_max, copy_inputs=False)   # step 1, untimed
+        save, bra, ket, t, terms = o["save_tau"], o["PSI_bra"], o["PSI_ket"], dt, 0
+        t0 = time.perf_counter()
+        for step in range(1, n_steps + 1):
+            S, h = frames[step % len(frames)]
+            o = api.legacy_propagationelhl(S, h, bra, ket, t, t + dt, np.minimum(tau_max, 1.15 * save), copy_inputs=False)
+            save, bra, ket = o["save_tau"], o["PSI_bra"], o["PSI_ket"]
+            terms += api.legacy_passes_last(); t += dt
+        el = time.perf_counter() - t0
+        return {"basis": N, "nuclear_steps": n_steps, "dt_ps": dt, "s_total": round(el, 3), "ms_per_nuclear_step": round(el / n_steps * 1e3, 3),
+                "terms": int(terms), "terms_per_s": round(terms / el, 1), "norm_el": float(abs(np.vdot(bra[:, 0], ket[:, 0]))),
+                "call": "propagationelhl2_gpucaller_ (host S, h of the frame -> H', packets, AO_bra), Taylor.f semantics"}
+    except Exception as e:
+        return {"error": repr(e)[:200]}
+    finally:
+        api.gpu_finalize()
 
 
 def mid_operator(args, sizes=(2048, 4096)):
