@@ -231,7 +231,7 @@ __device__ __noinline__ void mid_decide(MidShared* sh, int td, bool allow_chain)
 #pragma unroll
         for (int i = 0; i < MID_SCU; ++i) if (ob + 16 * i < P.n_own) need |= 1u << i;
         double sv[MID_SCU];
-        int ll_rounds = 0; (void)ll_rounds;
+        [[maybe_unused]] int ll_rounds = 0;
 #define DYB_SC_ADDR(i) (src + (size_t)(ob + 16 * (i)) * 8)
 #define DYB_SC_OUT(i, v) sv[i] = (v)
         unsigned pend = need;
@@ -323,7 +323,7 @@ __device__ __noinline__ bool mid_owner(MidShared* sh, double* val, double* own, 
         const ulonglong2* pkb = P.pk + (size_t)par * Gr * Gc * R * NQ;
         const ulonglong2* pbb = P.pb + (size_t)par * Gc * Gr * Cnp * NQ;
         const ulonglong2* scb = P.sc + (size_t)((t + 3) & 3) * G * 8 + tid;
-        int ll_rounds = 0;
+        [[maybe_unused]] int ll_rounds = 0;
 #define DYB_CO_ADDR(j) (off[j] >= 0 ? pkb + off[j] : pbb + ~off[j])
 #define DYB_CO_OUT(j, v) val[(j) * MID_THREADS + tid] = (v)
 #define DYB_CS_ADDR(j) (scb + (j) * MID_THREADS)
@@ -538,7 +538,7 @@ __device__ __noinline__ void mid_consume(MidShared* sh, double* sx, int t) {
     const ulonglong2* xb_src = P.xx + (((size_t)((t + 1) & 1) * 2 + 1) * N + row0) * NQ - (size_t)Cnp * NQ;    // indexed by wi
     const int nwk = min(Cnp, max(0, N - col0)) * NQ, nwb = min(R, max(0, N - row0)) * NQ, c4 = Cnp * NQ;
     unsigned pend = 0;
-    int ll_rounds = 0; (void)ll_rounds;
+    [[maybe_unused]] int ll_rounds = 0;
 #pragma unroll
     for (int u = 0; u < MID_XU; ++u) {
         const int wi = ct + u * MID_XT;
@@ -572,7 +572,7 @@ mid_series_kernel_t(const __grid_constant__ CUtensorMap tmap, const __grid_const
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int wr = w / WC, wc = w % WC;
     const int Gr = P.Gr, Gc = P.Gc, Cnp = P.Cnp, NT = P.NT, ST = P.ST, N = P.N, E = P.E;
-    const int G = Gr * Gc;
+    [[maybe_unused]] const int G = Gr * Gc;                    // (phase stamps of the diagnostic build)
     const int bi = blockIdx.x / Gc, bj = blockIdx.x % Gc;
     const int row0 = bi * R, col0 = bj * Cnp;
     const int o0 = blockIdx.x * E;                             // first owned index
